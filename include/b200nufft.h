@@ -1,0 +1,195 @@
+/*
+ * b200nufft.h -- C ABI of libb200nufft.so, the sm_100a NUFFT engine behind
+ * mri-nufft's `get_operator("b200")` backend.
+ *
+ * This is the drop-in boundary.  Every entry point names the
+ * reference interface it replaces (paths relative to the mri-nufft tree).
+ * In the reference the arithmetic of this path is delegated to the un-vendored
+ * third-party library finufft (pyproject.toml:23) through `finufft.Plan`; the
+ * functions below are what a binding for that path has to call instead.
+ *
+ * Conventions
+ *   - plain C, opaque plan handle, caller owns every data buffer, the plan owns
+ *     its workspace (oversampled grids, sorted points, cuFFT plan);
+ *   - all data pointers are DEVICE pointers unless the name ends in `_host`;
+ *   - `stream` is a `cudaStream_t` passed as `void*` (NULL = legacy default
+ *     stream); every call is asynchronous on that stream;
+ *   - complex data is interleaved float (re, im) = complex64, C-order, the last
+ *     image axis is the fastest one; `samples[:, i]` pairs with image axis `i`
+ *     (src/mrinufft/operators/interfaces/finufft.py:55-62);
+ *   - return value 0 = success, negative = error (see B200_E*), message through
+ *     b200_last_error() (thread local);
+ *   - a plan is bound to one device and is not thread-safe.
+ *
+ * Math (docs/explanations/nufft.rst:253-309, verified against
+ * src/mrinufft/operators/interfaces/nudft_numpy.py:12-55):
+ *   type 2:  c_j = scale * sum_n  f_n * exp(isign * i * x_j . (n - N/2))   (isign = -1)
+ *   type 1:  f_n = scale * sum_j  c_j * exp(isign * i * x_j . (n - N/2))   (isign = +1)
+ *   x_j in radians, folded periodically into [-pi, pi).
+ */
+#ifndef B200NUFFT_H
+#define B200NUFFT_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct b200_plan b200_plan;
+
+#define B200_OK          0
+#define B200_EINVAL     -1   /* bad argument                                  */
+#define B200_ECUDA      -2   /* CUDA runtime error                            */
+#define B200_ECUFFT     -3   /* cuFFT error                                   */
+#define B200_ENOMEM     -4   /* allocation failed                             */
+#define B200_ESTATE     -5   /* call order (e.g. execute before setpts)       */
+
+/* plan flags */
+#define B200_SPREAD_ONLY 1   /* finufft `spreadinterponly=1` (finufft.py:225-232) */
+
+/* Version of this ABI (bumped on any signature change). */
+int b200_abi_version(void);
+
+/* Thread-local message of the last failing call on this thread. */
+const char* b200_last_error(void);
+
+/*
+ * Create a plan: replaces `finufft.Plan(2, shape, n_trans, eps, dtype=..., **kw)`
+ * (src/mrinufft/operators/interfaces/finufft.py:43-50) and the second type-1
+ * plan of the cufinufft interface (cufinufft.py:83-92).  One plan serves both
+ * transform types and both signs.
+ *   dim          2 or 3 (1 is accepted)
+ *   n_modes      image shape, n_modes[i] pairs with samples[:, i]
+ *   n_trans_max  largest number of transforms batched in one execute call
+ *   eps          requested tolerance (kernel width w = ceil(log10(10/eps)) at sigma = 2)
+ *   upsampfac    sigma; 0 -> 2.0
+ *   flags        B200_SPREAD_ONLY: no FFT, no deapodisation, grid size = n_modes
+ *   device       CUDA device ordinal
+ */
+int b200_plan_create(b200_plan** plan, int dim, const int64_t* n_modes,
+                     int n_trans_max, double eps, double upsampfac,
+                     int flags, int device);
+
+int b200_plan_destroy(b200_plan* plan);
+
+/*
+ * Plan geometry, for the host side and the bit-exact sort test.
+ * info[0..2]  = fine grid size per axis (nf)
+ * info[3]     = kernel width w
+ * info[4..6]  = bin size per axis (cells)
+ * info[7..9]  = number of bins per axis
+ * info[10]    = polynomial degree of the kernel evaluator
+ * info[11]    = number of points M (0 before setpts)
+ * info[12]    = workspace bytes held by the plan
+ */
+int b200_plan_info(const b200_plan* plan, int64_t info[16]);
+
+/* Kernel shape parameters: out[0] = beta, out[1] = c (= 4 / w^2), out[2] = sigma. */
+int b200_plan_kernel_params(const b200_plan* plan, double out[4]);
+
+/*
+ * Set the non-uniform points: replaces `Plan.setpts(x, y, z)`
+ * (finufft.py:55-62, called from MRIfinufft.__init__ L130-135 and
+ * update_samples L150-181).  This is kernel K1: fold to fine-grid units,
+ * footprint origin + in-cell offset, bin key, stable sort by bin key.
+ *   xyz   device pointer, float32, shape (M, dim), C-order, radians
+ */
+int b200_plan_setpts(b200_plan* plan, int64_t M, const float* xyz, void* stream);
+
+/*
+ * Read back the sort for the bit-exact test (no reference counterpart: finufft
+ * keeps its sort private).  Any pointer may be NULL.
+ *   origin  int32 (dim, M)  footprint origin cell per axis, UNSORTED point order
+ *   x1      float32 (dim, M) offset of the first tap, UNSORTED point order
+ *   key     int32 (M)       bin key, UNSORTED point order
+ *   perm    int32 (M)       perm[s] = index of the point at sorted position s
+ */
+int b200_plan_get_sort(b200_plan* plan, int32_t* origin, float* x1,
+                       int32_t* key, int32_t* perm, void* stream);
+
+/*
+ * Type 2 (uniform -> non-uniform) for T <= n_trans_max transforms: replaces
+ * `RawFinufftPlan.op` / `Plan.execute` (finufft.py:71-76) together with the
+ * per-chunk sensitivity-map multiply and the `ret *= inv_norm_factor` pass of
+ * `FourierOperatorSimple._op_sense/_op_calibless/op`
+ * (src/mrinufft/operators/base.py:949-1013).
+ *   img    complex64; (T, *n_modes) if smaps == NULL, else (*n_modes) (one image)
+ *   smaps  NULL or complex64 (T, *n_modes); coil images img*smaps[t] are formed on the fly
+ *   ksp    complex64 (T, M) output, natural (unsorted) point order
+ *   isign  -1 (forward model) or +1 (the `grad` plan of finufft.py:183-193)
+ *   scale  multiplied into the output (1/norm_factor)
+ *   conj_smaps  use conj(smaps) (toggle_grad_traj, base.py:1234-1238)
+ */
+int b200_type2(b200_plan* plan, const void* img, const void* smaps, void* ksp,
+               int T, int isign, float scale, int conj_smaps, void* stream);
+
+/*
+ * Type 1 (non-uniform -> uniform) for T transforms: replaces
+ * `RawFinufftPlan.adj_op` / `Plan.execute_adjoint` (finufft.py:64-69), the density
+ * multiply of `_adj_op` (base.py:1068-1073), the conj-smaps multiply + coil
+ * accumulation of `_adj_op_sense` (base.py:1037-1052; CUDA twin
+ * `_coil_combine_kernel`, src/mrinufft/operators/gpu_utils.py:12-24) and the final
+ * `ret *= inv_norm_factor`.
+ *   ksp      complex64 (T, M)
+ *   density  NULL or float32 (M): multiplies ksp before spreading
+ *   smaps    NULL or complex64 (T, *n_modes): img = sum_t conj(smaps[t]) * f_t
+ *   img      complex64 (*n_modes) if smaps else (T, *n_modes)
+ *   accumulate  0: overwrite img, 1: img += result (next coil chunk)
+ *   conj_smaps  0: multiply by conj(smaps) (adjoint), 1: by smaps (toggled plan)
+ */
+int b200_type1(b200_plan* plan, const void* ksp, const float* density,
+               const void* smaps, void* img, int T, int accumulate, int isign,
+               float scale, int conj_smaps, void* stream);
+
+/*
+ * Fused data-consistency gradient chunk  A^H (A x - y): replaces one iteration of the
+ * loop in `_grad_sense/_grad_calibless` (base.py:1092-1139; GPU twin
+ * cufinufft.py:992-1178).  The k-space residual never leaves the device and is never
+ * materialised in caller memory.
+ *   img   as in b200_type2, obs complex64 (T, M), grad as `img` of b200_type1
+ *   The residual is r = scale * A x - obs, then (density .* r), then grad (+)= scale * A^H r.
+ */
+int b200_data_consistency(b200_plan* plan, const void* img, const void* smaps,
+                          const void* obs, const float* density, void* grad,
+                          int T, int accumulate, float scale, void* stream);
+
+/*
+ * Spread / interpolate only (plans created with B200_SPREAD_ONLY): replaces the
+ * `spreadinterponly=1` plan used by `MRIfinufft.pipe` (finufft.py:225-239).
+ *   grid  complex64 (T, *n_modes)
+ */
+int b200_spread(b200_plan* plan, const void* ksp, void* grid, int T, void* stream);
+int b200_interp(b200_plan* plan, const void* grid, void* ksp, int T, void* stream);
+
+/*
+ * One fixed-point iteration of Pipe's density compensation,  d <- d / |G G^H d|
+ * (finufft.py:233-239), device resident.  `d` float32 (M), updated in place.
+ */
+int b200_pipe_iteration(b200_plan* plan, float* d, void* stream);
+
+/*
+ * Counters for bench.py: number of kernels this library launched and number of cuFFT
+ * executions since the last reset (process wide).
+ */
+int b200_launch_count(int64_t* kernels, int64_t* ffts, int reset);
+
+/*
+ * Select kernel variants at run time (A/B measurements; 0 = default for every key).
+ *   key 0: spread method   (0 auto, 1 global-atomic point driven, 2 tiled)
+ *   key 1: interp method   (0 auto, 1 point driven, 2 tiled)
+ */
+int b200_plan_set_option(b200_plan* plan, int key, int64_t value);
+
+/*
+ * Timing hooks for the roofline report: the plan records CUDA events around its
+ * dominant kernels.  out[0] = spread ms, out[1] = interp ms, out[2] = fft ms,
+ * out[3] = pad/crop ms of the LAST execute call (synchronises the stream).
+ */
+int b200_plan_last_timings(b200_plan* plan, float out[8]);
+int b200_plan_enable_timing(b200_plan* plan, int on);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200NUFFT_H */

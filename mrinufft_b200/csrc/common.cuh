@@ -1,0 +1,151 @@
+// common.cuh -- plan structure, error plumbing and launch helpers shared by every
+// translation unit of libb200nufft.so (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <cufft.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+
+#include "../../include/b200nufft.h"
+
+#define B200_MAX_W 16
+#define B200_MAX_DEG 15
+#define B200_NUM_SMS 148
+
+// ---------------------------------------------------------------- error plumbing
+void b200_set_error(const char* fmt, ...);
+
+#define CUDA_TRY(expr)                                                              \
+  do {                                                                              \
+    cudaError_t _e = (expr);                                                        \
+    if (_e != cudaSuccess) {                                                        \
+      b200_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr,                  \
+                     cudaGetErrorString(_e));                                       \
+      return B200_ECUDA;                                                            \
+    }                                                                               \
+  } while (0)
+
+#define CUFFT_TRY(expr)                                                             \
+  do {                                                                              \
+    cufftResult _r = (expr);                                                        \
+    if (_r != CUFFT_SUCCESS) {                                                      \
+      b200_set_error("%s:%d: %s -> cufft error %d", __FILE__, __LINE__, #expr,      \
+                     (int)_r);                                                      \
+      return B200_ECUFFT;                                                           \
+    }                                                                               \
+  } while (0)
+
+#define B200_TRY(expr)                                                              \
+  do {                                                                              \
+    int _s = (expr);                                                                \
+    if (_s != B200_OK) return _s;                                                   \
+  } while (0)
+
+// process-wide launch counters (bench.py's `gpu_launches`)
+extern long long g_kernel_launches;
+extern long long g_fft_execs;
+#define COUNT_LAUNCH() (++g_kernel_launches)
+
+#define CHECK_LAUNCH()                                                              \
+  do {                                                                              \
+    COUNT_LAUNCH();                                                                 \
+    cudaError_t _e = cudaGetLastError();                                            \
+    if (_e != cudaSuccess) {                                                        \
+      b200_set_error("%s:%d: kernel launch -> %s", __FILE__, __LINE__,              \
+                     cudaGetErrorString(_e));                                       \
+      return B200_ECUDA;                                                            \
+    }                                                                               \
+  } while (0)
+
+// ---------------------------------------------------------------- geometry passed to kernels by value
+struct Geom {
+  int dim;
+  int w;           // kernel width
+  int deg;         // polynomial degree
+  int nf[3];       // fine grid size per axis (axis dim-1 fastest); unused axes = 1
+  int N[3];        // image size per axis
+  int bin[3];      // bin size per axis (cells)
+  int nbins[3];    // bins per axis
+  long long nftot; // prod nf
+  long long Ntot;  // prod N
+};
+
+// ---------------------------------------------------------------- the plan
+struct b200_plan {
+  Geom g;
+  int flags = 0;
+  int device = 0;
+  int ntrans_max = 1;
+  double eps = 1e-6, sigma = 2.0, beta = 0, cpar = 0;
+
+  // device tables
+  float* d_poly = nullptr;                       // [(deg+1)][w]: coefficient k of tap i at k*w+i
+  float* d_deapod[3] = {nullptr, nullptr, nullptr};  // N[a] floats: (-1)^k / phihat(k)
+
+  // points
+  long long M = 0, Mcap = 0;
+  int32_t* d_org_u[3] = {nullptr, nullptr, nullptr};  // footprint origin, unsorted
+  float* d_x1_u[3] = {nullptr, nullptr, nullptr};     // first-tap offset, unsorted
+  int32_t* d_key_u = nullptr;                         // bin key, unsorted
+  int32_t* d_key_s = nullptr;                         // bin key, sorted
+  int32_t* d_perm = nullptr;                          // sorted position -> point index
+  int32_t* d_iota = nullptr;
+  int32_t* d_org_s[3] = {nullptr, nullptr, nullptr};  // sorted copies
+  float* d_x1_s[3] = {nullptr, nullptr, nullptr};
+  int32_t* d_bin_start = nullptr;                     // nbins_tot + 1
+  long long nbins_tot = 0;
+  void* d_sort_tmp = nullptr;
+  size_t sort_tmp_bytes = 0;
+
+  // workspace
+  float2* d_fw = nullptr;       // [ntrans_max][nftot] oversampled grids
+  float2* d_ksp_tmp = nullptr;  // [ntrans_max][M] residual of data_consistency
+  float* d_pipe_tmp = nullptr;
+  size_t ws_bytes = 0;
+
+  cufftHandle fft = 0, fft1 = 0;  // batched plan and single-grid plan (tails)
+  bool fft_ok = false, fft1_ok = false;
+  int fft_batch = 0;
+  bool pts_set = false;
+
+  // state of the tiled spread/interp kernels (spread_tiled.cu)
+  void* tiled = nullptr;
+
+  // options
+  int spread_method = 0, interp_method = 0;
+
+  // timing
+  bool timing = false;
+  cudaEvent_t ev[10] = {};
+  bool ev_ok = false;
+  int ev_used[5] = {0, 0, 0, 0, 0};
+};
+
+// ---------------------------------------------------------------- host-side kernel math (es_kernel_host.cpp)
+struct KernelTables {
+  int w, deg;
+  double beta;
+  std::vector<float> poly;  // (deg+1) * w
+};
+void es_kernel_params(double eps, double sigma, int* w, double* beta);
+int next235even(int n);
+void es_fit_polynomial(int w, double beta, double eps, KernelTables* out);
+void es_deapod_vector(int n, int nf, int w, double beta, std::vector<float>* out);
+
+// ---------------------------------------------------------------- kernels (implemented in the .cu files)
+int k1_setpts(b200_plan* p, const float* xyz, cudaStream_t st);
+int k2_spread(b200_plan* p, const float2* ksp, const float* density, float2* fw, int T,
+              cudaStream_t st);
+int k3_interp(b200_plan* p, const float2* fw, float2* ksp, int T, float scale,
+              const float2* obs, const float* density, cudaStream_t st);
+int k4a_pad(b200_plan* p, const float2* img, const float2* smaps, float2* fw, int T,
+            int conj_smaps, cudaStream_t st);
+int k4b_crop(b200_plan* p, const float2* fw, const float2* smaps, float2* img, int T,
+             int accumulate, float scale, int conj_smaps, cudaStream_t st);
+int k_pipe_update(b200_plan* p, float* d, const float2* ksp, cudaStream_t st);
+int k_real_to_cpx(b200_plan* p, const float* d, float2* out, cudaStream_t st);
+
+static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }

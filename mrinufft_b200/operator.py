@@ -1,0 +1,646 @@
+"""``get_operator("b200")``: the B200-native NUFFT backend for mri-nufft.
+
+Host-side mirror of the reference's backend interface for the type-2 ``op`` / type-1 ``adj_op`` hot
+path.  It is modelled on
+
+* ``MRIfinufft``      (``src/mrinufft/operators/interfaces/finufft.py:83-245``) -- the parity target:
+  same constructor signature and defaults, ``samples`` kept as a host array in radians, ``pipe``;
+* ``FourierOperatorSimple`` (``src/mrinufft/operators/base.py:880-1139``) -- shapes, squeeze rules,
+  SENSE / calibrationless semantics, ``norm_factor`` on both op and adjoint, density before the
+  adjoint only;
+* ``MRICufiNUFFT``    (``src/mrinufft/operators/interfaces/cufinufft.py:140-1331``) -- device-resident
+  smaps / density, ``n_trans`` must divide ``n_batchs * n_coils``.
+
+All arithmetic runs in ``libb200nufft.so`` (hand-written sm_100a CUDA + cuFFT) through the C ABI in
+``include/b200nufft.h``.  torch is used for device memory and streams only.  There is no CPU
+fallback: without the library or without a GPU the backend registers as unavailable and the
+constructor raises.
+"""
+
+from __future__ import annotations
+
+import logging
+import warnings
+from contextlib import contextmanager
+
+import numpy as np
+import torch
+
+from mrinufft._utils import proper_trajectory
+from mrinufft.operators.base import FourierOperatorBase
+
+from . import _lib
+from ._arrays import describe, from_device, module_name, to_device
+
+log = logging.getLogger("mrinufft_b200")
+
+_IGNORED_FINUFFT_KWARGS = {
+    "nthreads", "debug", "spread_debug", "showwarn", "spread_sort", "spread_kerevalmeth",
+    "spread_kerpad", "chkbnds", "fftw", "modeord", "spread_thread", "maxbatchsize",
+    "spread_nthr_atomic", "spread_max_sp_size", "allow_eps_too_small", "gpu_method", "gpu_sort",
+    "gpu_kerevalmeth", "gpu_maxsubprobsize", "gpu_maxbatchsize", "gpu_spreadinterponly",
+}
+
+
+def _gpu_available() -> bool:
+    try:
+        return bool(_lib.library_built() and torch.cuda.is_available())
+    except Exception:  # pragma: no cover
+        return False
+
+
+class RawB200Plan:
+    """Device plan: one trajectory, type 1 and type 2, both signs (role of ``RawFinufftPlan``,
+    ``finufft.py:23-80``, and ``RawCufinufftPlan``, ``cufinufft.py:51-137``)."""
+
+    def __init__(self, samples, shape, n_trans=1, eps=1e-6, upsampfac=2.0, spread_only=False,
+                 device=None):
+        self.device = torch.device("cuda", torch.cuda.current_device() if device is None else device)
+        self.shape = tuple(int(s) for s in shape)
+        self.ndim = len(self.shape)
+        self.eps = float(eps)
+        self.n_trans = int(n_trans)
+        self.spread_only = bool(spread_only)
+        self.isign_flip = False  # toggle_grad_traj: e^{-i} <-> e^{+i}
+        self.plan = _lib.Plan(self.shape, n_trans_max=self.n_trans, eps=eps, upsampfac=upsampfac,
+                              spread_only=spread_only, device=self.device.index)
+        self.n_samples = 0
+        self._pts = None
+        self._set_pts(samples)
+
+    @property
+    def stream(self):
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def _set_pts(self, samples):
+        """``Plan.setpts`` (finufft.py:55-62): fold + bin-sort on the device."""
+        pts = to_device(samples, self.device, torch.float32)
+        if pts.ndim != 2 or pts.shape[1] != self.ndim:
+            raise ValueError(f"samples should have shape (M, {self.ndim}), got {tuple(pts.shape)}")
+        self._pts = pts
+        self.n_samples = int(pts.shape[0])
+        self.plan.setpts(pts.data_ptr(), self.n_samples, self.stream)
+
+    def toggle_grad_traj(self):
+        """Role of ``RawFinufftPlan.toggle_grad_traj`` (finufft.py:78-80): the same plan serves the
+        opposite sign, no second plan is needed."""
+        self.isign_flip = not self.isign_flip
+
+    def sort_indices(self):
+        """(origin (d,M) int32, x1 (d,M) f32, key (M,) int32, perm (M,) int32) as numpy."""
+        M, d = self.n_samples, self.ndim
+        origin = torch.empty((d, M), dtype=torch.int32, device=self.device)
+        x1 = torch.empty((d, M), dtype=torch.float32, device=self.device)
+        key = torch.empty(M, dtype=torch.int32, device=self.device)
+        perm = torch.empty(M, dtype=torch.int32, device=self.device)
+        self.plan.get_sort(origin.data_ptr(), x1.data_ptr(), key.data_ptr(), perm.data_ptr(),
+                           self.stream)
+        torch.cuda.synchronize(self.device)
+        return origin.cpu().numpy(), x1.cpu().numpy(), key.cpu().numpy(), perm.cpu().numpy()
+
+    # raw transforms on device tensors -------------------------------------------------------
+    def type2(self, img, smaps, ksp, scale=1.0, conj_smaps=False):
+        T = ksp.shape[0]
+        isign = +1 if self.isign_flip else -1
+        self.plan.type2(img.data_ptr(), 0 if smaps is None else smaps.data_ptr(), ksp.data_ptr(),
+                        T, isign, scale, int(conj_smaps), self.stream)
+
+    def type1(self, ksp, density, smaps, img, accumulate=False, scale=1.0, conj_smaps=False):
+        T = ksp.shape[0]
+        isign = -1 if self.isign_flip else +1
+        self.plan.type1(ksp.data_ptr(), 0 if density is None else density.data_ptr(),
+                        0 if smaps is None else smaps.data_ptr(), img.data_ptr(), T,
+                        int(accumulate), isign, scale, int(conj_smaps), self.stream)
+
+
+class MRIB200NUFFT(FourierOperatorBase):
+    """MRI non-Cartesian Fourier operator running on one NVIDIA B200.
+
+    Parameters
+    ----------
+    samples: array
+        Sample locations ``(M, d)`` (or ``(Nc, Ns, d)``), in [-0.5, 0.5) or radians
+        (rescaled like ``proper_trajectory(..., "pi")``).
+    shape: tuple
+        Image shape (2D or 3D).
+    density: bool, array, str, dict or callable
+        Density compensation (same grammar as ``FourierOperatorBase.compute_density``).
+    n_coils, n_batchs, n_trans, smaps, squeeze_dims:
+        As for ``MRIfinufft`` (finufft.py:116-127).  ``n_trans`` is the number of transforms
+        batched in one device call and must divide ``n_batchs * n_coils``; with the default
+        ``n_trans=1`` the batch size is chosen automatically from the free device memory
+        (results do not depend on it).
+    eps: float
+        Requested tolerance (default 1e-6 -> kernel width 7 at upsampfac 2).
+    upsampfac: float
+        Oversampling factor sigma (default 2.0).
+    gpu_device_id: int, optional
+        CUDA device ordinal (default: current torch device).
+    """
+
+    backend = "b200"
+    available = _gpu_available()
+    autograd_available = True
+
+    def __init__(
+        self,
+        samples,
+        shape,
+        density=False,
+        n_coils=1,
+        n_batchs=1,
+        n_trans=1,
+        smaps=None,
+        squeeze_dims=True,
+        eps=1e-6,
+        upsampfac=2.0,
+        gpu_device_id=None,
+        coil_chunk=None,
+        spreadinterponly=0,
+        isign=None,
+        **kwargs,
+    ):
+        if not _lib.library_built():
+            raise RuntimeError(
+                f"'{self.backend}' backend is not available: {_lib.LIB_PATH} has not been built."
+            )
+        if not torch.cuda.is_available():
+            raise RuntimeError(f"'{self.backend}' backend is not available: no CUDA device.")
+        unknown = set(kwargs) - _IGNORED_FINUFFT_KWARGS
+        if unknown:
+            raise TypeError(f"MRIB200NUFFT got unexpected keyword arguments {sorted(unknown)}")
+        super().__init__()
+        self._smaps_d = None
+        self._density_d = None
+        self.shape = shape
+        if len(self.shape) not in (1, 2, 3):
+            raise ValueError("b200 backend supports 1D, 2D and 3D transforms")
+        dev_index = torch.cuda.current_device() if gpu_device_id is None else int(gpu_device_id)
+        self.device = torch.device("cuda", dev_index)
+
+        samples = self._normalize_samples(samples)
+        self._samples = samples
+        self.dtype = np.float32
+        if n_coils < 1:
+            raise ValueError("n_coils should be ≥ 1")
+        self.n_coils = n_coils
+        self.n_batchs = n_batchs
+        self.n_trans = int(n_trans)
+        if (self.n_batchs * self.n_coils) % self.n_trans != 0:
+            raise ValueError("n_batchs * n_coils should be a multiple of n_transf")
+        self.squeeze_dims = squeeze_dims
+        self.eps = float(eps)
+        self.upsampfac = float(upsampfac) if upsampfac else 2.0
+        self._spread_only = bool(spreadinterponly)
+        self._user_isign_flip = isign is not None and int(isign) > 0
+        self._conj_smaps = False
+        self._coil_chunk = coil_chunk
+
+        self.raw_op = RawB200Plan(
+            samples, self.shape, n_trans=self._pick_chunk(), eps=self.eps, upsampfac=self.upsampfac,
+            spread_only=self._spread_only, device=dev_index,
+        )
+        if self._user_isign_flip:
+            self.raw_op.toggle_grad_traj()
+        # Density compensation, then multi coil setup (order of base.py:942-945).
+        self.compute_density(density)
+        self.compute_smaps(smaps)
+
+    # ------------------------------------------------------------------ helpers
+    def _normalize_samples(self, samples):
+        if module_name(samples) == "torch":
+            samples = samples.detach().cpu().numpy()
+        elif not isinstance(samples, np.ndarray):
+            if hasattr(samples, "get"):
+                samples = samples.get()
+            samples = np.asarray(samples)
+        samples = proper_trajectory(samples, normalize="pi")
+        if samples.dtype != np.float32:
+            if samples.dtype == np.float64:
+                self.log.info("b200 backend computes in float32/complex64: casting float64 samples.")
+            samples = samples.astype(np.float32)
+        return np.ascontiguousarray(samples.reshape(-1, len(self.shape)))
+
+    def _pick_chunk(self) -> int:
+        """Number of transforms batched per device call (workspace = chunk oversampled grids)."""
+        total = self.n_batchs * self.n_coils
+        if self._coil_chunk:
+            return max(1, min(int(self._coil_chunk), self.n_coils))
+        if self.n_trans > 1:
+            return self.n_trans
+        if self._spread_only:
+            return min(self.n_coils, 8)
+        sigma = self.upsampfac
+        grid_bytes = 8 * float(np.prod([max(2 * 8, int(np.ceil(sigma * s))) for s in self.shape]))
+        free, _ = torch.cuda.mem_get_info(self.device)
+        # grids + cuFFT work area (same order) may take at most ~45% of the free memory
+        cap = int(0.45 * free / (2.0 * grid_bytes))
+        cap = max(1, min(cap, 32))
+        # largest chunk <= cap that divides n_coils (keeps chunks inside one batch volume)
+        best = 1
+        for c in range(1, min(cap, self.n_coils) + 1):
+            if self.n_coils % c == 0:
+                best = c
+        _ = total
+        return best
+
+    @property
+    def stream(self):
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def _in(self, arr, dtype=torch.complex64):
+        kind, dev = describe(arr)
+        t = to_device(arr, self.device, dtype)
+        return t, kind, dev
+
+    def _out(self, t, kind, dev):
+        return from_device(t, kind, dev)
+
+    # ------------------------------------------------------------------ smaps / density / samples
+    @property
+    def smaps(self):
+        """Sensitivity maps (as given; a complex64 copy lives on the device)."""
+        return self._smaps
+
+    @smaps.setter
+    def smaps(self, new_smaps):
+        # accepts numpy, torch (cpu/cuda) and cupy arrays; the base setter only takes numpy
+        # (base.py:759-760) -- same override as cufinufft.py:277-315.
+        if new_smaps is None:
+            self._smaps = None
+            self._smaps_d = None
+            return
+        shape = tuple(new_smaps.shape)
+        C, XYZ = shape[0], shape[1:]
+        if XYZ != self.shape:
+            raise ValueError("Smaps should match image shape.")
+        if C != self._n_coils:
+            self._n_coils = int(C)
+            self.log.warning("updating number of coils via Smaps.")
+        self._smaps = new_smaps
+        # a contiguous complex64 CUDA tensor on this device is used zero-copy (never written to)
+        self._smaps_d = to_device(new_smaps, self.device, torch.complex64)
+
+    def compute_smaps(self, method=None):
+        """Same grammar as ``FourierOperatorBase.compute_smaps`` (base.py:407-448) + device arrays."""
+        if method is not None and not isinstance(method, (str, dict)) and not callable(method):
+            if hasattr(method, "shape"):
+                self.smaps = method.reshape(self.n_coils, *self.shape)
+                return
+        if method is None:
+            self.smaps = None
+            return
+        super().compute_smaps(method)
+
+    @property
+    def density(self):
+        """Density compensation weights (host numpy float32, or ``None``)."""
+        return self._density
+
+    @density.setter
+    def density(self, new_density):
+        if new_density is None:
+            self._density = None
+            self._density_d = None
+            return
+        if len(new_density) != self.n_samples:
+            raise ValueError("Density and samples should have the same length")
+        d = to_device(new_density, self.device)
+        if d.is_complex():
+            d = d.real
+        d = d.to(torch.float32).contiguous().reshape(-1)
+        self._density_d = d
+        self._density = new_density if isinstance(new_density, np.ndarray) else d.cpu().numpy()
+
+    def compute_density(self, method=None):
+        """``FourierOperatorBase.compute_density`` (base.py:576-624) with device-array support."""
+        if method is not None and not isinstance(method, (str, dict, bool)) and not callable(method):
+            if hasattr(method, "shape"):
+                self.density = method
+                return
+        if method is None or method is False:
+            self.density = None
+            return
+        super().compute_density(method)
+        # the base class may have stored a raw array without going through the setter
+        if self._density is not None and self._density_d is None:
+            self.density = self._density
+
+    @property
+    def samples(self):
+        """Host numpy ``(M, d)`` float32 array in radians (as ``MRIfinufft``, finufft.py:128-129)."""
+        return self._samples
+
+    @samples.setter
+    def samples(self, new_samples):
+        self.update_samples(new_samples)
+
+    def update_samples(self, new_samples, *, unsafe: bool = False):
+        """Update the sample locations (``MRIfinufft.update_samples``, finufft.py:150-181)."""
+        if unsafe and module_name(new_samples) == "torch" and new_samples.is_cuda:
+            self.raw_op._set_pts(new_samples.detach())
+            self._samples = new_samples.detach().cpu().numpy()
+        else:
+            self._samples = self._normalize_samples(new_samples)
+            self.raw_op._set_pts(self._samples)
+        if self._density_method is not None:
+            self.compute_density(self._density_method)
+
+    # ------------------------------------------------------------------ toggles for the trajectory gradient
+    def toggle_grad_traj(self):
+        """Role of ``_ToggleGradPlanMixin.toggle_grad_traj`` (base.py:1234-1238): opposite FFT sign
+        and conjugated smaps, without copying the maps or building a second plan."""
+        if self.uses_sense:
+            self._conj_smaps = not self._conj_smaps
+        self.raw_op.toggle_grad_traj()
+
+    @contextmanager
+    def grad_traj_plan(self):
+        self.toggle_grad_traj()
+        try:
+            yield
+        finally:
+            self.toggle_grad_traj()
+
+    def _make_plan_grad(self, **kwargs):
+        """Nothing to build: the plan handles both signs (cf. finufft.py:183-193)."""
+
+    # ------------------------------------------------------------------ device-level transforms
+    def _chunks(self):
+        T = self.raw_op.n_trans
+        C = self.n_coils
+        return [(c0, min(c0 + T, C)) for c0 in range(0, C, T)]
+
+    def _op_device(self, img: torch.Tensor, ksp: torch.Tensor | None = None) -> torch.Tensor:
+        """img (B, 1|C, *XYZ) complex64 on device -> ksp (B, C, K)."""
+        B, C, K, XYZ = self.n_batchs, self.n_coils, self.n_samples, self.shape
+        inv_norm = float(self.inv_norm_factor)
+        if ksp is None:
+            ksp = torch.empty((B, C, K), dtype=torch.complex64, device=self.device)
+        ksp = ksp.view(B, C, K)
+        raw = self.raw_op
+        if self._spread_only:
+            img = img.reshape(B, C, *XYZ)
+            for b in range(B):
+                for c0, c1 in self._chunks():
+                    raw.plan.interp(img[b, c0:c1].data_ptr(), ksp[b, c0:c1].data_ptr(), c1 - c0,
+                                    self.stream)
+            ksp *= inv_norm
+            return ksp
+        if self.uses_sense:
+            img = img.reshape(B, *XYZ)
+            for b in range(B):
+                for c0, c1 in self._chunks():
+                    raw.type2(img[b], self._smaps_d[c0:c1], ksp[b, c0:c1], inv_norm, self._conj_smaps)
+        else:
+            img = img.reshape(B, C, *XYZ)
+            for b in range(B):
+                for c0, c1 in self._chunks():
+                    raw.type2(img[b, c0:c1], None, ksp[b, c0:c1], inv_norm)
+        return ksp
+
+    def _adj_device(self, ksp: torch.Tensor, img: torch.Tensor | None = None) -> torch.Tensor:
+        """ksp (B, C, K) complex64 on device -> img (B, 1|C, *XYZ)."""
+        B, C, K, XYZ = self.n_batchs, self.n_coils, self.n_samples, self.shape
+        inv_norm = float(self.inv_norm_factor)
+        ksp = ksp.reshape(B, C, K)
+        raw = self.raw_op
+        dens = self._density_d
+        if self._spread_only:
+            if img is None:
+                img = torch.empty((B, C, *XYZ), dtype=torch.complex64, device=self.device)
+            img = img.view(B, C, *XYZ)
+            for b in range(B):
+                for c0, c1 in self._chunks():
+                    k = ksp[b, c0:c1]
+                    if dens is not None:
+                        k = k * dens
+                    raw.plan.spread(k.data_ptr(), img[b, c0:c1].data_ptr(), c1 - c0, self.stream)
+            img *= inv_norm
+            return img
+        if self.uses_sense:
+            if img is None:
+                img = torch.empty((B, 1, *XYZ), dtype=torch.complex64, device=self.device)
+            img = img.view(B, 1, *XYZ)
+            for b in range(B):
+                for i, (c0, c1) in enumerate(self._chunks()):
+                    raw.type1(ksp[b, c0:c1], dens, self._smaps_d[c0:c1], img[b, 0], accumulate=i > 0,
+                              scale=inv_norm, conj_smaps=self._conj_smaps)
+        else:
+            if img is None:
+                img = torch.empty((B, C, *XYZ), dtype=torch.complex64, device=self.device)
+            img = img.view(B, C, *XYZ)
+            for b in range(B):
+                for c0, c1 in self._chunks():
+                    raw.type1(ksp[b, c0:c1], dens, None, img[b, c0:c1], accumulate=False,
+                              scale=inv_norm)
+        return img
+
+    def _dc_device(self, img: torch.Tensor, obs: torch.Tensor) -> torch.Tensor:
+        """Fused A^H(Ax - y) (base.py:1075-1139), the k-space residual stays inside the library."""
+        B, C, K, XYZ = self.n_batchs, self.n_coils, self.n_samples, self.shape
+        inv_norm = float(self.inv_norm_factor)
+        obs = obs.reshape(B, C, K)
+        raw = self.raw_op
+        dens = self._density_d
+        dptr = 0 if dens is None else dens.data_ptr()
+        if self._spread_only or raw.isign_flip or self._conj_smaps:
+            return self._adj_device(self._op_device(img) - obs)
+        if self.uses_sense:
+            img = img.reshape(B, *XYZ)
+            grad = torch.empty((B, 1, *XYZ), dtype=torch.complex64, device=self.device)
+            for b in range(B):
+                for i, (c0, c1) in enumerate(self._chunks()):
+                    raw.plan.data_consistency(
+                        img[b].data_ptr(), self._smaps_d[c0:c1].data_ptr(), obs[b, c0:c1].data_ptr(),
+                        dptr, grad[b, 0].data_ptr(), c1 - c0, int(i > 0), inv_norm, self.stream)
+        else:
+            img = img.reshape(B, C, *XYZ)
+            grad = torch.empty((B, C, *XYZ), dtype=torch.complex64, device=self.device)
+            for b in range(B):
+                for c0, c1 in self._chunks():
+                    raw.plan.data_consistency(
+                        img[b, c0:c1].data_ptr(), 0, obs[b, c0:c1].data_ptr(), dptr,
+                        grad[b, c0:c1].data_ptr(), c1 - c0, 0, inv_norm, self.stream)
+        return grad
+
+    # ------------------------------------------------------------------ public API
+    def op(self, data, ksp=None):
+        r"""Non-Cartesian MRI forward operator :math:`\mathcal{F}\mathcal{S}_\ell x` (base.py:949-977).
+
+        Accepts numpy / torch / cupy arrays; the result has the type and device of ``data``.
+        """
+        self.check_shape(image=data, ksp=ksp)
+        img, kind, dev = self._in(data)
+        out = None
+        if ksp is not None and module_name(ksp) == "torch" and ksp.is_cuda and ksp.is_contiguous() \
+                and ksp.dtype == torch.complex64 and ksp.device == self.device:
+            out = ksp
+        res = self._op_device(img, out)
+        res = self._safe_squeeze(res)
+        if ksp is not None and out is None:
+            _copy_into(ksp, res)
+            return ksp
+        return self._out(res, kind, dev)
+
+    def adj_op(self, coeffs, img=None):
+        """Non-Cartesian MRI adjoint operator (base.py:1015-1035)."""
+        self.check_shape(image=img, ksp=coeffs)
+        ksp, kind, dev = self._in(coeffs)
+        out = None
+        if img is not None and module_name(img) == "torch" and img.is_cuda and img.is_contiguous() \
+                and img.dtype == torch.complex64 and img.device == self.device:
+            out = img
+        res = self._adj_device(ksp, out)
+        res = self._safe_squeeze(res)
+        if img is not None and out is None:
+            _copy_into(img, res)
+            return img
+        return self._out(res, kind, dev)
+
+    def data_consistency(self, image_data, obs_data):
+        """Gradient of the data-consistency term ``A^H (A x - y)`` (base.py:1075-1139)."""
+        self.check_shape(image=image_data, ksp=obs_data)
+        img, kind, dev = self._in(image_data)
+        obs, _, _ = self._in(obs_data)
+        return self._out(self._safe_squeeze(self._dc_device(img, obs)), kind, dev)
+
+    def _op(self, image, coeffs):
+        """Raw batched type 2 without smaps / normalisation; writes into ``coeffs`` (base.py:1013)."""
+        img, _, _ = self._in(image)
+        T = int(np.prod(img.shape[: img.ndim - len(self.shape)])) if img.ndim > len(self.shape) else 1
+        img = img.reshape(T, *self.shape)
+        out = torch.empty((T, self.n_samples), dtype=torch.complex64, device=self.device)
+        step = self.raw_op.n_trans
+        for t0 in range(0, T, step):
+            if self._spread_only:
+                self.raw_op.plan.interp(img[t0:t0 + step].data_ptr(), out[t0:t0 + step].data_ptr(),
+                                        min(step, T - t0), self.stream)
+            else:
+                self.raw_op.type2(img[t0:t0 + step], None, out[t0:t0 + step], 1.0)
+        _copy_into(coeffs, out.reshape(coeffs.shape))
+        return coeffs
+
+    def _adj_op(self, coeffs, image):
+        """Raw batched type 1 (density applied, no smaps / normalisation); writes into ``image``
+        (base.py:1068-1073).  Used in place by the Toeplitz kernel builder (toeplitz.py:143-149)."""
+        ksp, _, _ = self._in(coeffs)
+        ksp = ksp.reshape(-1, self.n_samples)
+        T = ksp.shape[0]
+        out = torch.empty((T, *self.shape), dtype=torch.complex64, device=self.device)
+        step = self.raw_op.n_trans
+        for t0 in range(0, T, step):
+            k = ksp[t0:t0 + step]
+            if self._spread_only:
+                if self._density_d is not None:
+                    k = k * self._density_d
+                self.raw_op.plan.spread(k.data_ptr(), out[t0:t0 + step].data_ptr(), k.shape[0],
+                                        self.stream)
+            else:
+                self.raw_op.type1(k, self._density_d, None, out[t0:t0 + step], False, 1.0)
+        _copy_into(image, out.reshape(image.shape))
+        return image
+
+    # ------------------------------------------------------------------ Lipschitz constant / solvers
+    def get_lipschitz_cst(self, max_iter=10):
+        """Power method on the single-coil ``A^H A`` (density included), device resident.
+
+        Mirrors ``FourierOperatorBase.get_lipschitz_cst`` + ``power_method``
+        (base.py:626-665, 1155-1221): random start from ``np.random.random``, stop when the norm
+        changes by less than 1e-6.  Returns a numpy float32 scalar.
+        """
+        saved = (self._n_coils, self._n_batchs, self._smaps, self._smaps_d, self.squeeze_dims)
+        self._smaps = None
+        self._smaps_d = None
+        self._n_coils = 1
+        self._n_batchs = 1
+        try:
+            x = np.random.random(self.shape).astype(np.complex64)
+            x = to_device(x, self.device, torch.complex64)
+            x_norm = torch.linalg.norm(x)
+            x = x / x_norm
+            x_new_norm = x_norm
+            i = 0
+            for i in range(max_iter):  # noqa: B007
+                x_new = self._adj_device(self._op_device(x.reshape(1, 1, *self.shape)))
+                x_new_norm = torch.linalg.norm(x_new)
+                x_new = x_new / x_new_norm
+                if torch.abs(x_norm - x_new_norm) < 1e-6:
+                    break
+                x_norm = x_new_norm
+                x = x_new
+            if i == max_iter - 1:
+                warnings.warn("Lipschitz constant did not converge")
+            return np.float32(x_new_norm.item())
+        finally:
+            self._n_coils, self._n_batchs, self._smaps, self._smaps_d, self.squeeze_dims = saved
+
+    def pinv_solver(self, kspace_data, optim="lsqr", **kwargs):
+        """Solve ``A x = y`` (base.py:667-690).  ``optim="cg"`` runs device resident
+        (``solvers.cg``); other optimisers use the reference implementations on top of this
+        operator's ``op`` / ``adj_op``."""
+        if optim == "cg":
+            from .solvers import cg
+
+            return cg(self, kspace_data, **kwargs)
+        return super().pinv_solver(kspace_data, optim=optim, **kwargs)
+
+    # ------------------------------------------------------------------ autodiff
+    def make_autograd(self, *, wrt_data=True, wrt_traj=False, paired_batch=False):
+        """Torch autograd wrapper (role of base.py:536-574).  The reference module hard-imports
+        ``deepinv`` (autodiff.py:11); ours is the same wrapper without that dependency."""
+        if not self.autograd_available:
+            raise ValueError("Backend does not support auto-differentiation.")
+        from .autodiff import MRINufftAutoGrad
+
+        return MRINufftAutoGrad(self, wrt_data=wrt_data, wrt_traj=wrt_traj, paired_batch=paired_batch)
+
+    # ------------------------------------------------------------------ density compensation
+    @classmethod
+    def pipe(cls, kspace_loc, volume_shape, max_iter=10, osf=2, normalize=True, **kwargs):
+        """Pipe's iterative density compensation, device resident (``MRIfinufft.pipe``,
+        finufft.py:195-245): ``d <- d / |G G^H d|`` with a spread/interp-only plan on a grid of
+        size ``volume_shape`` whose kernel shape is set by ``osf``; optional PSF normalisation
+        with one full op + adj_op."""
+        kwargs.pop("backend", None)
+        grid_op = cls(samples=kspace_loc, shape=volume_shape, upsampfac=osf, spreadinterponly=1,
+                      **kwargs)
+        M = grid_op.n_samples
+        d = torch.ones(M, dtype=torch.float32, device=grid_op.device)
+        norm2 = float(grid_op.norm_factor) ** 2
+        for _ in range(max_iter):
+            grid_op.raw_op.plan.pipe_iteration(d.data_ptr(), grid_op.stream)
+            d *= norm2  # the reference applies 1/norm in both op and adj_op of grid_op
+        if normalize:
+            test_op = cls(samples=kspace_loc, shape=volume_shape, **kwargs)
+            test_im = torch.ones((1, 1, *test_op.shape), dtype=torch.complex64, device=test_op.device)
+            ksp = test_op._op_device(test_im)
+            ksp = ksp * d.to(test_op.device)
+            recon = test_op._adj_device(ksp)
+            d = d / torch.mean(torch.abs(recon))
+        return torch.abs(d).cpu().numpy()
+
+    def __repr__(self):
+        return (
+            f"{self.__class__.__name__}(\n"
+            f"  shape: {self.shape}\n"
+            f"  n_coils: {self.n_coils}\n"
+            f"  n_samples: {self.n_samples}\n"
+            f"  uses_sense: {self.uses_sense}\n"
+            f"  device: {self.device}, eps: {self.eps}, upsampfac: {self.upsampfac},"
+            f" kernel width: {self.raw_op.plan.w}, fine grid: {self.raw_op.plan.nf}\n"
+            ")"
+        )
+
+
+def _copy_into(dst, src: torch.Tensor):
+    """Write the device result ``src`` into the caller-provided buffer ``dst`` (any array type)."""
+    root = module_name(dst)
+    if root == "torch":
+        dst.copy_(src.reshape(dst.shape))
+    elif isinstance(dst, np.ndarray):
+        dst[...] = src.reshape(dst.shape).cpu().numpy()
+    else:
+        t = torch.as_tensor(dst, device=src.device)
+        t.copy_(src.reshape(t.shape))
+

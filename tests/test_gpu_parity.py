@@ -1,0 +1,489 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the reference's golden vectors, the
+CPU oracle and the reference's own behavioural contract (tests/operators/*.py of mri-nufft).
+
+Tolerances (BASELINE.json north_star): complex64, eps = 1e-6 -> relative L2 error <= 5e-6 against the
+exact NDFT, which implies <= 1e-5 against finufft (itself ~1.2e-6 from the NDFT);
+sort / bin indices bit exact.
+"""
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN_CASES, load_golden, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+TOL_NDFT = 5e-6
+
+
+@pytest.fixture(scope="module")
+def mods():
+    import torch
+
+    import mrinufft
+    import mrinufft_b200
+
+    assert mrinufft_b200.MRIB200NUFFT.available, "libb200nufft.so missing or no GPU"
+    return mrinufft, mrinufft_b200, torch
+
+
+def make_op(mrinufft, g, **kw):
+    return mrinufft.get_operator("b200")(
+        g["samples"], g["shape"], n_coils=g["n_coils"], smaps=g.get("smaps"), squeeze_dims=False, **kw
+    )
+
+
+# ------------------------------------------------------------------ K1: bit-exact sort
+@pytest.mark.parametrize("case", GOLDEN_CASES)
+def test_sort_bit_exact(mods, case):
+    from oracle import es_nufft as E
+
+    mrinufft, _, _ = mods
+    g = load_golden(case)
+    op = make_op(mrinufft, g)
+    plan = op.raw_op.plan
+    ref = E.bin_sort(g["samples"], plan.nf, plan.w, plan.bins)
+    origin, x1, key, perm = op.raw_op.sort_indices()
+    assert np.array_equal(origin, ref["origin"])
+    assert np.array_equal(x1.view(np.uint32), ref["x1"].view(np.uint32))
+    assert np.array_equal(key, ref["key"])
+    assert np.array_equal(perm, ref["perm"])
+
+
+def test_sort_bit_exact_adversarial(mods):
+    """x = +-pi exactly, +-pi(1 +- 2^-23), 0, denormals, |x| up to 3 pi, cell boundaries."""
+    from oracle import es_nufft as E
+
+    mrinufft, _, _ = mods
+    pi32 = np.float32(np.pi)
+    specials = np.array(
+        [0.0, pi32, -pi32, np.nextafter(pi32, np.float32(4)), np.nextafter(pi32, np.float32(0)),
+         -np.nextafter(pi32, np.float32(4)), -np.nextafter(pi32, np.float32(0)), 1e-45, -1e-45,
+         1e-38, 3 * pi32, -3 * pi32, 2 * pi32, -2 * pi32, 0.5 * pi32, -0.5 * pi32,
+         np.float32(2 * np.pi / 128), np.float32(2 * np.pi * 3.5 / 128), np.float32(-2 * np.pi * 3.5 / 128)],
+        dtype=np.float32)
+    rng = np.random.default_rng(0)
+    for shape in [(64, 64), (32, 32, 32)]:
+        d = len(shape)
+        pts = rng.uniform(-3 * np.pi, 3 * np.pi, (20000, d)).astype(np.float32)
+        pts[: len(specials)] = specials[:, None]
+        pts[len(specials): 2 * len(specials), 0] = specials
+        # points exactly on fine-grid cell boundaries and half cells
+        nf = 2 * shape[0]
+        cells = (np.arange(300) % nf - nf // 2) * (2 * np.pi / nf)
+        pts[100:400, d - 1] = cells.astype(np.float32)
+        pts[400:700, 0] = (cells + np.pi / nf).astype(np.float32)
+        op = mrinufft.get_operator("b200")(pts, shape)
+        assert np.array_equal(op.samples, pts)  # |x| > 0.5 -> taken as radians, not rescaled
+        plan = op.raw_op.plan
+        ref = E.bin_sort(pts, plan.nf, plan.w, plan.bins)
+        origin, x1, key, perm = op.raw_op.sort_indices()
+        assert np.array_equal(origin, ref["origin"])
+        assert np.array_equal(x1.view(np.uint32), ref["x1"].view(np.uint32))
+        assert np.array_equal(key, ref["key"])
+        assert np.array_equal(perm, ref["perm"])
+        assert np.array_equal(np.sort(perm), np.arange(len(pts)))
+
+
+# ------------------------------------------------------------------ op / adj_op vs the reference's NDFT goldens
+@pytest.mark.parametrize("case", GOLDEN_CASES)
+def test_op_matches_reference_ndft(mods, case):
+    mrinufft, _, _ = mods
+    g = load_golden(case)
+    op = make_op(mrinufft, g)
+    y = op.op(g["img"])
+    assert y.shape == g["op"].shape and y.dtype == np.complex64
+    assert rel_l2(y, g["op"]) <= TOL_NDFT
+
+
+@pytest.mark.parametrize("case", GOLDEN_CASES)
+def test_adj_op_matches_reference_ndft(mods, case):
+    mrinufft, _, _ = mods
+    g = load_golden(case)
+    op = make_op(mrinufft, g)
+    x = op.adj_op(g["ksp"])
+    assert x.shape == g["adj"].shape and x.dtype == np.complex64
+    assert rel_l2(x, g["adj"]) <= TOL_NDFT
+
+
+@pytest.mark.parametrize("case", GOLDEN_CASES)
+def test_density_and_data_consistency_match_reference(mods, case):
+    mrinufft, _, _ = mods
+    g = load_golden(case)
+    opd = make_op(mrinufft, g, density=g["density"])
+    assert rel_l2(opd.adj_op(g["ksp"]), g["adj_density"]) <= TOL_NDFT
+    op = make_op(mrinufft, g)
+    dc = op.data_consistency(g["img"], g["ksp"])
+    assert dc.shape == g["dc"].shape
+    assert rel_l2(dc, g["dc"]) <= TOL_NDFT
+    # data_consistency == adj_op(op(x) - y)   (tests/operators/test_batch.py:166-199)
+    naive = op.adj_op(op.op(g["img"]) - g["ksp"])
+    assert rel_l2(dc, naive) <= 2e-6
+
+
+def test_known_answer_cartesian_grid(mods):
+    """NDFT on a Cartesian grid == fftn(fftshift(img)) (reference tests/test_ndft.py:58-79)."""
+    import scipy.fft as sfft
+
+    mrinufft, _, _ = mods
+    g = load_golden("grid2D")
+    op = mrinufft.get_operator("b200")(g["samples"], g["shape"])
+    img = g["img"][0, 0]
+    y = op.op(img) * op.norm_factor
+    ref = sfft.fftshift(sfft.fftn(sfft.fftshift(img.astype(np.complex128))))
+    assert rel_l2(y.reshape(g["shape"]), ref) <= TOL_NDFT
+
+
+@pytest.mark.parametrize("case", ["random2D_sense", "random3D", "cones3D"])
+def test_matches_cpu_oracle_tightly(mods, case):
+    """Same kernel family / parameters as the finufft restatement -> far closer to it than either
+    is to the NDFT (float32 rounding only)."""
+    from oracle.c_oracle import CpuNufft
+
+    mrinufft, _, _ = mods
+    g = load_golden(case)
+    op = make_op(mrinufft, g)
+    cpu = CpuNufft(g["samples"], g["shape"], eps=1e-6, precision="f64")
+    smaps = g.get("smaps")
+    if smaps is not None:
+        y_ref = cpu.op(g["img"][0, 0], smaps)
+    else:
+        y_ref = np.stack([cpu.op(g["img"][0, c])[0] for c in range(g["n_coils"])])
+    y = op.op(g["img"])
+    assert rel_l2(y, y_ref.reshape(y.shape)) <= 1.5e-6
+
+
+# ------------------------------------------------------------------ adjointness, Lipschitz (test_interfaces.py:138-176)
+@pytest.mark.parametrize("case", ["random2D", "random3D_sense", "spiral2D_sense", "cones3D"])
+def test_adjointness(mods, case):
+    mrinufft, _, _ = mods
+    g = load_golden(case)
+    op = make_op(mrinufft, g)
+    rng = np.random.default_rng(3)
+    errs = []
+    for _ in range(5):
+        x = (rng.standard_normal(op.img_full_shape) + 1j * rng.standard_normal(op.img_full_shape)).astype(np.complex64)
+        y = (rng.standard_normal(op.ksp_full_shape) + 1j * rng.standard_normal(op.ksp_full_shape)).astype(np.complex64)
+        lhs = np.vdot(op.op(x).astype(np.complex128), y.astype(np.complex128))
+        rhs = np.vdot(x.astype(np.complex128), op.adj_op(y).astype(np.complex128))
+        errs.append(abs(lhs - rhs) / abs(rhs))
+    assert np.mean(errs) < 5e-5
+    assert np.mean(errs) < 5e-6  # spread and interp share the sorted points and weights
+
+
+def test_lipschitz(mods):
+    mrinufft, _, _ = mods
+    g = load_golden("random2D")
+    op = mrinufft.get_operator("b200")(g["samples"], g["shape"])
+    np.random.seed(0)
+    L = op.get_lipschitz_cst(max_iter=30)
+    assert isinstance(L, np.floating)
+    rng = np.random.default_rng(0)
+    for _ in range(5):
+        x = (rng.standard_normal(g["shape"]) + 1j * rng.standard_normal(g["shape"])).astype(np.complex64)
+        assert np.linalg.norm(op.adj_op(op.op(x))) <= 1.05 * L * np.linalg.norm(x)
+
+
+# ------------------------------------------------------------------ shapes / squeeze / errors (base.py:225-273)
+def test_shapes_squeeze_and_errors(mods):
+    mrinufft, _, _ = mods
+    g = load_golden("random2D")
+    op = mrinufft.get_operator("b200")(g["samples"], g["shape"])
+    img = g["img"][0, 0]
+    y = op.op(img)
+    assert y.shape == (1000,)
+    assert op.adj_op(y).shape == g["shape"]
+    with pytest.raises(ValueError):
+        op.op(img[:-1])
+    with pytest.raises(ValueError):
+        op.adj_op(y[:-1])
+    with pytest.raises(ValueError):
+        mrinufft.get_operator("b200")(g["samples"], g["shape"], n_coils=3, n_trans=2)
+    with pytest.raises(ValueError):
+        op.density = np.ones(3, np.float32)
+    assert mrinufft.get_operator("b200").__name__ == "MRIB200NUFFT"
+    assert abs(op.norm_factor - np.sqrt(64 * 128 * 4)) < 1e-9
+
+
+@pytest.mark.parametrize("n_batchs,n_coils,n_trans,sense", [(1, 1, 1, False), (3, 1, 1, False),
+                                                             (1, 4, 2, True), (2, 4, 1, True),
+                                                             (2, 4, 4, False), (3, 2, 2, False),
+                                                             (2, 6, 3, True)])
+def test_batched_equals_flat(mods, n_batchs, n_coils, n_trans, sense):
+    """Batched op/adj == per (batch, coil) single transforms (tests/operators/test_batch.py:106-163)."""
+    mrinufft, _, _ = mods
+    g = load_golden("nyquist_radial2D")
+    rng = np.random.default_rng(5)
+    shape = g["shape"]
+    smaps = None
+    if sense:
+        smaps = (rng.standard_normal((n_coils, *shape)) + 1j * rng.standard_normal((n_coils, *shape))).astype(np.complex64)
+        smaps /= np.linalg.norm(smaps, axis=0)
+    op = mrinufft.get_operator("b200")(g["samples"], shape, n_coils=n_coils, n_batchs=n_batchs,
+                                       n_trans=n_trans, smaps=smaps, squeeze_dims=False)
+    flat = mrinufft.get_operator("b200")(g["samples"], shape, squeeze_dims=True)
+    img = (rng.standard_normal(op.img_full_shape) + 1j * rng.standard_normal(op.img_full_shape)).astype(np.complex64)
+    ksp = (rng.standard_normal(op.ksp_full_shape) + 1j * rng.standard_normal(op.ksp_full_shape)).astype(np.complex64)
+    y = op.op(img)
+    x = op.adj_op(ksp)
+    y_ref = np.zeros_like(y)
+    x_ref = np.zeros_like(x)
+    for b in range(n_batchs):
+        for c in range(n_coils):
+            if sense:
+                y_ref[b, c] = flat.op(img[b, 0] * smaps[c])
+                x_ref[b, 0] += np.conj(smaps[c]) * flat.adj_op(ksp[b, c])
+            else:
+                y_ref[b, c] = flat.op(img[b, c])
+                x_ref[b, c] = flat.adj_op(ksp[b, c])
+    assert rel_l2(y, y_ref) < 1e-6
+    assert rel_l2(x, x_ref) < 1e-6
+
+
+def test_inputs_are_read_only_safe(mods):
+    """Inputs are never mutated and read-only arrays are accepted (test_batch.py:202-210)."""
+    mrinufft, _, _ = mods
+    g = load_golden("random2D_sense")
+    op = make_op(mrinufft, g)
+    img, ksp = g["img"].copy(), g["ksp"].copy()
+    img.setflags(write=False)
+    ksp.setflags(write=False)
+    op.op(img)
+    op.adj_op(ksp)
+    op.data_consistency(img, ksp)
+    assert np.array_equal(img, g["img"]) and np.array_equal(ksp, g["ksp"])
+
+
+def test_array_types_in_same_type_out(mods):
+    mrinufft, _, torch = mods
+    g = load_golden("random2D_sense")
+    op = make_op(mrinufft, g)
+    y_np = op.op(g["img"])
+    y_tc = op.op(torch.from_numpy(g["img"]))
+    y_tg = op.op(torch.from_numpy(g["img"]).cuda())
+    assert isinstance(y_np, np.ndarray)
+    assert isinstance(y_tc, torch.Tensor) and y_tc.device.type == "cpu"
+    assert isinstance(y_tg, torch.Tensor) and y_tg.device.type == "cuda"
+    assert np.array_equal(y_np, y_tc.numpy()) and np.array_equal(y_np, y_tg.cpu().numpy())
+    x_tg = op.adj_op(torch.from_numpy(g["ksp"]).cuda())
+    assert x_tg.is_cuda and rel_l2(x_tg.cpu().numpy(), g["adj"]) <= TOL_NDFT
+    # float64 / complex128 inputs are cast
+    y64 = op.op(g["img"].astype(np.complex128))
+    assert y64.dtype == np.complex64 and np.array_equal(y64, y_np)
+    # smaps given as a CUDA tensor
+    op2 = mrinufft.get_operator("b200")(g["samples"], g["shape"], n_coils=g["n_coils"],
+                                        smaps=torch.from_numpy(g["smaps"]).cuda(), squeeze_dims=False)
+    assert np.array_equal(op2.op(g["img"]), y_np)
+
+
+# ------------------------------------------------------------------ updates (tests/operators/test_update.py:131-248)
+def test_update_samples_density_smaps(mods):
+    mrinufft, _, _ = mods
+    g = load_golden("random2D_sense")
+    rng = np.random.default_rng(9)
+    op = make_op(mrinufft, g)
+    new_samples = g["samples"] + rng.uniform(-0.05, 0.05, g["samples"].shape).astype(np.float32)
+    op.samples = new_samples
+    fresh = mrinufft.get_operator("b200")(new_samples, g["shape"], n_coils=g["n_coils"],
+                                          smaps=g["smaps"], squeeze_dims=False)
+    assert np.array_equal(op.op(g["img"]), fresh.op(g["img"]))
+    assert rel_l2(op.adj_op(g["ksp"]), fresh.adj_op(g["ksp"])) < 1e-6
+    # in-place jitter on the returned array then re-assignment (test_update.py:139-145)
+    s = op.samples
+    s += np.float32(0.01)
+    op.samples = s
+    fresh = mrinufft.get_operator("b200")(s, g["shape"], n_coils=g["n_coils"], smaps=g["smaps"],
+                                          squeeze_dims=False)
+    assert np.array_equal(op.op(g["img"]), fresh.op(g["img"]))
+    # density / smaps setters
+    op.density = g["density"]
+    fresh = mrinufft.get_operator("b200")(s, g["shape"], n_coils=g["n_coils"], smaps=g["smaps"],
+                                          squeeze_dims=False, density=g["density"])
+    assert rel_l2(op.adj_op(g["ksp"]), fresh.adj_op(g["ksp"])) < 1e-6
+    new_smaps = np.ascontiguousarray(g["smaps"][::-1])
+    op.smaps = new_smaps
+    fresh.smaps = new_smaps
+    assert np.array_equal(op.op(g["img"]), fresh.op(g["img"]))
+    op.density = None
+    assert not op.uses_density
+
+
+# ------------------------------------------------------------------ pipe density (test_density_for_op.py:20-57)
+@pytest.mark.parametrize("osf", [1.5, 2])
+@pytest.mark.parametrize("dim", [2, 3])
+def test_pipe_density(mods, osf, dim):
+    mrinufft, _, _ = mods
+    from mrinufft.trajectories import initialize_2D_radial, initialize_3D_phyllotaxis_radial
+
+    if dim == 2:
+        traj, shape = initialize_2D_radial(128, 16).astype(np.float32), (32, 32)
+    else:
+        traj, shape = initialize_3D_phyllotaxis_radial(256, 16).astype(np.float32), (32, 32, 32)
+    d = mrinufft.get_operator("b200").pipe(traj.reshape(-1, dim), shape, max_iter=10, osf=osf)
+    assert d.shape == (traj.reshape(-1, dim).shape[0],) and d.dtype == np.float32
+    assert np.all(np.isfinite(d)) and np.all(d > 0)
+    r = np.linalg.norm(traj.reshape(-1, dim), axis=-1)
+    # density compensation of a radial trajectory grows like r^(d-1)
+    mask = r > 0.02
+    corr = np.corrcoef(d[mask], r[mask] ** (dim - 1))[0, 1]
+    assert corr > 0.8
+    # density="pipe" through the operator constructor (base.py:608-614 -> density/nufft_based.py)
+    op = mrinufft.get_operator("b200")(traj, shape, density=True)
+    assert op.uses_density and op.density.shape == d.shape
+    ref = mrinufft.get_operator("b200").pipe(traj.reshape(-1, dim), shape)
+    assert np.allclose(op.density, ref, rtol=1e-5)
+
+
+def test_pipe_matches_cpu_oracle(mods):
+    """d <- d / |G G^H d| with the spread/interp-only ES kernel, against the C oracle."""
+    from oracle.c_oracle import CpuNufft
+    from oracle import es_nufft as E
+
+    mrinufft, _, _ = mods
+    from mrinufft.trajectories import initialize_2D_radial
+
+    traj = initialize_2D_radial(64, 32).astype(np.float32).reshape(-1, 2)
+    shape = (48, 48)
+    d = mrinufft.get_operator("b200").pipe(traj, shape, max_iter=10, osf=2, normalize=False)
+    # oracle: grid = image shape, kernel from eps=1e-6 / sigma=2
+    samples = (traj * 2 * np.pi).astype(np.float32)
+    cpu = CpuNufft(samples, shape, precision="f64")
+    cpu.nfs = shape
+    cpu.nf_arr = np.asarray(shape, np.int32)
+    for a in range(2):
+        from oracle.c_oracle import fold
+
+        cpu.origin[a], cpu.x1[a] = fold(samples[:, a], shape[a], cpu.w)
+    cpu.perm = np.argsort(E.make_key(cpu.origin, shape, E.default_bins(2)), kind="stable").astype(np.int32)
+    dd = np.ones(len(samples))
+    norm2 = np.prod(shape) * 4.0
+    for _ in range(10):
+        dd = dd / np.abs(cpu.interp(cpu.spread(dd.astype(np.complex128)))[0]) * norm2
+    assert rel_l2(d, dd) < 2e-5
+
+
+# ------------------------------------------------------------------ solvers
+def test_cg_matches_reference_golden(mods):
+    mrinufft, _, _ = mods
+    g = load_golden("cg2D_sense")
+    op = mrinufft.get_operator("b200")(g["samples"], g["shape"], n_coils=4, smaps=g["smaps"])
+    np.random.seed(1234)
+    L = op.get_lipschitz_cst()
+    assert abs(L - g["lipschitz"]) / g["lipschitz"] < 1e-4
+    np.random.seed(1234)
+    x = op.pinv_solver(g["y"], optim="cg", max_iter=10)
+    assert x.shape == g["shape"]
+    assert rel_l2(x, g["x_cg"]) < 1e-4
+
+
+@pytest.mark.parametrize("optim", ["cg", "lsqr", "lsmr"])
+def test_pinv_solver_residual_decreases(mods, optim):
+    """tests/operators/test_optim.py:60-68 and test_batch.py:255-272."""
+    mrinufft, _, _ = mods
+    from mrinufft.extras.optim import loss_l2_reg
+
+    g = load_golden("cg2D_sense")
+    op = mrinufft.get_operator("b200")(g["samples"], g["shape"], n_coils=4, smaps=g["smaps"])
+    x, res = op.pinv_solver(g["y"], optim=optim, max_iter=5, callback=loss_l2_reg, progressbar=False)
+    assert x.shape == g["shape"]
+    res = np.asarray(res).ravel()
+    assert res[-1] <= res[0]
+
+
+# ------------------------------------------------------------------ autodiff (tests/operators/test_autodiff.py)
+def test_autodiff_data_and_trajectory(mods):
+    mrinufft, _, torch = mods
+    from oracle import es_nufft as E
+
+    rng = np.random.default_rng(2)
+    shape = (12, 16)
+    M = 200
+    samples = rng.uniform(-np.pi, np.pi, (M, 2)).astype(np.float32)
+    op = mrinufft.get_operator("b200", wrt_data=True, wrt_traj=True)(samples, shape, squeeze_dims=False)
+    norm = np.sqrt(np.prod(shape) * 4.0)
+    x = torch.from_numpy((rng.standard_normal((1, 1, *shape)) + 1j * rng.standard_normal((1, 1, *shape))).astype(np.complex64)).cuda()
+    x.requires_grad_(True)
+    ktraj = op.samples
+    y = op.op(x)
+    # dense NDFT model in torch (float64) for the expected gradients
+    st = torch.from_numpy(samples.astype(np.float64)).requires_grad_(True)
+    r = torch.stack(torch.meshgrid(*[torch.arange(s, dtype=torch.float64) - s // 2 for s in shape], indexing="ij"), 0).reshape(2, -1)
+    A = torch.exp(-1j * (st @ r)) / norm
+    xd = x.detach().cpu().to(torch.complex128).reshape(-1).requires_grad_(True)
+    yd = A @ xd
+    assert rel_l2(y.detach().cpu().numpy().ravel(), yd.detach().numpy()) <= TOL_NDFT
+    w = torch.from_numpy((rng.standard_normal(M) + 1j * rng.standard_normal(M)).astype(np.complex64))
+    loss = torch.sum(torch.abs(y.reshape(-1) - w.cuda()) ** 2)
+    loss.backward()
+    lossd = torch.sum(torch.abs(yd - w.to(torch.complex128)) ** 2)
+    lossd.backward()
+    assert rel_l2(x.grad.cpu().numpy().ravel(), xd.grad.numpy()) < 1e-4
+    assert rel_l2(ktraj.grad.numpy(), st.grad.numpy()) < 1e-3
+    # adjoint direction
+    ktraj.grad = None
+    k = torch.from_numpy((rng.standard_normal((1, 1, M)) + 1j * rng.standard_normal((1, 1, M))).astype(np.complex64)).cuda()
+    k.requires_grad_(True)
+    img = op.adj_op(k)
+    st2 = torch.from_numpy(samples.astype(np.float64)).requires_grad_(True)
+    A2 = torch.exp(-1j * (st2 @ r)) / norm
+    kd = k.detach().cpu().to(torch.complex128).reshape(-1).requires_grad_(True)
+    imgd = A2.conj().T @ kd
+    assert rel_l2(img.detach().cpu().numpy().ravel(), imgd.detach().numpy()) <= TOL_NDFT
+    t = torch.from_numpy((rng.standard_normal(shape) + 1j * rng.standard_normal(shape)).astype(np.complex64))
+    torch.sum(torch.abs(img.reshape(shape) - t.cuda()) ** 2).backward()
+    torch.sum(torch.abs(imgd.reshape(shape) - t.to(torch.complex128)) ** 2).backward()
+    assert rel_l2(k.grad.cpu().numpy().ravel(), kd.grad.numpy()) < 1e-4
+    assert rel_l2(ktraj.grad.numpy(), st2.grad.numpy()) < 1e-3
+    _ = E
+
+
+# ------------------------------------------------------------------ full-size properties (sampled exact NDFT)
+@pytest.mark.parametrize("shape,M,C", [((256, 256), 1 << 18, 4), ((96, 128, 80), 1 << 19, 3)])
+def test_large_sampled_ndft_and_linearity(mods, shape, M, C):
+    from oracle import es_nufft as E
+    from scipy.stats import truncnorm
+
+    mrinufft, _, torch = mods
+    d = len(shape)
+    rng = np.random.default_rng(0)
+    samples = (truncnorm(-3, 3, 0, 0.16).rvs((M, d), random_state=0) * 2 * np.pi).astype(np.float32)
+    smaps = (rng.standard_normal((C, *shape)) + 1j * rng.standard_normal((C, *shape))).astype(np.complex64)
+    smaps /= np.linalg.norm(smaps, axis=0)
+    op = mrinufft.get_operator("b200")(samples, shape, n_coils=C, smaps=smaps, squeeze_dims=False)
+    img = (rng.standard_normal(shape) + 1j * rng.standard_normal(shape)).astype(np.complex64)
+    y = op.op(img[None, None])
+    idx = rng.choice(M, 64, replace=False)
+    for c in (0, C - 1):
+        ref = E.ndft_type2_sampled(samples, img.astype(np.complex128) * smaps[c], idx) / op.norm_factor
+        assert rel_l2(y[0, c, idx], ref) <= TOL_NDFT
+    ksp = (rng.standard_normal((1, C, M)) + 1j * rng.standard_normal((1, C, M))).astype(np.complex64)
+    x = op.adj_op(ksp)
+    vox = np.stack([rng.integers(0, s, 24) for s in shape], -1)
+    ref = np.zeros(len(vox), np.complex128)
+    for c in range(C):
+        ref += np.conj(smaps[c][tuple(vox.T)]) * E.ndft_type1_sampled(samples, ksp[0, c], shape, vox)
+    ref /= op.norm_factor
+    assert rel_l2(x[0, 0][tuple(vox.T)], ref) <= TOL_NDFT
+    # linearity + adjointness at full size
+    img2 = (rng.standard_normal(shape) + 1j * rng.standard_normal(shape)).astype(np.complex64)
+    y2 = op.op(img2[None, None])
+    y12 = op.op((img + 2j * img2)[None, None])
+    assert rel_l2(y12, y + 2j * y2) < 2e-6
+    lhs = np.vdot(y.astype(np.complex128), ksp.astype(np.complex128))
+    rhs = np.vdot(img.astype(np.complex128), x[0, 0].astype(np.complex128))
+    assert abs(lhs - rhs) / abs(rhs) < 5e-6
+
+
+def test_empty_and_tiny_inputs(mods):
+    mrinufft, _, _ = mods
+    rng = np.random.default_rng(0)
+    shape = (16, 16)
+    one = np.array([[0.3, -1.2]], np.float32)
+    op = mrinufft.get_operator("b200")(one, shape)
+    img = (rng.standard_normal(shape) + 1j * rng.standard_normal(shape)).astype(np.complex64)
+    from oracle import es_nufft as E
+
+    A = E.ndft_matrix(one, shape)
+    assert rel_l2(op.op(img) * op.norm_factor, A @ img.ravel()) <= TOL_NDFT
+    x = op.adj_op(np.array([1 + 2j], np.complex64))
+    assert rel_l2(x.ravel() * op.norm_factor, A.conj().T @ np.array([1 + 2j])) <= TOL_NDFT
