@@ -264,16 +264,18 @@ def test_array_types_in_same_type_out(mods):
     assert isinstance(y_np, np.ndarray)
     assert isinstance(y_tc, torch.Tensor) and y_tc.device.type == "cpu"
     assert isinstance(y_tg, torch.Tensor) and y_tg.device.type == "cuda"
-    assert np.array_equal(y_np, y_tc.numpy()) and np.array_equal(y_np, y_tg.cpu().numpy())
+    # same arithmetic whatever the container type (the interpolation epilogue accumulates with
+    # float atomics, so repeated runs may differ in the last bits, never more)
+    assert rel_l2(y_tc.numpy(), y_np) < 1e-6 and rel_l2(y_tg.cpu().numpy(), y_np) < 1e-6
     x_tg = op.adj_op(torch.from_numpy(g["ksp"]).cuda())
     assert x_tg.is_cuda and rel_l2(x_tg.cpu().numpy(), g["adj"]) <= TOL_NDFT
     # float64 / complex128 inputs are cast
     y64 = op.op(g["img"].astype(np.complex128))
-    assert y64.dtype == np.complex64 and np.array_equal(y64, y_np)
+    assert y64.dtype == np.complex64 and rel_l2(y64, y_np) < 1e-6
     # smaps given as a CUDA tensor
     op2 = mrinufft.get_operator("b200")(g["samples"], g["shape"], n_coils=g["n_coils"],
                                         smaps=torch.from_numpy(g["smaps"]).cuda(), squeeze_dims=False)
-    assert np.array_equal(op2.op(g["img"]), y_np)
+    assert rel_l2(op2.op(g["img"]), y_np) < 1e-6
 
 
 # ------------------------------------------------------------------ updates (tests/operators/test_update.py:131-248)
@@ -286,7 +288,7 @@ def test_update_samples_density_smaps(mods):
     op.samples = new_samples
     fresh = mrinufft.get_operator("b200")(new_samples, g["shape"], n_coils=g["n_coils"],
                                           smaps=g["smaps"], squeeze_dims=False)
-    assert np.array_equal(op.op(g["img"]), fresh.op(g["img"]))
+    assert rel_l2(op.op(g["img"]), fresh.op(g["img"])) < 1e-6
     assert rel_l2(op.adj_op(g["ksp"]), fresh.adj_op(g["ksp"])) < 1e-6
     # in-place jitter on the returned array then re-assignment (test_update.py:139-145)
     s = op.samples
@@ -294,7 +296,7 @@ def test_update_samples_density_smaps(mods):
     op.samples = s
     fresh = mrinufft.get_operator("b200")(s, g["shape"], n_coils=g["n_coils"], smaps=g["smaps"],
                                           squeeze_dims=False)
-    assert np.array_equal(op.op(g["img"]), fresh.op(g["img"]))
+    assert rel_l2(op.op(g["img"]), fresh.op(g["img"])) < 1e-6
     # density / smaps setters
     op.density = g["density"]
     fresh = mrinufft.get_operator("b200")(s, g["shape"], n_coils=g["n_coils"], smaps=g["smaps"],
@@ -303,7 +305,7 @@ def test_update_samples_density_smaps(mods):
     new_smaps = np.ascontiguousarray(g["smaps"][::-1])
     op.smaps = new_smaps
     fresh.smaps = new_smaps
-    assert np.array_equal(op.op(g["img"]), fresh.op(g["img"]))
+    assert rel_l2(op.op(g["img"]), fresh.op(g["img"])) < 1e-6
     op.density = None
     assert not op.uses_density
 
