@@ -153,6 +153,11 @@ int b200_plan_create(b200_plan** out, int dim, const int64_t* n_modes, int n_tra
   p->flags = flags;
   p->device = device;
   p->ntrans_max = n_trans_max;
+  {
+    int sms = 0;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && sms > 0)
+      p->num_sms = sms;
+  }
   p->eps = eps;
   p->sigma = upsampfac > 0 ? upsampfac : 2.0;
   int w;
@@ -198,6 +203,7 @@ int b200_plan_create(b200_plan** out, int dim, const int64_t* n_modes, int n_tra
   g.bin[dim - 1] = BX;
   g.nbins[dim - 1] = (g.nf[dim - 1] + BX - 1) / BX;
   for (int a = 0; a < dim; ++a) p->nbins_tot *= g.nbins[a];
+  if (dim >= 2) p->nbins_tot *= 2;  // interior / crossing sub-bins (setpts.cu)
   if (p->nbins_tot >= (1LL << 31)) {
     b200_set_error("too many bins (%lld)", p->nbins_tot);
     delete p;

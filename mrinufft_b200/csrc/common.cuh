@@ -79,6 +79,7 @@ struct b200_plan {
   int flags = 0;
   int device = 0;
   int ntrans_max = 1;
+  int num_sms = B200_NUM_SMS;
   double eps = 1e-6, sigma = 2.0, beta = 0, cpar = 0;
 
   // device tables

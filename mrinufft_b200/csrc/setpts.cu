@@ -12,10 +12,12 @@
 // every step one IEEE-754 double operation rounded to nearest (explicit __d*_rn intrinsics, so
 // the compiler cannot contract them into FMAs).
 //
-// Bins are "pencils": one cell along every axis but the fastest, BX cells along the fastest
-// axis.  The key orders pencils so that, for a fixed slow origin and x-bin, consecutive middle
-// origins are consecutive keys (3-D: key = (o0 * nbx + bx) * nf1 + o1; 2-D: key = bx * nf0 + o0;
-// 1-D: key = bx).  The tiled spread/interp kernels rely on that order.
+// Bins are "pencils": one cell along every axis but the fastest, BX = 32 cells along the fastest
+// axis, each split in two sub-bins by `cross` (does the footprint leave the 32-cell tile?).  The key
+// orders them so that, for a fixed slow origin, x-tile and cross flag, consecutive middle origins
+// are consecutive keys (3-D: key = ((o0 * nbx + bx) * 2 + cross) * nf1 + o1;
+// 2-D: key = (bx * 2 + cross) * nf0 + o0; 1-D: key = bx).  The row kernels (spread_rows.cu) rely
+// on that order: the points visiting a grid row are a handful of contiguous key ranges.
 #include <cub/device/device_radix_sort.cuh>
 
 #include "common.cuh"
@@ -36,15 +38,19 @@ __device__ __forceinline__ void fold_one(float x, int nf, int w, int* origin, fl
   *origin = o;
 }
 
+// Bin key.  x-tiles of BX cells; `cross` = the footprint [ox, ox + w) leaves the point's own tile
+// (the last tile may be shorter than BX).
 __device__ __forceinline__ int make_key(const Geom& g, const int* o) {
-  if (g.dim == 3) {
-    int bx = o[2] / g.bin[2];
-    return (o[0] * g.nbins[2] + bx) * g.nf[1] + o[1];
-  } else if (g.dim == 2) {
-    int bx = o[1] / g.bin[1];
-    return bx * g.nf[0] + o[0];
-  }
-  return o[0] / g.bin[0];
+  if (g.dim == 1) return o[0] / g.bin[0];
+  const int ox = o[g.dim - 1];
+  const int BX = g.bin[g.dim - 1];
+  const int nfx = g.nf[g.dim - 1];
+  const int bx = ox / BX;
+  const int rest = nfx - bx * BX;
+  const int tlen = rest < BX ? rest : BX;
+  const int cross = (ox - bx * BX + g.w - 1 >= tlen) ? 1 : 0;
+  if (g.dim == 3) return ((o[0] * g.nbins[2] + bx) * 2 + cross) * g.nf[1] + o[1];
+  return (bx * 2 + cross) * g.nf[0] + o[0];
 }
 
 __global__ void __launch_bounds__(256)

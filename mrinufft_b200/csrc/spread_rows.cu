@@ -1,0 +1,793 @@
+// spread_rows.cu -- "method 2": output-owned, register-accumulating spreading (K2) and its
+// transpose for interpolation (K3), written for sm_100a.
+//
+// Why not the usual shared-memory sub-grid + atomicAdd design: a 3-D width-7 kernel needs 343
+// complex accumulations per point per coil; with 32 coils batched that is 1.8e11 float atomics per
+// transform, and on sm_100a a float atomicAdd on shared memory is an ATOMS.CAST.SPIN
+// compare-and-swap loop (checked with cuobjdump).  Shared memory cannot feed the FMA pipe either
+// (128 B/clk/SM against 128 FFMA/clk/SM).  The register file can.  So every fine-grid "row"
+//
+//        32 consecutive cells along the fastest axis at fixed slow coordinates (z, y), all coils
+//
+// is OWNED by one warp at a time and lives in REGISTERS: lane = coil, register i = cell i
+// (64 accumulators).  The points whose footprint covers the row ("visits") are found through the
+// bin sort of K1 without any search or filtering:
+//
+//   * bins are pencils of 1 x 1 x 32 cells, split in two sub-bins: points whose footprint stays
+//     inside the 32-cell tile ("interior") and points whose footprint crosses into the next tile
+//     ("crossing"); key order (z0, x-tile, crossing, y0);
+//   * the visits of row (z, y, tile) are therefore exactly 3 contiguous ranges of sorted points
+//     per slow-axis offset dz (own interior, own crossing, left neighbour's crossing), each
+//     spanning the w values y0 in [y-w+1, y]  (twice that when the range wraps periodically);
+//   * the ranges of a row are concatenated by a warp prefix sum; blocks of 16 visits are staged
+//     lane-parallel (one lane = one visit: load the point's weight record, form
+//     wx[0..w) * wy[dy] * wz[dz], write 32 bytes of shared memory) while the sample values of
+//     those 16 points for all coils stream in with cp.async (one coalesced 256-byte row per point
+//     from the (sorted point, coil) transposed k-space batch), double buffered;
+//   * the consume loop then costs 2 LDS.128 (weights, warp broadcast) + 1 LDS.64 (this lane's
+//     coil value) + a warp-uniform jump on the x offset + 2w FFMA into statically indexed
+//     registers per visit -- the FMA pipe is the intended bottleneck;
+//   * a row is written to HBM exactly once as full 256-byte coalesced stores per coil (through a
+//     shared-memory transpose): no memset of the oversampled grid, no halo flush, no atomics.
+//
+// Load balance: a trajectory like 3-D radial puts ~1e5 visits on the few rows through the k-space
+// centre.  Rows with more than CHUNK visits are split into several work items whose partial rows
+// are merged with vector red.global.add on a pre-zeroed row; all items are handed out dynamically
+// (groups of 4 neighbouring rows per atomic fetch, so a warp re-uses the point records it just
+// pulled into L1).
+//
+// Interpolation is the exact transpose: the warp loads its row into registers once (coalesced),
+// every visiting point takes its w-tap dot product from registers and adds the partial sum into
+// the (sorted point, coil) accumulator with one vector `red.global.add.v2.f32` per lane.
+//
+// Replaces finufft's spread/interp stage (call sites
+// src/mrinufft/operators/interfaces/finufft.py:69,76; algorithm docs/explanations/nufft.rst:253-309).
+#include <cub/device/device_scan.cuh>
+
+#include "common.cuh"
+#include "device_utils.cuh"
+
+namespace {
+
+constexpr int CX = 32;          // cells per row segment (== pencil-bin width, B200_BIN_X)
+constexpr int REC = 24;         // floats per point record: wx[7] xo | wy[7] y0 | wz[7] z0
+constexpr int BLK = 16;         // visits staged per block
+constexpr int WARPS = 4;        // warps per CTA
+constexpr int THREADS = WARPS * 32;
+constexpr int CHUNK = 4096;     // visits per work item
+constexpr int NSLOT = 64;       // range slots per row (2 per lane)
+constexpr int GROUP = 4;        // work items fetched per atomic
+
+constexpr int ITEM_EMPTY = -1;        // chunk field: row without visits
+constexpr int ITEM_SPLIT = 1 << 30;   // chunk flag: row is shared by several items
+
+// per-warp shared memory (bytes)
+constexpr int SM_VBUF = 2 * BLK * 32 * 8;   // double-buffered coil values of BLK points
+constexpr int SM_META = 2 * BLK * 32;       // double-buffered {w'[0..7) , off}
+constexpr int SM_SIDX = 2 * BLK * 4;        // sorted index of each staged visit (interp)
+constexpr int SM_SLOT = 2 * NSLOT * 4;      // pre[], begin[]
+constexpr int SM_WARP = SM_VBUF + SM_META + SM_SIDX + SM_SLOT;
+static_assert(SM_VBUF + SM_META >= 32 * 33 * 8, "transpose buffer must fit in vbuf+meta");
+
+struct RowsState {
+  float* d_rec = nullptr;        // [M][REC] per sorted point
+  float2* d_kt = nullptr;        // [M][32] transposed (sorted point, coil) k-space batch
+  size_t kt_bytes = 0;
+  int32_t* d_nchunks = nullptr;  // [nrows + 1]
+  int32_t* d_item_start = nullptr;  // [nrows + 1]
+  int2* d_items = nullptr;       // [nitems] {row, chunk | flags}
+  int32_t* d_split_rows = nullptr;
+  int* d_counters = nullptr;     // [0] work counter, [1] split-row counter
+  void* d_scan_tmp = nullptr;
+  size_t scan_tmp_bytes = 0;
+  long long nrows = 0, nitems = 0, nsplit = 0;
+  long long M = -1;
+  bool valid = false;
+};
+
+RowsState* state(b200_plan* p) {
+  if (!p->tiled) p->tiled = new RowsState();
+  return (RowsState*)p->tiled;
+}
+
+// ------------------------------------------------------------------------------ geometry helpers
+template <int DIM>
+__host__ __device__ __forceinline__ int num_xtiles(const Geom& g) {
+  return (g.nf[DIM - 1] + CX - 1) / CX;
+}
+
+template <int DIM>
+__host__ __device__ __forceinline__ long long num_rows(const Geom& g) {
+  const long long nyg = (g.nf[DIM - 2] + 3) / 4;
+  const long long nz = DIM == 3 ? g.nf[0] : 1;
+  return nz * nyg * num_xtiles<DIM>(g) * 4;
+}
+
+struct RowCoord {
+  int z, y, bx;
+  long long rowbase;  // linear index of (z, y, 0) in one coil's grid
+};
+
+// row id -> coordinates; order (z, y-group of 4, x-tile, y within group) so that the GROUP = 4
+// consecutive ids fetched together are 4 neighbouring y rows of the same tile.
+template <int DIM>
+__device__ __forceinline__ bool decode_row(const Geom& g, long long row, RowCoord* rc) {
+  const int nfx = g.nf[DIM - 1];
+  const int nfy = g.nf[DIM - 2];
+  const int nbx = num_xtiles<DIM>(g);
+  const int nyg = (nfy + 3) / 4;
+  const int ys = (int)(row & 3);
+  long long r = row >> 2;
+  rc->bx = (int)(r % nbx);
+  r /= nbx;
+  const int yg = (int)(r % nyg);
+  rc->z = (int)(r / nyg);
+  rc->y = yg * 4 + ys;
+  if (rc->y >= nfy) return false;
+  rc->rowbase = ((long long)rc->z * nfy + rc->y) * nfx;
+  return true;
+}
+
+// Range slot -> [begin, begin + len) in sorted point order.
+//   slot = ((dz * 3) + sub) * 2 + part ; sub 0: own interior, 1: own crossing, 2: left crossing ;
+//   part 0: y0 in [max(y-w+1, 0), y], part 1: the periodic wrap [y-w+1+nfy, nfy-1] (if any).
+template <int DIM, int W>
+__device__ __forceinline__ void slot_range(const Geom& g, const RowCoord& rc, int slot,
+                                           const int32_t* __restrict__ bin_start, int* begin,
+                                           int* len) {
+  constexpr int NZ = (DIM == 3) ? W : 1;
+  *begin = 0;
+  *len = 0;
+  if (slot >= NZ * 6) return;
+  const int part = slot & 1;
+  const int sub = (slot >> 1) % 3;
+  const int dz = (slot >> 1) / 3;
+  const int nfy = g.nf[DIM - 2];
+  const int nbx = num_xtiles<DIM>(g);
+  const int ylo = rc.y - (W - 1);
+  int a, b;
+  if (part == 0) {
+    a = ylo > 0 ? ylo : 0;
+    b = rc.y;
+  } else {
+    if (ylo >= 0) return;
+    a = ylo + nfy;
+    b = nfy - 1;
+  }
+  int z0 = 0;
+  if (DIM == 3) {
+    z0 = rc.z - dz;
+    if (z0 < 0) z0 += g.nf[0];
+  }
+  const int bxx = (sub == 2) ? (rc.bx == 0 ? nbx - 1 : rc.bx - 1) : rc.bx;
+  const int cross = sub != 0;
+  const long long kb = (((long long)z0 * nbx + bxx) * 2 + cross) * nfy;
+  const int s0 = __ldg(bin_start + kb + a);
+  *begin = s0;
+  *len = __ldg(bin_start + kb + b + 1) - s0;
+}
+
+// ------------------------------------------------------------------------------ pre-passes
+template <int W>
+__global__ void __launch_bounds__(256)
+k_point_records(Geom g, long long M, const float* __restrict__ poly,
+                const int32_t* __restrict__ o0, const int32_t* __restrict__ o1,
+                const int32_t* __restrict__ o2, const float* __restrict__ f0,
+                const float* __restrict__ f1, const float* __restrict__ f2,
+                float* __restrict__ rec) {
+  __shared__ float spoly[(B200_MAX_DEG + 1) * B200_MAX_W];
+  for (int i = threadIdx.x; i < (g.deg + 1) * W; i += blockDim.x) spoly[i] = poly[i];
+  __syncthreads();
+  long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= M) return;
+  // axis roles: x = fastest axis (dim-1), y = dim-2, z = dim-3
+  const int32_t* op[3] = {o0, o1, o2};
+  const float* fp[3] = {f0, f1, f2};
+  float out[REC];
+#pragma unroll
+  for (int i = 0; i < REC; ++i) out[i] = 0.f;
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {  // r = 0: x, 1: y, 2: z
+    const int a = g.dim - 1 - r;
+    if (a < 0) {
+      out[r * 8] = 1.f;  // unused axis: single unit tap
+      continue;
+    }
+    const float z = fmaf(2.f, fp[a][s], (float)(W - 1));
+#pragma unroll
+    for (int i = 0; i < W; ++i) {
+      float acc = spoly[g.deg * W + i];
+      for (int k = g.deg - 1; k >= 0; --k) acc = fmaf(acc, z, spoly[k * W + i]);
+      out[r * 8 + i] = acc;
+    }
+    int o = op[a][s];
+    if (r == 0) o = o % CX;  // x: offset inside the point's own tile
+    out[r * 8 + 7] = __int_as_float(o);
+  }
+  float4* dst = reinterpret_cast<float4*>(rec + s * REC);
+#pragma unroll
+  for (int q = 0; q < REC / 4; ++q)
+    dst[q] = make_float4(out[4 * q], out[4 * q + 1], out[4 * q + 2], out[4 * q + 3]);
+}
+
+// visits per row -> number of work items of the row (0 for ids outside the grid)
+template <int DIM, int W>
+__global__ void __launch_bounds__(256)
+k_row_chunks(Geom g, long long nrows, const int32_t* __restrict__ bin_start,
+             int32_t* __restrict__ nchunks) {
+  const long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (row > nrows) return;
+  if (row == nrows) {
+    nchunks[row] = 0;
+    return;
+  }
+  RowCoord rc;
+  if (!decode_row<DIM>(g, row, &rc)) {
+    nchunks[row] = 0;
+    return;
+  }
+  constexpr int NZ = (DIM == 3) ? W : 1;
+  long long total = 0;
+  for (int slot = 0; slot < NZ * 6; ++slot) {
+    int b, l;
+    slot_range<DIM, W>(g, rc, slot, bin_start, &b, &l);
+    total += l;
+  }
+  // rows without visits still get one (empty) item, flagged -1: the spreader writes their zeros
+  nchunks[row] = total == 0 ? -1 : (int32_t)((total + CHUNK - 1) / CHUNK);
+}
+
+__global__ void __launch_bounds__(256)
+k_abs_chunks(long long n, const int32_t* __restrict__ in, int32_t* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = in[i] < 0 ? 1 : in[i];
+}
+
+__global__ void __launch_bounds__(256)
+k_fill_items(long long nrows, const int32_t* __restrict__ nchunks,
+             const int32_t* __restrict__ item_start, int2* __restrict__ items,
+             int32_t* __restrict__ split_rows, int* __restrict__ split_counter) {
+  const long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= nrows) return;
+  const int n = nchunks[row];
+  const int at = item_start[row];
+  if (n < 0) {
+    items[at] = make_int2((int)row, ITEM_EMPTY);
+  } else if (n == 1) {
+    items[at] = make_int2((int)row, 0);
+  } else if (n > 1) {
+    for (int c = 0; c < n; ++c) items[at + c] = make_int2((int)row, c | ITEM_SPLIT);
+    split_rows[atomicAdd(split_counter, 1)] = (int32_t)row;
+  }
+}
+
+// kt[s][t] = ksp[t][perm[s]] * density[perm[s]]   (t < T; lanes t >= T are zero-filled)
+__global__ void __launch_bounds__(256)
+k_gather_kspace(long long M, int T, const int32_t* __restrict__ perm,
+                const float2* __restrict__ ksp, const float* __restrict__ density,
+                float2* __restrict__ kt) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long s = idx >> 5;
+  int t = (int)(idx & 31);
+  if (s >= M) return;
+  float2 v = make_float2(0.f, 0.f);
+  if (t < T) {
+    const int j = perm[s];
+    v = ksp[(long long)t * M + j];
+    if (density) {
+      const float d = density[j];
+      v.x *= d;
+      v.y *= d;
+    }
+  }
+  kt[s * 32 + t] = v;
+}
+
+// ksp[t][perm[s]] = scale * kt[s][t] (- obs[t][perm[s]])
+__global__ void __launch_bounds__(256)
+k_scatter_kspace(long long M, int T, const int32_t* __restrict__ perm,
+                 const float2* __restrict__ kt, float2* __restrict__ ksp, float scale,
+                 const float2* __restrict__ obs) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long s = idx >> 5;
+  int t = (int)(idx & 31);
+  if (s >= M || t >= T) return;
+  const int j = perm[s];
+  float2 v = kt[s * 32 + t];
+  v.x *= scale;
+  v.y *= scale;
+  const long long oi = (long long)t * M + j;
+  if (obs) {
+    const float2 y = obs[oi];
+    v.x -= y.x;
+    v.y -= y.y;
+  }
+  ksp[oi] = v;
+}
+
+// rows shared by several work items are accumulated with red.add: zero them first
+template <int DIM>
+__global__ void __launch_bounds__(128)
+k_zero_split_rows(Geom g, int T, long long nsplit, const int32_t* __restrict__ split_rows,
+                  float2* __restrict__ fw) {
+  const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (w >= nsplit) return;
+  RowCoord rc;
+  if (!decode_row<DIM>(g, split_rows[w], &rc)) return;
+  const int x = rc.bx * CX + lane;
+  if (x >= g.nf[DIM - 1]) return;
+  for (int t = 0; t < T; ++t) fw[(long long)t * g.nftot + rc.rowbase + x] = make_float2(0.f, 0.f);
+}
+
+// ------------------------------------------------------------------------------ row kernels
+template <int W, int OFF>
+__device__ __forceinline__ void taps_spread(float2 (&acc)[CX], const float (&wx)[8], float2 v) {
+#pragma unroll
+  for (int i = 0; i < W; ++i) {
+    if (OFF + i >= 0 && OFF + i < CX) {
+      acc[OFF + i].x = fmaf(v.x, wx[i], acc[OFF + i].x);
+      acc[OFF + i].y = fmaf(v.y, wx[i], acc[OFF + i].y);
+    }
+  }
+}
+
+template <int W, int OFF>
+__device__ __forceinline__ float2 taps_interp(const float2 (&acc)[CX], const float (&wx)[8]) {
+  float2 r = make_float2(0.f, 0.f);
+#pragma unroll
+  for (int i = 0; i < W; ++i) {
+    if (OFF + i >= 0 && OFF + i < CX) {
+      r.x = fmaf(acc[OFF + i].x, wx[i], r.x);
+      r.y = fmaf(acc[OFF + i].y, wx[i], r.y);
+    }
+  }
+  return r;
+}
+
+#define OFF_CASES(M_)                                                                           \
+  M_(-6) M_(-5) M_(-4) M_(-3) M_(-2) M_(-1) M_(0) M_(1) M_(2) M_(3) M_(4) M_(5) M_(6) M_(7)     \
+  M_(8) M_(9) M_(10) M_(11) M_(12) M_(13) M_(14) M_(15) M_(16) M_(17) M_(18) M_(19) M_(20)      \
+  M_(21) M_(22) M_(23) M_(24) M_(25) M_(26) M_(27) M_(28) M_(29) M_(30) M_(31)
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
+}
+
+// registers of one lane's visit between "issue" (loads in flight) and "finish" (meta written)
+struct Staged {
+  float4 a, b;   // wx[0..6], xo
+  float4 c, d;   // wy[0..6], y0
+  float wz;
+  int s;         // sorted point index, -1 if this lane has no visit in the block
+  int left_len;  // 0, or the length of the left tile for left-crossing visits
+};
+
+template <int DIM, int W, bool SPREAD>
+__global__ void __launch_bounds__(THREADS, 4)
+k_rows(Geom g, int T, long long nitems, const int2* __restrict__ items,
+       const int32_t* __restrict__ bin_start, const float* __restrict__ rec,
+       float2* __restrict__ kt, float2* __restrict__ fw, int* __restrict__ counter) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  unsigned char* wsm = smem_raw + (size_t)warp * SM_WARP;
+  float2* vbuf = reinterpret_cast<float2*>(wsm);                       // [2][BLK][32]
+  float4* meta = reinterpret_cast<float4*>(wsm + SM_VBUF);             // [2][BLK][2]
+  int* sidx = reinterpret_cast<int*>(wsm + SM_VBUF + SM_META);          // [2][BLK]
+  int* s_pre = reinterpret_cast<int*>(wsm + SM_VBUF + SM_META + SM_SIDX);  // [NSLOT]
+  int* s_beg = s_pre + NSLOT;                                           // [NSLOT]
+  float2* tbuf = reinterpret_cast<float2*>(wsm);                        // [32][33] transpose (aliases)
+
+  const int nfx = g.nf[DIM - 1];
+  const int nfy = g.nf[DIM - 2];
+  const int nbx = num_xtiles<DIM>(g);
+
+  for (;;) {
+    long long item0 = 0;
+    if (lane == 0) item0 = (long long)atomicAdd(counter, GROUP);
+    item0 = __shfl_sync(0xffffffffu, item0, 0);
+    if (item0 >= nitems) break;
+#pragma unroll 1
+    for (int gi = 0; gi < GROUP; ++gi) {
+      const long long item = item0 + gi;
+      if (item >= nitems) break;
+      const int2 it = __ldg(items + item);
+      RowCoord rc;
+      if (!decode_row<DIM>(g, it.x, &rc)) continue;
+      const int x = rc.bx * CX + lane;
+      const bool split = (it.y != ITEM_EMPTY) && (it.y & ITEM_SPLIT);
+
+      if (it.y == ITEM_EMPTY) {
+        if (SPREAD && x < nfx) {
+          float2* dst = fw + rc.rowbase + x;
+          for (int t = 0; t < T; ++t) dst[(long long)t * g.nftot] = make_float2(0.f, 0.f);
+        }
+        continue;
+      }
+      const int chunk = it.y & (ITEM_SPLIT - 1);
+
+      // ---- ranges of this row: 2 slots per lane, exclusive prefix sum over the 64 slots
+      int b0, l0, b1, l1;
+      slot_range<DIM, W>(g, rc, lane, bin_start, &b0, &l0);
+      slot_range<DIM, W>(g, rc, lane + 32, bin_start, &b1, &l1);
+      int inc0 = l0, inc1 = l1;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const int u0 = __shfl_up_sync(0xffffffffu, inc0, d);
+        const int u1 = __shfl_up_sync(0xffffffffu, inc1, d);
+        if (lane >= d) {
+          inc0 += u0;
+          inc1 += u1;
+        }
+      }
+      const int tot0 = __shfl_sync(0xffffffffu, inc0, 31);
+      const int total = tot0 + __shfl_sync(0xffffffffu, inc1, 31);
+      __syncwarp();
+      s_pre[lane] = inc0 - l0;
+      s_pre[lane + 32] = tot0 + inc1 - l1;
+      s_beg[lane] = b0;
+      s_beg[lane + 32] = b1;
+      __syncwarp();
+      const int v_lo = chunk * CHUNK;
+      const int v_hi = min(total, v_lo + CHUNK);
+      const int nblk = (v_hi - v_lo + BLK - 1) / BLK;
+      const int left_len = (rc.bx == 0) ? (nfx - (nbx - 1) * CX) : CX;
+
+      // ---- accumulators
+      float2 acc[CX];
+      if (SPREAD) {
+#pragma unroll
+        for (int i = 0; i < CX; ++i) acc[i] = make_float2(0.f, 0.f);
+      } else {
+        // load the row: coalesced per coil -> smem -> registers (lane = coil)
+        const float2* src = fw + rc.rowbase + x;
+#pragma unroll 8
+        for (int t = 0; t < 32; ++t) {
+          float2 v = make_float2(0.f, 0.f);
+          if (t < T && x < nfx) v = __ldg(src + (long long)t * g.nftot);
+          tbuf[t * 33 + lane] = v;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < CX; ++i) acc[i] = tbuf[lane * 33 + i];
+        __syncwarp();
+      }
+
+      // ---- staging helpers
+      auto stage_issue = [&](int blk, int buf, Staged& st) {
+        const int v = v_lo + blk * BLK + lane;
+        st.s = -1;
+        st.left_len = 0;
+        int dz = 0;
+        if (lane < BLK && v < v_hi) {
+          int pos = 0;
+#pragma unroll
+          for (int step = NSLOT / 2; step >= 1; step >>= 1)
+            if (s_pre[pos + step] <= v) pos += step;
+          st.s = s_beg[pos] + (v - s_pre[pos]);
+          const int sub = (pos >> 1) % 3;
+          dz = (pos >> 1) / 3;
+          if (sub == 2) st.left_len = left_len;
+          const float4* r = reinterpret_cast<const float4*>(rec + (long long)st.s * REC);
+          st.a = __ldg(r);
+          st.b = __ldg(r + 1);
+          st.c = __ldg(r + 2);
+          st.d = __ldg(r + 3);
+          st.wz = (DIM == 3) ? __ldg(rec + (long long)st.s * REC + 16 + dz) : 1.f;
+        }
+        if (SPREAD) {
+          // coil values of the block's points: 2 points per instruction, 16 bytes per lane
+          float2* vb = vbuf + buf * (BLK * 32);
+#pragma unroll
+          for (int i = 0; i < BLK / 2; ++i) {
+            const int kk = 2 * i + (lane >> 4);
+            const int sk = __shfl_sync(0xffffffffu, st.s, kk);
+            if (sk >= 0) cp_async16(vb + kk * 32 + (lane & 15) * 2, kt + (long long)sk * 32 + (lane & 15) * 2);
+          }
+          cp_async_commit();
+        }
+      };
+      auto stage_finish = [&](int buf, const Staged& st) {
+        if (st.s >= 0) {
+          int dy = rc.y - __float_as_int(st.d.w);
+          if (dy < 0) dy += nfy;
+          float wy = st.c.x;
+          wy = dy == 1 ? st.c.y : wy;
+          wy = dy == 2 ? st.c.z : wy;
+          wy = dy == 3 ? st.c.w : wy;
+          wy = dy == 4 ? st.d.x : wy;
+          wy = dy == 5 ? st.d.y : wy;
+          wy = dy == 6 ? st.d.z : wy;
+          const float wyz = wy * st.wz;
+          const int off = __float_as_int(st.b.w) - st.left_len;
+          float4* m = meta + (buf * BLK + lane) * 2;
+          m[0] = make_float4(st.a.x * wyz, st.a.y * wyz, st.a.z * wyz, st.a.w * wyz);
+          m[1] = make_float4(st.b.x * wyz, st.b.y * wyz, st.b.z * wyz, __int_as_float(off));
+          if (!SPREAD) sidx[buf * BLK + lane] = st.s;
+        }
+      };
+
+      Staged st;
+      if (nblk > 0) {
+        stage_issue(0, 0, st);
+        stage_finish(0, st);
+      }
+      for (int blk = 0; blk < nblk; ++blk) {
+        const int cur = blk & 1;
+        const bool more = blk + 1 < nblk;
+        if (more) stage_issue(blk + 1, cur ^ 1, st);
+        if (SPREAD) {
+          if (more) cp_async_wait<1>();
+          else cp_async_wait<0>();
+        }
+        __syncwarp();
+        const int n = min(BLK, v_hi - v_lo - blk * BLK);
+        const float4* m = meta + cur * BLK * 2;
+        const float2* vb = vbuf + cur * (BLK * 32) + lane;
+        const int* sx = sidx + cur * BLK;
+#pragma unroll 1
+        for (int k = 0; k < n; ++k) {
+          const float4 m0 = m[2 * k], m1 = m[2 * k + 1];
+          const float wx[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, 0.f};
+          const int off = __float_as_int(m1.w);
+          if (SPREAD) {
+            const float2 v = vb[k * 32];
+            switch (off) {
+#define CASE_(O) case O: if (O > -W) taps_spread<W, O>(acc, wx, v); break;
+              OFF_CASES(CASE_)
+#undef CASE_
+              default: break;
+            }
+          } else {
+            float2 p = make_float2(0.f, 0.f);
+            switch (off) {
+#define CASE_(O) case O: if (O > -W) p = taps_interp<W, O>(acc, wx); break;
+              OFF_CASES(CASE_)
+#undef CASE_
+              default: break;
+            }
+            if (lane < T) atomicAdd(kt + (long long)sx[k] * 32 + lane, p);
+          }
+        }
+        if (more) stage_finish(cur ^ 1, st);
+        __syncwarp();
+      }
+
+      if (SPREAD) {
+        // flush: registers (lane = coil, i = cell) -> smem transpose -> coalesced rows per coil
+#pragma unroll
+        for (int i = 0; i < CX; ++i) tbuf[lane * 33 + i] = acc[i];
+        __syncwarp();
+        if (x < nfx) {
+          float2* dst = fw + rc.rowbase + x;
+          if (split) {
+            for (int t = 0; t < T; ++t) atomicAdd(dst + (long long)t * g.nftot, tbuf[t * 33 + lane]);
+          } else {
+            for (int t = 0; t < T; ++t) dst[(long long)t * g.nftot] = tbuf[t * 33 + lane];
+          }
+        }
+        __syncwarp();
+      }
+    }
+  }
+}
+
+template <int DIM, int W>
+int build_items(b200_plan* p, RowsState* ts, cudaStream_t st) {
+  const long long nrows = num_rows<DIM>(p->g);
+  if (nrows >= (1LL << 31) - 2) {
+    b200_set_error("too many grid rows (%lld) for the row kernels", nrows);
+    return B200_EINVAL;
+  }
+  auto fr = [](void* q) {
+    if (q) cudaFree(q);
+  };
+  if (ts->nrows != nrows) {
+    fr(ts->d_nchunks);
+    fr(ts->d_item_start);
+    ts->d_nchunks = ts->d_item_start = nullptr;
+    CUDA_TRY(cudaMalloc(&ts->d_nchunks, (size_t)(nrows + 1) * 4));
+    CUDA_TRY(cudaMalloc(&ts->d_item_start, (size_t)(nrows + 1) * 4));
+    ts->nrows = nrows;
+  }
+  k_row_chunks<DIM, W><<<ceil_div(nrows + 1, 256), 256, 0, st>>>(p->g, nrows, p->d_bin_start,
+                                                                 ts->d_nchunks);
+  CHECK_LAUNCH();
+  // item_start = exclusive scan of |nchunks| (an empty row still owns one item)
+  k_abs_chunks<<<ceil_div(nrows + 1, 256), 256, 0, st>>>(nrows + 1, ts->d_nchunks, ts->d_item_start);
+  CHECK_LAUNCH();
+  size_t need = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, need, ts->d_item_start, ts->d_item_start, (int)(nrows + 1), st);
+  if (need > ts->scan_tmp_bytes) {
+    fr(ts->d_scan_tmp);
+    ts->d_scan_tmp = nullptr;
+    CUDA_TRY(cudaMalloc(&ts->d_scan_tmp, need));
+    ts->scan_tmp_bytes = need;
+  }
+  CUDA_TRY(cub::DeviceScan::ExclusiveSum(ts->d_scan_tmp, need, ts->d_item_start, ts->d_item_start,
+                                         (int)(nrows + 1), st));
+  g_kernel_launches += 2;
+  int32_t nitems = 0;
+  CUDA_TRY(cudaMemcpyAsync(&nitems, ts->d_item_start + nrows, 4, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  fr(ts->d_items);
+  fr(ts->d_split_rows);
+  ts->d_items = nullptr;
+  ts->d_split_rows = nullptr;
+  CUDA_TRY(cudaMalloc(&ts->d_items, (size_t)(nitems > 0 ? nitems : 1) * sizeof(int2)));
+  CUDA_TRY(cudaMalloc(&ts->d_split_rows, (size_t)(nitems / 2 + 1) * 4));
+  CUDA_TRY(cudaMemsetAsync(ts->d_counters, 0, 64, st));
+  k_fill_items<<<ceil_div(nrows, 256), 256, 0, st>>>(nrows, ts->d_nchunks, ts->d_item_start,
+                                                     ts->d_items, ts->d_split_rows,
+                                                     ts->d_counters + 1);
+  CHECK_LAUNCH();
+  int nsplit = 0;
+  CUDA_TRY(cudaMemcpyAsync(&nsplit, ts->d_counters + 1, 4, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  ts->nitems = nitems;
+  ts->nsplit = nsplit;
+  return B200_OK;
+}
+
+template <int DIM, int W>
+int prepare(b200_plan* p, RowsState* ts, cudaStream_t st) {
+  const long long M = p->M;
+  if (!ts->d_counters) CUDA_TRY(cudaMalloc(&ts->d_counters, 64));
+  if (ts->d_rec) cudaFree(ts->d_rec);
+  ts->d_rec = nullptr;
+  CUDA_TRY(cudaMalloc(&ts->d_rec, (size_t)(M > 0 ? M : 1) * REC * sizeof(float)));
+  if (M > 0) {
+    k_point_records<W><<<ceil_div(M, 256), 256, 0, st>>>(
+        p->g, M, p->d_poly, p->d_org_s[0], p->d_org_s[1], p->d_org_s[2], p->d_x1_s[0],
+        p->d_x1_s[1], p->d_x1_s[2], ts->d_rec);
+    CHECK_LAUNCH();
+  }
+  B200_TRY((build_items<DIM, W>(p, ts, st)));
+  ts->M = M;
+  ts->valid = true;
+  return B200_OK;
+}
+
+template <int DIM, int W, bool SPREAD>
+int launch_rows(b200_plan* p, RowsState* ts, float2* fw, int T, cudaStream_t st) {
+  auto kern = k_rows<DIM, W, SPREAD>;
+  const size_t smem = (size_t)WARPS * SM_WARP;
+  static bool attr_done = false;
+  static int ctas_per_sm = 1;
+  if (!attr_done) {
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, THREADS, smem));
+    if (ctas_per_sm < 1) ctas_per_sm = 1;
+    attr_done = true;
+  }
+  if (SPREAD && ts->nsplit > 0) {
+    k_zero_split_rows<DIM><<<ceil_div(ts->nsplit * 32, 128), 128, 0, st>>>(p->g, T, ts->nsplit,
+                                                                         ts->d_split_rows, fw);
+    CHECK_LAUNCH();
+  }
+  CUDA_TRY(cudaMemsetAsync(ts->d_counters, 0, sizeof(int), st));
+  const long long want = (ts->nitems + GROUP * WARPS - 1) / (GROUP * WARPS);
+  const long long cap = (long long)p->num_sms * ctas_per_sm;
+  const int grid = (int)(want < cap ? (want > 0 ? want : 1) : cap);
+  kern<<<grid, THREADS, smem, st>>>(p->g, T, ts->nitems, ts->d_items, p->d_bin_start, ts->d_rec,
+                                    ts->d_kt, fw, ts->d_counters);
+  CHECK_LAUNCH();
+  return B200_OK;
+}
+
+int ensure_kt(RowsState* ts, long long M) {
+  const size_t need = (size_t)(M > 0 ? M : 1) * 32 * sizeof(float2);
+  if (ts->kt_bytes < need) {
+    if (ts->d_kt) cudaFree(ts->d_kt);
+    ts->d_kt = nullptr;
+    ts->kt_bytes = 0;
+    CUDA_TRY(cudaMalloc(&ts->d_kt, need));
+    ts->kt_bytes = need;
+  }
+  return B200_OK;
+}
+
+}  // namespace
+
+bool tiled_supported(const b200_plan* p, int T) {
+  const Geom& g = p->g;
+  if (g.dim < 2 || g.dim > 3) return false;
+  if (g.w < 4 || g.w > 7) return false;
+  if (T > 32) return false;
+  const int nfx = g.nf[g.dim - 1];
+  const int rem = nfx % CX;
+  if (rem != 0 && rem < g.w - 1) return false;  // a footprint may touch at most two tiles
+  for (int a = 0; a < g.dim; ++a)
+    if (g.nf[a] < 2 * g.w) return false;
+  return true;
+}
+
+void tiled_free(b200_plan* p) {
+  if (!p->tiled) return;
+  RowsState* ts = (RowsState*)p->tiled;
+  auto fr = [](void* q) {
+    if (q) cudaFree(q);
+  };
+  fr(ts->d_rec);
+  fr(ts->d_kt);
+  fr(ts->d_nchunks);
+  fr(ts->d_item_start);
+  fr(ts->d_items);
+  fr(ts->d_split_rows);
+  fr(ts->d_counters);
+  fr(ts->d_scan_tmp);
+  delete ts;
+  p->tiled = nullptr;
+}
+
+#define DISPATCH_DW(FN, ...)                                   \
+  do {                                                         \
+    const int d_ = p->g.dim, w_ = p->g.w;                      \
+    if (d_ == 3) {                                             \
+      if (w_ == 7) return FN<3, 7>(__VA_ARGS__);               \
+      if (w_ == 6) return FN<3, 6>(__VA_ARGS__);               \
+      if (w_ == 5) return FN<3, 5>(__VA_ARGS__);               \
+      return FN<3, 4>(__VA_ARGS__);                            \
+    } else {                                                   \
+      if (w_ == 7) return FN<2, 7>(__VA_ARGS__);               \
+      if (w_ == 6) return FN<2, 6>(__VA_ARGS__);               \
+      if (w_ == 5) return FN<2, 5>(__VA_ARGS__);               \
+      return FN<2, 4>(__VA_ARGS__);                            \
+    }                                                          \
+  } while (0)
+
+#define DISPATCH_DWS(FN, S, ...)                               \
+  do {                                                         \
+    const int d_ = p->g.dim, w_ = p->g.w;                      \
+    if (d_ == 3) {                                             \
+      if (w_ == 7) return FN<3, 7, S>(__VA_ARGS__);            \
+      if (w_ == 6) return FN<3, 6, S>(__VA_ARGS__);            \
+      if (w_ == 5) return FN<3, 5, S>(__VA_ARGS__);            \
+      return FN<3, 4, S>(__VA_ARGS__);                         \
+    } else {                                                   \
+      if (w_ == 7) return FN<2, 7, S>(__VA_ARGS__);            \
+      if (w_ == 6) return FN<2, 6, S>(__VA_ARGS__);            \
+      if (w_ == 5) return FN<2, 5, S>(__VA_ARGS__);            \
+      return FN<2, 4, S>(__VA_ARGS__);                         \
+    }                                                          \
+  } while (0)
+
+static int ensure_state(b200_plan* p, cudaStream_t st) {
+  RowsState* ts = state(p);
+  if (ts->valid && ts->M == p->M) return B200_OK;
+  DISPATCH_DW(prepare, p, ts, st);
+}
+
+int spread_tiled(b200_plan* p, const float2* ksp, const float* density, float2* fw, int T,
+                 cudaStream_t st) {
+  B200_TRY(ensure_state(p, st));
+  RowsState* ts = state(p);
+  const long long M = p->M;
+  B200_TRY(ensure_kt(ts, M));
+  if (M > 0) {
+    k_gather_kspace<<<ceil_div(M * 32, 256), 256, 0, st>>>(M, T, p->d_perm, ksp, density, ts->d_kt);
+    CHECK_LAUNCH();
+  }
+  DISPATCH_DWS(launch_rows, true, p, ts, fw, T, st);
+}
+
+int interp_tiled(b200_plan* p, const float2* fw, float2* ksp, int T, float scale,
+                 const float2* obs, cudaStream_t st) {
+  B200_TRY(ensure_state(p, st));
+  RowsState* ts = state(p);
+  const long long M = p->M;
+  if (M == 0) return B200_OK;
+  B200_TRY(ensure_kt(ts, M));
+  CUDA_TRY(cudaMemsetAsync(ts->d_kt, 0, (size_t)M * 32 * sizeof(float2), st));
+  int rc = [&]() -> int { DISPATCH_DWS(launch_rows, false, p, ts, const_cast<float2*>(fw), T, st); }();
+  if (rc != B200_OK) return rc;
+  k_scatter_kspace<<<ceil_div(M * 32, 256), 256, 0, st>>>(M, T, p->d_perm, ts->d_kt, ksp, scale, obs);
+  CHECK_LAUNCH();
+  return B200_OK;
+}

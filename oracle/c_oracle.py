@@ -87,7 +87,7 @@ class CpuNufft:
         for a in range(self.d):
             self.origin[a], self.x1[a] = fold(self.samples[:, a], self.nfs[a], self.w)
         bins = bins or E.default_bins(self.d)
-        key = E.make_key(self.origin, self.nfs, bins)
+        key = E.make_key(self.origin, self.nfs, bins, self.w)
         self.perm = np.argsort(key, kind="stable").astype(np.int32)
         self._mode_idx = [(np.arange(n) - n // 2) % nf for n, nf in zip(self.shape, self.nfs)]
 

@@ -357,7 +357,7 @@ def test_pipe_matches_cpu_oracle(mods):
         from oracle.c_oracle import fold
 
         cpu.origin[a], cpu.x1[a] = fold(samples[:, a], shape[a], cpu.w)
-    cpu.perm = np.argsort(E.make_key(cpu.origin, shape, E.default_bins(2)), kind="stable").astype(np.int32)
+    cpu.perm = np.argsort(E.make_key(cpu.origin, shape, E.default_bins(2), cpu.w), kind="stable").astype(np.int32)
     dd = np.ones(len(samples))
     norm2 = np.prod(shape) * 4.0
     for _ in range(10):
