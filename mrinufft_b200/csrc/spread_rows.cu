@@ -63,10 +63,9 @@ constexpr int ITEM_SPLIT = 1 << 30;   // chunk flag: row is shared by several it
 
 // per-warp shared memory (bytes)
 constexpr int SM_VBUF = 2 * BLK * 32 * 8;   // double-buffered coil values of BLK points
-constexpr int SM_META = 2 * BLK * 32;       // double-buffered {w'[0..7) , off}
-constexpr int SM_SIDX = 2 * BLK * 4;        // sorted index of each staged visit (interp)
+constexpr int SM_META = 2 * BLK * 64;       // double-buffered {(w'[i], w'[i]) i < 7, idx, s}
 constexpr int SM_SLOT = 2 * NSLOT * 4;      // pre[], begin[]
-constexpr int SM_WARP = SM_VBUF + SM_META + SM_SIDX + SM_SLOT;
+constexpr int SM_WARP = SM_VBUF + SM_META + SM_SLOT;
 static_assert(SM_VBUF + SM_META >= 32 * 33 * 8, "transpose buffer must fit in vbuf+meta");
 
 struct RowsState {
@@ -321,34 +320,43 @@ k_zero_split_rows(Geom g, int T, long long nsplit, const int32_t* __restrict__ s
 }
 
 // ------------------------------------------------------------------------------ row kernels
-template <int W, int OFF>
-__device__ __forceinline__ void taps_spread(float2 (&acc)[CX], const float (&wx)[8], float2 v) {
-#pragma unroll
-  for (int i = 0; i < W; ++i) {
-    if (OFF + i >= 0 && OFF + i < CX) {
-      acc[OFF + i].x = fmaf(v.x, wx[i], acc[OFF + i].x);
-      acc[OFF + i].y = fmaf(v.y, wx[i], acc[OFF + i].y);
-    }
-  }
+// Per-visit tap kernels: generated inline PTX (tools/gen_taps.py) -- one `brx.idx` on the x offset,
+// then w packed `fma.rn.f32x2` (SASS FFMA2) on statically indexed 64-bit (re, im) accumulators.
+// A C++ `switch` is lowered by nvcc to a compare/branch tree that cost 17 issue slots per visit.
+typedef unsigned long long u64;
+#include "taps_generated.inc"
+
+template <int W>
+__device__ __forceinline__ void taps_spread(u64 (&acc)[CX], unsigned idx, const u64 (&w)[8], u64 v) {
+  if (W == 7) taps_spread_w7(acc, idx, w, v);
+  else if (W == 6) taps_spread_w6(acc, idx, w, v);
+  else if (W == 5) taps_spread_w5(acc, idx, w, v);
+  else taps_spread_w4(acc, idx, w, v);
+}
+template <int W>
+__device__ __forceinline__ u64 taps_interp(const u64 (&acc)[CX], unsigned idx, const u64 (&w)[8]) {
+  if (W == 7) return taps_interp_w7(acc, idx, w);
+  if (W == 6) return taps_interp_w6(acc, idx, w);
+  if (W == 5) return taps_interp_w5(acc, idx, w);
+  return taps_interp_w4(acc, idx, w);
 }
 
-template <int W, int OFF>
-__device__ __forceinline__ float2 taps_interp(const float2 (&acc)[CX], const float (&wx)[8]) {
-  float2 r = make_float2(0.f, 0.f);
-#pragma unroll
-  for (int i = 0; i < W; ++i) {
-    if (OFF + i >= 0 && OFF + i < CX) {
-      r.x = fmaf(acc[OFF + i].x, wx[i], r.x);
-      r.y = fmaf(acc[OFF + i].y, wx[i], r.y);
-    }
-  }
-  return r;
+__device__ __forceinline__ u64 pack2(float lo, float hi) {
+  return ((u64)__float_as_uint(hi) << 32) | (u64)__float_as_uint(lo);
 }
 
-#define OFF_CASES(M_)                                                                           \
-  M_(-6) M_(-5) M_(-4) M_(-3) M_(-2) M_(-1) M_(0) M_(1) M_(2) M_(3) M_(4) M_(5) M_(6) M_(7)     \
-  M_(8) M_(9) M_(10) M_(11) M_(12) M_(13) M_(14) M_(15) M_(16) M_(17) M_(18) M_(19) M_(20)      \
-  M_(21) M_(22) M_(23) M_(24) M_(25) M_(26) M_(27) M_(28) M_(29) M_(30) M_(31)
+// kt[addr] += p for lanes with pred != 0 (vector reduction, no branch)
+__device__ __forceinline__ void red_add_f32x2(float2* addr, u64 p, int pred) {
+  asm volatile(
+      "{\n"
+      ".reg .pred q;\n"
+      ".reg .f32 lo, hi;\n"
+      "setp.ne.s32 q, %2, 0;\n"
+      "mov.b64 {lo, hi}, %1;\n"
+      "@q red.global.add.v2.f32 [%0], {lo, hi};\n"
+      "}\n" ::"l"(addr), "l"(p), "r"(pred)
+      : "memory");
+}
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
   const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -377,16 +385,16 @@ k_rows(Geom g, int T, long long nitems, const int2* __restrict__ items,
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   unsigned char* wsm = smem_raw + (size_t)warp * SM_WARP;
-  float2* vbuf = reinterpret_cast<float2*>(wsm);                       // [2][BLK][32]
-  float4* meta = reinterpret_cast<float4*>(wsm + SM_VBUF);             // [2][BLK][2]
-  int* sidx = reinterpret_cast<int*>(wsm + SM_VBUF + SM_META);          // [2][BLK]
-  int* s_pre = reinterpret_cast<int*>(wsm + SM_VBUF + SM_META + SM_SIDX);  // [NSLOT]
+  u64* vbuf = reinterpret_cast<u64*>(wsm);                              // [2][BLK][32] (re, im)
+  ulonglong2* meta = reinterpret_cast<ulonglong2*>(wsm + SM_VBUF);      // [2][BLK][4]
+  int* s_pre = reinterpret_cast<int*>(wsm + SM_VBUF + SM_META);         // [NSLOT]
   int* s_beg = s_pre + NSLOT;                                           // [NSLOT]
-  float2* tbuf = reinterpret_cast<float2*>(wsm);                        // [32][33] transpose (aliases)
+  u64* tbuf = reinterpret_cast<u64*>(wsm);                              // [32][33] transpose (aliases)
 
   const int nfx = g.nf[DIM - 1];
   const int nfy = g.nf[DIM - 2];
   const int nbx = num_xtiles<DIM>(g);
+  u64* fw64 = reinterpret_cast<u64*>(fw);
 
   for (;;) {
     long long item0 = 0;
@@ -405,8 +413,8 @@ k_rows(Geom g, int T, long long nitems, const int2* __restrict__ items,
 
       if (it.y == ITEM_EMPTY) {
         if (SPREAD && x < nfx) {
-          float2* dst = fw + rc.rowbase + x;
-          for (int t = 0; t < T; ++t) dst[(long long)t * g.nftot] = make_float2(0.f, 0.f);
+          u64* dst = fw64 + rc.rowbase + x;
+          for (int t = 0; t < T; ++t) dst[(long long)t * g.nftot] = 0ull;
         }
         continue;
       }
@@ -439,17 +447,17 @@ k_rows(Geom g, int T, long long nitems, const int2* __restrict__ items,
       const int nblk = (v_hi - v_lo + BLK - 1) / BLK;
       const int left_len = (rc.bx == 0) ? (nfx - (nbx - 1) * CX) : CX;
 
-      // ---- accumulators
-      float2 acc[CX];
+      // ---- accumulators: acc[i] = packed (re, im) of cell i for this lane's coil
+      u64 acc[CX];
       if (SPREAD) {
 #pragma unroll
-        for (int i = 0; i < CX; ++i) acc[i] = make_float2(0.f, 0.f);
+        for (int i = 0; i < CX; ++i) acc[i] = 0ull;
       } else {
         // load the row: coalesced per coil -> smem -> registers (lane = coil)
-        const float2* src = fw + rc.rowbase + x;
+        const u64* src = fw64 + rc.rowbase + x;
 #pragma unroll 8
         for (int t = 0; t < 32; ++t) {
-          float2 v = make_float2(0.f, 0.f);
+          u64 v = 0ull;
           if (t < T && x < nfx) v = __ldg(src + (long long)t * g.nftot);
           tbuf[t * 33 + lane] = v;
         }
@@ -483,12 +491,13 @@ k_rows(Geom g, int T, long long nitems, const int2* __restrict__ items,
         }
         if (SPREAD) {
           // coil values of the block's points: 2 points per instruction, 16 bytes per lane
-          float2* vb = vbuf + buf * (BLK * 32);
+          u64* vb = vbuf + buf * (BLK * 32);
 #pragma unroll
           for (int i = 0; i < BLK / 2; ++i) {
             const int kk = 2 * i + (lane >> 4);
             const int sk = __shfl_sync(0xffffffffu, st.s, kk);
-            if (sk >= 0) cp_async16(vb + kk * 32 + (lane & 15) * 2, kt + (long long)sk * 32 + (lane & 15) * 2);
+            if (sk >= 0)
+              cp_async16(vb + kk * 32 + (lane & 15) * 2, kt + (long long)sk * 32 + (lane & 15) * 2);
           }
           cp_async_commit();
         }
@@ -505,11 +514,14 @@ k_rows(Geom g, int T, long long nitems, const int2* __restrict__ items,
           wy = dy == 5 ? st.d.y : wy;
           wy = dy == 6 ? st.d.z : wy;
           const float wyz = wy * st.wz;
-          const int off = __float_as_int(st.b.w) - st.left_len;
-          float4* m = meta + (buf * BLK + lane) * 2;
-          m[0] = make_float4(st.a.x * wyz, st.a.y * wyz, st.a.z * wyz, st.a.w * wyz);
-          m[1] = make_float4(st.b.x * wyz, st.b.y * wyz, st.b.z * wyz, __int_as_float(off));
-          if (!SPREAD) sidx[buf * BLK + lane] = st.s;
+          const unsigned idx = (unsigned)(__float_as_int(st.b.w) - st.left_len + (W - 1));
+          const float w0 = st.a.x * wyz, w1 = st.a.y * wyz, w2 = st.a.z * wyz, w3 = st.a.w * wyz;
+          const float w4 = st.b.x * wyz, w5 = st.b.y * wyz, w6 = st.b.z * wyz;
+          ulonglong2* m = meta + (buf * BLK + lane) * 4;
+          m[0] = make_ulonglong2(pack2(w0, w0), pack2(w1, w1));
+          m[1] = make_ulonglong2(pack2(w2, w2), pack2(w3, w3));
+          m[2] = make_ulonglong2(pack2(w4, w4), pack2(w5, w5));
+          m[3] = make_ulonglong2(pack2(w6, w6), ((u64)(unsigned)st.s << 32) | (u64)idx);
         }
       };
 
@@ -528,31 +540,19 @@ k_rows(Geom g, int T, long long nitems, const int2* __restrict__ items,
         }
         __syncwarp();
         const int n = min(BLK, v_hi - v_lo - blk * BLK);
-        const float4* m = meta + cur * BLK * 2;
-        const float2* vb = vbuf + cur * (BLK * 32) + lane;
-        const int* sx = sidx + cur * BLK;
+        const ulonglong2* m = meta + cur * BLK * 4;
+        const u64* vb = vbuf + cur * (BLK * 32) + lane;
 #pragma unroll 1
         for (int k = 0; k < n; ++k) {
-          const float4 m0 = m[2 * k], m1 = m[2 * k + 1];
-          const float wx[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, 0.f};
-          const int off = __float_as_int(m1.w);
+          const ulonglong2 m0 = m[4 * k], m1 = m[4 * k + 1], m2 = m[4 * k + 2], m3 = m[4 * k + 3];
+          const u64 wx[8] = {m0.x, m0.y, m1.x, m1.y, m2.x, m2.y, m3.x, 0ull};
+          const unsigned idx = (unsigned)m3.y;
           if (SPREAD) {
-            const float2 v = vb[k * 32];
-            switch (off) {
-#define CASE_(O) case O: if (O > -W) taps_spread<W, O>(acc, wx, v); break;
-              OFF_CASES(CASE_)
-#undef CASE_
-              default: break;
-            }
+            taps_spread<W>(acc, idx, wx, vb[k * 32]);
           } else {
-            float2 p = make_float2(0.f, 0.f);
-            switch (off) {
-#define CASE_(O) case O: if (O > -W) p = taps_interp<W, O>(acc, wx); break;
-              OFF_CASES(CASE_)
-#undef CASE_
-              default: break;
-            }
-            if (lane < T) atomicAdd(kt + (long long)sx[k] * 32 + lane, p);
+            const u64 p = taps_interp<W>(acc, idx, wx);
+            const long long s = (long long)(m3.y >> 32);
+            red_add_f32x2(kt + s * 32 + lane, p, lane < T);
           }
         }
         if (more) stage_finish(cur ^ 1, st);
@@ -565,10 +565,12 @@ k_rows(Geom g, int T, long long nitems, const int2* __restrict__ items,
         for (int i = 0; i < CX; ++i) tbuf[lane * 33 + i] = acc[i];
         __syncwarp();
         if (x < nfx) {
-          float2* dst = fw + rc.rowbase + x;
+          u64* dst = fw64 + rc.rowbase + x;
           if (split) {
-            for (int t = 0; t < T; ++t) atomicAdd(dst + (long long)t * g.nftot, tbuf[t * 33 + lane]);
+            for (int t = 0; t < T; ++t)
+              red_add_f32x2(reinterpret_cast<float2*>(dst + (long long)t * g.nftot), tbuf[t * 33 + lane], 1);
           } else {
+#pragma unroll 4
             for (int t = 0; t < T; ++t) dst[(long long)t * g.nftot] = tbuf[t * 33 + lane];
           }
         }
