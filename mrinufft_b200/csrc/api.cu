@@ -94,6 +94,36 @@ int do_interp(b200_plan* p, const float2* fw, float2* ksp, int T, float scale, c
   return interp_point_driven(p, fw, ksp, T, scale, obs, st);
 }
 
+bool use_fftp(const b200_plan* p) {
+  return p->fft_method != 1 && fftp_supported(p);
+}
+
+// image(s) -> transformed oversampled grid (K4a + FFT)
+int image_to_grid(b200_plan* p, const float2* img, const float2* smaps, int T, int isign,
+                  int conj_smaps, cudaStream_t st) {
+  if (use_fftp(p)) {
+    Timed tm(p, EV_FFT, st);
+    return fftp_type2(p, img, smaps, p->d_fw, T, isign, conj_smaps, st);
+  }
+  {
+    Timed tm(p, EV_GRID, st);
+    B200_TRY(k4a_pad(p, img, smaps, p->d_fw, T, conj_smaps, st));
+  }
+  return exec_fft(p, p->d_fw, T, isign, st);
+}
+
+// spread oversampled grid -> image(s) (FFT + K4b)
+int grid_to_image(b200_plan* p, const float2* smaps, float2* img, int T, int accumulate, int isign,
+                  float scale, int conj_smaps, cudaStream_t st) {
+  if (use_fftp(p)) {
+    Timed tm(p, EV_FFT, st);
+    return fftp_type1(p, p->d_fw, smaps, img, T, accumulate, isign, scale, conj_smaps, st);
+  }
+  B200_TRY(exec_fft(p, p->d_fw, T, isign, st));
+  Timed tm(p, EV_GRID, st);
+  return k4b_crop(p, p->d_fw, smaps, img, T, accumulate, scale, conj_smaps, st);
+}
+
 int check_exec(b200_plan* p, int T, bool need_fft) {
   if (!p) {
     b200_set_error("null plan");
@@ -294,6 +324,7 @@ int b200_plan_destroy(b200_plan* p) {
   fr(p->d_poly);
   for (int a = 0; a < 3; ++a) {
     fr(p->d_deapod[a]);
+    fr(p->d_tw[a]);
     fr(p->d_org_u[a]);
     fr(p->d_x1_u[a]);
     fr(p->d_org_s[a]);
@@ -354,6 +385,7 @@ int b200_plan_set_option(b200_plan* p, int key, int64_t value) {
   switch (key) {
     case 0: p->spread_method = (int)value; break;
     case 1: p->interp_method = (int)value; break;
+    case 2: p->fft_method = (int)value; break;
     default:
       b200_set_error("unknown option key %d", key);
       return B200_EINVAL;
@@ -435,11 +467,7 @@ int b200_type2(b200_plan* p, const void* img, const void* smaps, void* ksp, int 
   }
   DeviceGuard guard(p->device);
   cudaStream_t st = (cudaStream_t)stream;
-  {
-    Timed tm(p, EV_GRID, st);
-    B200_TRY(k4a_pad(p, (const float2*)img, (const float2*)smaps, p->d_fw, T, conj_smaps, st));
-  }
-  B200_TRY(exec_fft(p, p->d_fw, T, isign, st));
+  B200_TRY(image_to_grid(p, (const float2*)img, (const float2*)smaps, T, isign, conj_smaps, st));
   return do_interp(p, p->d_fw, (float2*)ksp, T, scale, nullptr, st);
 }
 
@@ -453,10 +481,8 @@ int b200_type1(b200_plan* p, const void* ksp, const float* density, const void* 
   DeviceGuard guard(p->device);
   cudaStream_t st = (cudaStream_t)stream;
   B200_TRY(do_spread(p, (const float2*)ksp, density, p->d_fw, T, st));
-  B200_TRY(exec_fft(p, p->d_fw, T, isign, st));
-  Timed tm(p, EV_GRID, st);
-  return k4b_crop(p, p->d_fw, (const float2*)smaps, (float2*)img, T, accumulate, scale,
-                  conj_smaps, st);
+  return grid_to_image(p, (const float2*)smaps, (float2*)img, T, accumulate, isign, scale, conj_smaps,
+                       st);
 }
 
 int b200_data_consistency(b200_plan* p, const void* img, const void* smaps, const void* obs,
@@ -473,13 +499,11 @@ int b200_data_consistency(b200_plan* p, const void* img, const void* smaps, cons
     CUDA_TRY(cudaMalloc(&p->d_ksp_tmp,
                         (size_t)p->ntrans_max * (size_t)(p->M > 0 ? p->M : 1) * sizeof(float2)));
   }
-  B200_TRY(k4a_pad(p, (const float2*)img, (const float2*)smaps, p->d_fw, T, 0, st));
-  B200_TRY(exec_fft(p, p->d_fw, T, -1, st));
+  B200_TRY(image_to_grid(p, (const float2*)img, (const float2*)smaps, T, -1, 0, st));
   // K5: residual fused into the interpolation epilogue
   B200_TRY(do_interp(p, p->d_fw, p->d_ksp_tmp, T, scale, (const float2*)obs, st));
   B200_TRY(do_spread(p, p->d_ksp_tmp, density, p->d_fw, T, st));
-  B200_TRY(exec_fft(p, p->d_fw, T, +1, st));
-  return k4b_crop(p, p->d_fw, (const float2*)smaps, (float2*)grad, T, accumulate, scale, 0, st);
+  return grid_to_image(p, (const float2*)smaps, (float2*)grad, T, accumulate, +1, scale, 0, st);
 }
 
 int b200_spread(b200_plan* p, const void* ksp, void* grid, int T, void* stream) {

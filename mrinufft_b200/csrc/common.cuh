@@ -85,6 +85,7 @@ struct b200_plan {
   // device tables
   float* d_poly = nullptr;                       // [(deg+1)][w]: coefficient k of tap i at k*w+i
   float* d_deapod[3] = {nullptr, nullptr, nullptr};  // N[a] floats: (-1)^k / phihat(k)
+  float2* d_tw[3] = {nullptr, nullptr, nullptr};     // nf[a] roots of unity (fft_pruned.cu)
 
   // points
   long long M = 0, Mcap = 0;
@@ -116,7 +117,7 @@ struct b200_plan {
   void* tiled = nullptr;
 
   // options
-  int spread_method = 0, interp_method = 0;
+  int spread_method = 0, interp_method = 0, fft_method = 0;
 
   // timing
   bool timing = false;
@@ -148,5 +149,12 @@ int k4b_crop(b200_plan* p, const float2* fw, const float2* smaps, float2* img, i
              int accumulate, float scale, int conj_smaps, cudaStream_t st);
 int k_pipe_update(b200_plan* p, float* d, const float2* ksp, cudaStream_t st);
 int k_real_to_cpx(b200_plan* p, const float* d, float2* out, cudaStream_t st);
+
+// fused pad/crop + zero-padding-aware FFT passes (fft_pruned.cu)
+bool fftp_supported(const b200_plan* p);
+int fftp_type2(b200_plan* p, const float2* img, const float2* smaps, float2* fw, int T, int isign,
+               int conj_smaps, cudaStream_t st);
+int fftp_type1(b200_plan* p, float2* fw, const float2* smaps, float2* img, int T, int accumulate,
+               int isign, float scale, int conj_smaps, cudaStream_t st);
 
 static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }

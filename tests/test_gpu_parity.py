@@ -539,3 +539,44 @@ def test_odd_grid_sizes_wrap(mods, shape):
         op.raw_op.plan.set_option(1, im)
         assert rel_l2(op.op(img), cpu.op(img)[0]) <= 2e-6
         assert rel_l2(op.adj_op(ksp), cpu.adj_op(ksp)[0]) <= 2e-6
+
+
+# ------------------------------------------------------------------ fused zero-padding-aware FFT passes
+@pytest.mark.parametrize("shape,C,sense", [((32, 64), 3, True), ((16, 128), 1, False), ((16, 32, 64), 3, True),
+                                           ((64, 16, 32), 2, False), ((128, 128, 128), 2, True)])
+def test_pruned_fft_matches_cufft_path_and_oracle(mods, shape, C, sense):
+    """Power-of-two grids take the fused pad/crop + pruned FFT passes (option key 2 = 2); they must
+    agree with the cuFFT + k_pad/k_crop path (key 2 = 1) and with the CPU oracle, both signs, SENSE
+    coil sum, accumulate over coil chunks, data consistency."""
+    from oracle.c_oracle import CpuNufft
+
+    mrinufft, _, _ = mods
+    rng = np.random.default_rng(7)
+    d = len(shape)
+    M = 20000 if np.prod(shape) > 1e5 else 4000
+    samples = rng.uniform(-np.pi, np.pi, (M, d)).astype(np.float32)
+    smaps = None
+    if sense:
+        smaps = (rng.standard_normal((C, *shape)) + 1j * rng.standard_normal((C, *shape))).astype(np.complex64)
+        smaps /= np.linalg.norm(smaps, axis=0)
+    # coil_chunk=2 with C=3 exercises accumulate=1 on the second chunk
+    op = mrinufft.get_operator("b200")(samples, shape, n_coils=C, smaps=smaps, squeeze_dims=False,
+                                       coil_chunk=2 if C == 3 else None)
+    plan = op.raw_op.plan
+    assert all(n in (32, 64, 128, 256, 512, 1024) for n in plan.nf)
+    img = (rng.standard_normal(op.img_full_shape) + 1j * rng.standard_normal(op.img_full_shape)).astype(np.complex64)
+    ksp = (rng.standard_normal(op.ksp_full_shape) + 1j * rng.standard_normal(op.ksp_full_shape)).astype(np.complex64)
+    res = {}
+    for method in (1, 2):
+        plan.set_option(2, method)
+        res[method] = (op.op(img), op.adj_op(ksp), op.data_consistency(img, ksp))
+        with op.grad_traj_plan():  # opposite sign (+ conjugated smaps)
+            res[method] += (op.op(img), op.adj_op(ksp))
+    for a, b in zip(res[1], res[2]):
+        assert rel_l2(b, a) < 1e-6
+    cpu = CpuNufft(samples, shape, precision="f64")
+    if np.prod(shape) <= 1e5:
+        y_o = cpu.op(img[0, 0], smaps) if sense else cpu.op(img[0])
+        x_o = cpu.adj_op(ksp[0], smaps)
+        assert rel_l2(res[2][0][0], y_o) <= 2e-6
+        assert rel_l2(res[2][1][0, 0] if sense else res[2][1][0], x_o) <= 2e-6
