@@ -35,6 +35,7 @@ using fftreg::sfor;
 
 constexpr int TX = 16;   // columns (strided passes) or rows (contiguous passes) per CTA
 constexpr int FT = 256;  // threads per CTA
+constexpr int TXR1 = 8;  // rows per CTA of the type-1 x-pass (two CTAs per SM at 128 registers)
 
 template <int L> struct Split;
 template <> struct Split<32>   { static constexpr int R1 = 8,  R2 = 4;  };
@@ -169,18 +170,39 @@ k_fft_rows_t2(RowArgs A, int nrows, const float2* __restrict__ tw) {
     float2 a[R1];
     if (r < nrows) {
       const RowInfo ri = row_info(A, r);
-      sfor<0, R1>([&](auto I) {
-        constexpr int n1 = decltype(I)::value;
-        const int ix = fine_to_mode(n1 * R2 + n2, Nx, L);
-        float2 v = make_float2(0.f, 0.f);
-        if (ix >= 0) {
-          v = cscale(__ldg(img + ri.img_off + ix), ri.dsl * A.d_fast[ix]);
-          if (sm) {
-            const float2 s = __ldg(sm + ri.img_off + ix);
-            v = A.conj_smaps ? cmul_conj(v, s) : cmul(v, s);
-          }
+      // predicated loads, issued in two batches of R1/2 taps so that all real loads of a batch
+      // (image, deapodisation factor, sensitivity map) are in flight together
+      sfor<0, 2>([&](auto HB) {
+        constexpr int h0 = decltype(HB)::value * (R1 / 2);
+        float dw[R1 / 2];
+        float2 sv[R1 / 2];
+        sfor<0, R1 / 2>([&](auto I) {
+          constexpr int q = decltype(I)::value;
+          const int ix = fine_to_mode((h0 + q) * R2 + n2, Nx, L);
+          a[h0 + q] = ix >= 0 ? __ldg(img + ri.img_off + ix) : make_float2(0.f, 0.f);
+        });
+        sfor<0, R1 / 2>([&](auto I) {
+          constexpr int q = decltype(I)::value;
+          const int ix = fine_to_mode((h0 + q) * R2 + n2, Nx, L);
+          dw[q] = ix >= 0 ? __ldg(A.d_fast + ix) : 0.f;
+        });
+        if (sm) {
+          sfor<0, R1 / 2>([&](auto I) {
+            constexpr int q = decltype(I)::value;
+            const int ix = fine_to_mode((h0 + q) * R2 + n2, Nx, L);
+            sv[q] = ix >= 0 ? __ldg(sm + ri.img_off + ix) : make_float2(0.f, 0.f);
+          });
+          sfor<0, R1 / 2>([&](auto I) {
+            constexpr int q = decltype(I)::value;
+            const float2 v = cscale(a[h0 + q], ri.dsl * dw[q]);
+            a[h0 + q] = A.conj_smaps ? cmul_conj(v, sv[q]) : cmul(v, sv[q]);
+          });
+        } else {
+          sfor<0, R1 / 2>([&](auto I) {
+            constexpr int q = decltype(I)::value;
+            a[h0 + q] = cscale(a[h0 + q], ri.dsl * dw[q]);
+          });
         }
-        a[n1] = v;
       });
     } else {
       sfor<0, R1>([&](auto I) { a[decltype(I)::value] = make_float2(0.f, 0.f); });
@@ -219,41 +241,86 @@ k_fft_rows_t2(RowArgs A, int nrows, const float2* __restrict__ tw) {
 // type 1 x-pass: grid row -> image row, crop + deapodise (+ conj(smaps) multiply + coil sum).
 // grid (ceil(nrows / TX), 1, smaps ? 1 : T); with smaps the CTA loops over the T coils and keeps
 // the coil sum of its outputs in registers.
-template <int L, int DIR>
-__global__ void __launch_bounds__(Split<L>::R1 * TX)
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
+}
+
+// With smaps the CTA loops over the T coils; the raw rows of coil t+1 stream into a second
+// shared-memory buffer with cp.async while coil t is transformed, and the sensitivity-map values of
+// coil t are requested before the barriers of the iteration, so no DRAM latency is exposed.
+// HALF: Nx == L / 2 (sigma = 2): a thread keeps outputs k2 < R2/4 and k2 >= 3 R2/4 only, so the coil
+// accumulators and map values are compact arrays of R2 / 2.
+template <int L, int DIR, bool HALF>
+__global__ void __launch_bounds__(Split<L>::R1 * TXR1, (L <= 512 ? 2 : 1))
 k_fft_rows_t1(RowArgs A, int nrows, const float2* __restrict__ tw) {
   constexpr int R1 = Split<L>::R1, R2 = Split<L>::R2, RS = R1 * (R2 + 1);
-  extern __shared__ float2 S[];
+  constexpr int NT = R1 * TXR1;
+  constexpr int KQ = HALF ? R2 / 2 : R2;  // outputs a thread may keep
+  extern __shared__ __align__(16) float2 S[];   // [TXR1][R1][R2 + 1] | raw[2][TXR1][L]
+  float2* raw = S + TXR1 * RS;
   const int Nx = A.g.N[A.g.dim - 1];
   const bool sense = A.smaps != nullptr;
   const int t_begin = sense ? 0 : blockIdx.z;
   const int t_end = sense ? A.T : blockIdx.z + 1;
-  // step-A role of this thread (threads >= R2 * TX idle in step A), step-B role (all R1 * TX threads)
+  // step-A role of this thread (threads >= R2 * TXR1 idle in step A), step-B role (all threads)
   const int rowA = threadIdx.x / R2, n2A = threadIdx.x % R2;
-  const int rA = blockIdx.x * TX + rowA;
-  const bool doA = threadIdx.x < R2 * TX;
+  const bool doA = threadIdx.x < R2 * TXR1;
   const int rowB = threadIdx.x / R1, k1 = threadIdx.x % R1;
-  const int rB = blockIdx.x * TX + rowB;
+  const int rB = blockIdx.x * TXR1 + rowB;
   const bool doB = rB < nrows;
-  const long long fw_offA = (doA && rA < nrows) ? row_info(A, rA).fw_off : 0;
   RowInfo riB{};
   if (doB) riB = row_info(A, rB);
-  float2 acc[R2];
+  float2 acc[KQ];
 #pragma unroll
-  for (int k2 = 0; k2 < R2; ++k2) acc[k2] = make_float2(0.f, 0.f);
+  for (int q = 0; q < KQ; ++q) acc[q] = make_float2(0.f, 0.f);
+  // q-th kept output of this thread: k = k1 + R1 * k2(q)
+  auto k2_of = [](int q) { return HALF ? (q < R2 / 4 ? q : q + R2 / 2) : q; };
 
+  // cp.async roles: 16-byte chunks, TXR1 * L / 2 of them per coil
+  constexpr int CHUNKS = TXR1 * L / 2;
+  auto prefetch = [&](int t, int buf) {
+    const float2* fwt = A.fw + (long long)t * A.g.nftot;
+    for (int c = threadIdx.x; c < CHUNKS; c += NT) {
+      const int row = c / (L / 2), e = (c % (L / 2)) * 2;
+      const int r = blockIdx.x * TXR1 + row;
+      if (r < nrows) cp_async16(raw + (buf * TXR1 + row) * L + e, fwt + row_info(A, r).fw_off + e);
+    }
+    cp_async_commit();
+  };
+  prefetch(t_begin, 0);
   for (int t = t_begin; t < t_end; ++t) {
+    const int buf = (t - t_begin) & 1;
+    if (t + 1 < t_end) {
+      prefetch(t + 1, buf ^ 1);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    // this coil's sensitivity-map values: issued now, consumed after both barriers
+    float2 sv[KQ];
+    if (sense && doB) {
+      const float2* sm = A.smaps + (long long)t * A.g.Ntot + riB.img_off;
+      sfor<0, KQ>([&](auto I) {
+        constexpr int q = decltype(I)::value;
+        const int ix = fine_to_mode(k1 + R1 * k2_of(q), Nx, L);
+        sv[q] = ix >= 0 ? __ldg(sm + ix) : make_float2(0.f, 0.f);
+      });
+    }
+    __syncthreads();
     if (doA) {
       float2 a[R1];
-      if (rA < nrows) {
-        const float2* in = A.fw + (long long)t * A.g.nftot + fw_offA;
-        sfor<0, R1>([&](auto I) {
-          constexpr int n1 = decltype(I)::value;
-          a[n1] = in[n1 * R2 + n2A];
-        });
-      } else {
-        sfor<0, R1>([&](auto I) { a[decltype(I)::value] = make_float2(0.f, 0.f); });
-      }
+      const float2* in = raw + (buf * TXR1 + rowA) * L;
+      const bool live = blockIdx.x * TXR1 + rowA < nrows;
+      sfor<0, R1>([&](auto I) {
+        constexpr int n1 = decltype(I)::value;
+        a[n1] = live ? in[n1 * R2 + n2A] : make_float2(0.f, 0.f);
+      });
       fftreg::fft<R1, DIR>(a);
       sfor<0, R1>([&](auto I) {
         constexpr int kk = decltype(I)::value;
@@ -274,36 +341,29 @@ k_fft_rows_t1(RowArgs A, int nrows, const float2* __restrict__ tw) {
         b[n2] = S[rowB * RS + k1 * (R2 + 1) + n2];
       });
       fftreg::fft<R2, DIR>(b);
-      if (sense) {
-        const float2* sm = A.smaps + (long long)t * A.g.Ntot + riB.img_off;
-        sfor<0, R2>([&](auto I) {
-          constexpr int k2 = decltype(I)::value;
-          const int ix = fine_to_mode(k1 + R1 * k2, Nx, L);
-          if (ix >= 0) {
-            const float2 s = __ldg(sm + ix);
-            const float2 v = b[brev(k2, R2)];
-            const float2 pr = A.conj_smaps ? cmul(v, s) : cmul_conj(v, s);
-            acc[k2].x += pr.x;
-            acc[k2].y += pr.y;
-          }
-        });
-      } else {
-        sfor<0, R2>([&](auto I) {
-          constexpr int k2 = decltype(I)::value;
-          acc[k2] = b[brev(k2, R2)];
-        });
-      }
+      sfor<0, KQ>([&](auto I) {
+        constexpr int q = decltype(I)::value;
+        constexpr int k2 = HALF ? (q < R2 / 4 ? q : q + R2 / 2) : q;
+        const float2 v = b[brev(k2, R2)];
+        if (sense) {
+          const float2 pr = A.conj_smaps ? cmul(v, sv[q]) : cmul_conj(v, sv[q]);
+          acc[q].x += pr.x;
+          acc[q].y += pr.y;
+        } else {
+          acc[q] = v;
+        }
+      });
     }
-    __syncthreads();
+    // the next iteration's first __syncthreads orders these reads of S / raw[buf] before their reuse
   }
   // epilogue: deapodise, scale, (accumulate,) store
   if (!doB) return;
   float2* outimg = sense ? A.img_out : A.img_out + (long long)blockIdx.z * A.g.Ntot;
-  sfor<0, R2>([&](auto I) {
-    constexpr int k2 = decltype(I)::value;
-    const int ix = fine_to_mode(k1 + R1 * k2, Nx, L);
+  sfor<0, KQ>([&](auto I) {
+    constexpr int q = decltype(I)::value;
+    const int ix = fine_to_mode(k1 + R1 * k2_of(q), Nx, L);
     if (ix >= 0) {
-      float2 v = cscale(acc[k2], riB.dsl * A.d_fast[ix] * A.scale);
+      float2 v = cscale(acc[q], riB.dsl * A.d_fast[ix] * A.scale);
       float2* o = outimg + riB.img_off + ix;
       if (A.accumulate) {
         const float2 old = *o;
@@ -388,18 +448,25 @@ int launch_rows_t2(const RowArgs& A, int nrows, const float2* tw, cudaStream_t s
   return B200_OK;
 }
 
-template <int L, int DIR>
-int launch_rows_t1(const RowArgs& A, int nrows, const float2* tw, cudaStream_t st) {
-  auto kern = k_fft_rows_t1<L, DIR>;
-  const size_t smem = (size_t)TX * Split<L>::R1 * (Split<L>::R2 + 1) * sizeof(float2);
+template <int L, int DIR, bool HALF>
+int launch_rows_t1_h(const RowArgs& A, int nrows, const float2* tw, cudaStream_t st) {
+  auto kern = k_fft_rows_t1<L, DIR, HALF>;
+  const size_t smem = ((size_t)TXR1 * Split<L>::R1 * (Split<L>::R2 + 1) + 2 * (size_t)TXR1 * L) * sizeof(float2);
   static bool done = false;
   if (!done) {
     B200_TRY(set_smem(kern, smem));
     done = true;
   }
-  kern<<<dim3(ceil_div(nrows, TX), 1, A.smaps ? 1 : A.T), Split<L>::R1 * TX, smem, st>>>(A, nrows, tw);
+  kern<<<dim3(ceil_div(nrows, TXR1), 1, A.smaps ? 1 : A.T), Split<L>::R1 * TXR1, smem, st>>>(A, nrows, tw);
   CHECK_LAUNCH();
   return B200_OK;
+}
+
+template <int L, int DIR>
+int launch_rows_t1(const RowArgs& A, int nrows, const float2* tw, cudaStream_t st) {
+  const int Nx = A.g.N[A.g.dim - 1];
+  if (2 * Nx == L && Nx % 2 == 0) return launch_rows_t1_h<L, DIR, true>(A, nrows, tw, st);
+  return launch_rows_t1_h<L, DIR, false>(A, nrows, tw, st);
 }
 
 // pass along axis `a` (not the fastest one) of the [nf0][nf1][nf2] (or [nf0][nf1]) grid

@@ -95,11 +95,18 @@ __host__ __device__ __forceinline__ int num_xtiles(const Geom& g) {
   return (g.nf[DIM - 1] + CX - 1) / CX;
 }
 
+// Row ids enumerate (y-block of YB rows, z, y-group of 4 inside the block, x-tile, y inside the
+// group): the GROUP = 4 ids fetched together are 4 neighbouring y rows of one tile, and the sweep
+// over z stays inside a slab of YB rows, so that the coil rows / records of the points (re-visited
+// by the next w - 1 planes) are still in L2: one z step streams YB * nfx * 8 B * T = 4 MB of grid,
+// not a whole 67 MB plane.
+constexpr int YB = 32;
+
 template <int DIM>
 __host__ __device__ __forceinline__ long long num_rows(const Geom& g) {
-  const long long nyg = (g.nf[DIM - 2] + 3) / 4;
+  const long long nyb = (g.nf[DIM - 2] + YB - 1) / YB;
   const long long nz = DIM == 3 ? g.nf[0] : 1;
-  return nz * nyg * num_xtiles<DIM>(g) * 4;
+  return nyb * nz * (YB / 4) * num_xtiles<DIM>(g) * 4;
 }
 
 struct RowCoord {
@@ -107,21 +114,21 @@ struct RowCoord {
   long long rowbase;  // linear index of (z, y, 0) in one coil's grid
 };
 
-// row id -> coordinates; order (z, y-group of 4, x-tile, y within group) so that the GROUP = 4
-// consecutive ids fetched together are 4 neighbouring y rows of the same tile.
 template <int DIM>
 __device__ __forceinline__ bool decode_row(const Geom& g, long long row, RowCoord* rc) {
   const int nfx = g.nf[DIM - 1];
   const int nfy = g.nf[DIM - 2];
   const int nbx = num_xtiles<DIM>(g);
-  const int nyg = (nfy + 3) / 4;
+  const int nz = DIM == 3 ? g.nf[0] : 1;
   const int ys = (int)(row & 3);
   long long r = row >> 2;
   rc->bx = (int)(r % nbx);
   r /= nbx;
-  const int yg = (int)(r % nyg);
-  rc->z = (int)(r / nyg);
-  rc->y = yg * 4 + ys;
+  const int yg = (int)(r % (YB / 4));
+  r /= (YB / 4);
+  rc->z = (int)(r % nz);
+  const int yb = (int)(r / nz);
+  rc->y = yb * YB + yg * 4 + ys;
   if (rc->y >= nfy) return false;
   rc->rowbase = ((long long)rc->z * nfy + rc->y) * nfx;
   return true;
