@@ -224,7 +224,7 @@ int b200_plan_create(b200_plan** out, int dim, const int64_t* n_modes, int n_tra
       return B200_EINVAL;
     }
   // pencil bins: 1 cell along slow axes, BX cells along the fastest axis
-  const int BX = 32;
+  const int BX = 16;  // pencil-bin width = tile width of the row kernels (spread_rows.cu)
   p->nbins_tot = 1;
   for (int a = 0; a < 3; ++a) {
     g.bin[a] = 1;

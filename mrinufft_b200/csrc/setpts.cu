@@ -12,8 +12,8 @@
 // every step one IEEE-754 double operation rounded to nearest (explicit __d*_rn intrinsics, so
 // the compiler cannot contract them into FMAs).
 //
-// Bins are "pencils": one cell along every axis but the fastest, BX = 32 cells along the fastest
-// axis, each split in two sub-bins by `cross` (does the footprint leave the 32-cell tile?).  The key
+// Bins are "pencils": one cell along every axis but the fastest, BX = 16 cells along the fastest
+// axis, each split in two sub-bins by `cross` (does the footprint leave the 16-cell tile?).  The key
 // orders them so that, for a fixed slow origin, x-tile and cross flag, consecutive middle origins
 // are consecutive keys (3-D: key = ((o0 * nbx + bx) * 2 + cross) * nf1 + o1;
 // 2-D: key = (bx * 2 + cross) * nf0 + o0; 1-D: key = bx).  The row kernels (spread_rows.cu) rely

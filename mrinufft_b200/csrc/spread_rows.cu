@@ -5,39 +5,42 @@
 // complex accumulations per point per coil; with 32 coils batched that is 1.8e11 float atomics per
 // transform, and on sm_100a a float atomicAdd on shared memory is an ATOMS.CAST.SPIN
 // compare-and-swap loop (checked with cuobjdump).  Shared memory cannot feed the FMA pipe either
-// (128 B/clk/SM against 128 FFMA/clk/SM).  The register file can.  So every fine-grid "row"
+// (128 B/clk/SM against 128 FFMA/clk/SM).  The register file can.  So every fine-grid TILE
 //
-//        32 consecutive cells along the fastest axis at fixed slow coordinates (z, y), all coils
+//        2 rows (y, y+1) x 16 consecutive cells along the fastest axis at fixed z, all coils
 //
-// is OWNED by one warp at a time and lives in REGISTERS: lane = coil, register i = cell i
-// (64 accumulators).  The points whose footprint covers the row ("visits") are found through the
-// bin sort of K1 without any search or filtering:
+// is OWNED by one warp at a time and lives in REGISTERS: lane = coil, 32 64-bit registers hold the
+// (cell 2j, cell 2j+1) pairs of the real and imaginary parts of both rows.  The points whose
+// footprint covers the tile ("visits") are found through the bin sort of K1 without any search:
 //
-//   * bins are pencils of 1 x 1 x 32 cells, split in two sub-bins: points whose footprint stays
-//     inside the 32-cell tile ("interior") and points whose footprint crosses into the next tile
+//   * bins are pencils of 1 x 1 x 16 cells, split in two sub-bins: points whose footprint stays
+//     inside the 16-cell tile ("interior") and points whose footprint crosses into the next tile
 //     ("crossing"); key order (z0, x-tile, crossing, y0);
-//   * the visits of row (z, y, tile) are therefore exactly 3 contiguous ranges of sorted points
-//     per slow-axis offset dz (own interior, own crossing, left neighbour's crossing), each
-//     spanning the w values y0 in [y-w+1, y]  (twice that when the range wraps periodically);
-//   * the ranges of a row are concatenated by a warp prefix sum; blocks of 16 visits are staged
-//     lane-parallel (one lane = one visit: load the point's weight record, form
-//     wx[0..w) * wy[dy] * wz[dz], write 32 bytes of shared memory) while the sample values of
-//     those 16 points for all coils stream in with cp.async (one coalesced 256-byte row per point
-//     from the (sorted point, coil) transposed k-space batch), double buffered;
-//   * the consume loop then costs 2 LDS.128 (weights, warp broadcast) + 1 LDS.64 (this lane's
-//     coil value) + a warp-uniform jump on the x offset + 2w FFMA into statically indexed
-//     registers per visit -- the FMA pipe is the intended bottleneck;
-//   * a row is written to HBM exactly once as full 256-byte coalesced stores per coil (through a
-//     shared-memory transpose): no memset of the oversampled grid, no halo flush, no atomics.
+//   * the visits of tile (z, y..y+1, bx) are therefore exactly 3 contiguous ranges of sorted points
+//     per slow-axis offset dz (own interior, own crossing, left neighbour's crossing), each spanning
+//     y0 in [y-w+1, y+1] (twice that when the range wraps periodically);
+//   * the ranges of a tile are concatenated by a warp prefix sum; blocks of 16 visits are staged
+//     lane-parallel (one lane = one visit: load the point's weight record, pair-pack the x weights
+//     by the parity of the x offset, form the two row scales wy[dy] wz[dz], write a 48-byte packet
+//     to shared memory) while the sample values of those 16 points for all coils stream in with
+//     cp.async (one coalesced 256-byte row per point from the (sorted point, coil) transposed
+//     k-space batch), double buffered;
+//   * the consume loop costs 3 LDS.128 (packet, warp broadcast) + 1 LDS.64 (this lane's coil
+//     value) + 8 FMUL + one indexed branch on the x offset + 16 packed FFMA2 per visit, for two
+//     grid rows: the weights broadcast -- the scarce resource, one L1 wavefront per clock per SM --
+//     is amortised over twice the FMAs of a one-row design;
+//   * a tile is written to HBM exactly once as 128-byte coalesced stores per coil and row (through
+//     a shared-memory transpose): no memset of the oversampled grid, no halo flush, no atomics.
 //
-// Load balance: a trajectory like 3-D radial puts ~1e5 visits on the few rows through the k-space
-// centre.  Rows with more than CHUNK visits are split into several work items whose partial rows
-// are merged with vector red.global.add on a pre-zeroed row; all items are handed out dynamically
-// (groups of 4 neighbouring rows per atomic fetch, so a warp re-uses the point records it just
-// pulled into L1).
+// Load balance: a trajectory like 3-D radial puts ~1e5 visits on the few tiles through the k-space
+// centre.  Tiles with more than CHUNK visits are split into several work items whose partial
+// results are merged with vector red.global.add on pre-zeroed rows; all items are handed out
+// dynamically (groups of 4 vertically adjacent tiles per atomic fetch, so a warp re-uses the point
+// records it just pulled into L1), in an order that sweeps z inside slabs of 32 rows so that a
+// point's data is still in L2 when the next plane needs it.
 //
-// Interpolation is the exact transpose: the warp loads its row into registers once (coalesced),
-// every visiting point takes its w-tap dot product from registers and adds the partial sum into
+// Interpolation is the exact transpose: the warp loads its tile into registers once (coalesced),
+// every visiting point takes its tap dot products from registers and adds the partial sum into
 // the (sorted point, coil) accumulator with one vector `red.global.add.v2.f32` per lane.
 //
 // Replaces finufft's spread/interp stage (call sites
@@ -49,7 +52,8 @@
 
 namespace {
 
-constexpr int CX = 32;          // cells per row segment (== pencil-bin width, B200_BIN_X)
+constexpr int CX = 16;          // cells per tile row (== pencil-bin width, B200_BIN_X)
+constexpr int NACC = 32;        // 64-bit accumulator registers per lane: [row 2][re/im 2][cell pair 8]
 constexpr int REC = 24;         // floats per point record: wx[7] xo | wy[7] y0 | wz[7] z0
 constexpr int BLK = 16;         // visits staged per block
 constexpr int WARPS = 4;        // warps per CTA
@@ -63,7 +67,7 @@ constexpr int ITEM_SPLIT = 1 << 30;   // chunk flag: row is shared by several it
 
 // per-warp shared memory (bytes)
 constexpr int SM_VBUF = 2 * BLK * 32 * 8;   // double-buffered coil values of BLK points
-constexpr int SM_META = 2 * BLK * 64;       // double-buffered {(w'[i], w'[i]) i < 7, idx, s}
+constexpr int SM_META = 2 * BLK * 48;       // double-buffered packets {P0..P3, s0, s1, idx, s}
 constexpr int SM_SLOT = 2 * NSLOT * 4;      // pre[], begin[]
 constexpr int SM_WARP = SM_VBUF + SM_META + SM_SLOT;
 static_assert(SM_VBUF + SM_META >= 32 * 33 * 8, "transpose buffer must fit in vbuf+meta");
@@ -95,22 +99,22 @@ __host__ __device__ __forceinline__ int num_xtiles(const Geom& g) {
   return (g.nf[DIM - 1] + CX - 1) / CX;
 }
 
-// Row ids enumerate (y-block of YB rows, z, y-group of 4 inside the block, x-tile, y inside the
-// group): the GROUP = 4 ids fetched together are 4 neighbouring y rows of one tile, and the sweep
-// over z stays inside a slab of YB rows, so that the coil rows / records of the points (re-visited
-// by the next w - 1 planes) are still in L2: one z step streams YB * nfx * 8 B * T = 4 MB of grid,
-// not a whole 67 MB plane.
+// Tile ids enumerate (y-block of YB rows, z, group of 4 row pairs inside the block, x-tile, pair
+// inside the group): the GROUP = 4 ids fetched together are 4 vertically adjacent tiles, and the
+// sweep over z stays inside a slab of YB rows, so that the coil rows / records of the points
+// (re-visited by the next w - 1 planes) are still in L2: one z step streams
+// YB * nfx * 8 B * T = 4 MB of grid, not a whole 67 MB plane.
 constexpr int YB = 32;
 
 template <int DIM>
 __host__ __device__ __forceinline__ long long num_rows(const Geom& g) {
   const long long nyb = (g.nf[DIM - 2] + YB - 1) / YB;
   const long long nz = DIM == 3 ? g.nf[0] : 1;
-  return nyb * nz * (YB / 4) * num_xtiles<DIM>(g) * 4;
+  return nyb * nz * (YB / 8) * num_xtiles<DIM>(g) * 4;
 }
 
 struct RowCoord {
-  int z, y, bx;
+  int z, y, bx;       // y = first (even) row of the pair
   long long rowbase;  // linear index of (z, y, 0) in one coil's grid
 };
 
@@ -120,23 +124,23 @@ __device__ __forceinline__ bool decode_row(const Geom& g, long long row, RowCoor
   const int nfy = g.nf[DIM - 2];
   const int nbx = num_xtiles<DIM>(g);
   const int nz = DIM == 3 ? g.nf[0] : 1;
-  const int ys = (int)(row & 3);
+  const int ps = (int)(row & 3);
   long long r = row >> 2;
   rc->bx = (int)(r % nbx);
   r /= nbx;
-  const int yg = (int)(r % (YB / 4));
-  r /= (YB / 4);
+  const int pg = (int)(r % (YB / 8));
+  r /= (YB / 8);
   rc->z = (int)(r % nz);
   const int yb = (int)(r / nz);
-  rc->y = yb * YB + yg * 4 + ys;
-  if (rc->y >= nfy) return false;
+  rc->y = yb * YB + pg * 8 + ps * 2;
+  if (rc->y >= nfy) return false;  // nfy is even: both rows of a pair are valid or neither
   rc->rowbase = ((long long)rc->z * nfy + rc->y) * nfx;
   return true;
 }
 
 // Range slot -> [begin, begin + len) in sorted point order.
 //   slot = ((dz * 3) + sub) * 2 + part ; sub 0: own interior, 1: own crossing, 2: left crossing ;
-//   part 0: y0 in [max(y-w+1, 0), y], part 1: the periodic wrap [y-w+1+nfy, nfy-1] (if any).
+//   part 0: y0 in [max(y-w+1, 0), y+1], part 1: the periodic wrap [y-w+1+nfy, nfy-1] (if any).
 template <int DIM, int W>
 __device__ __forceinline__ void slot_range(const Geom& g, const RowCoord& rc, int slot,
                                            const int32_t* __restrict__ bin_start, int* begin,
@@ -154,7 +158,7 @@ __device__ __forceinline__ void slot_range(const Geom& g, const RowCoord& rc, in
   int a, b;
   if (part == 0) {
     a = ylo > 0 ? ylo : 0;
-    b = rc.y;
+    b = rc.y + 1;
   } else {
     if (ylo >= 0) return;
     a = ylo + nfy;
@@ -321,9 +325,11 @@ k_zero_split_rows(Geom g, int T, long long nsplit, const int32_t* __restrict__ s
   if (w >= nsplit) return;
   RowCoord rc;
   if (!decode_row<DIM>(g, split_rows[w], &rc)) return;
-  const int x = rc.bx * CX + lane;
-  if (x >= g.nf[DIM - 1]) return;
-  for (int t = 0; t < T; ++t) fw[(long long)t * g.nftot + rc.rowbase + x] = make_float2(0.f, 0.f);
+  const int nfx = g.nf[DIM - 1];
+  const int x = rc.bx * CX + (lane & 15);
+  if (x >= nfx) return;
+  float2* dst = fw + rc.rowbase + (long long)(lane >> 4) * nfx + x;
+  for (int t = 0; t < T; ++t) dst[(long long)t * g.nftot] = make_float2(0.f, 0.f);
 }
 
 // ------------------------------------------------------------------------------ row kernels
@@ -334,18 +340,20 @@ typedef unsigned long long u64;
 #include "taps_generated.inc"
 
 template <int W>
-__device__ __forceinline__ void taps_spread(u64 (&acc)[CX], unsigned idx, const u64 (&w)[8], u64 v) {
-  if (W == 7) taps_spread_w7(acc, idx, w, v);
-  else if (W == 6) taps_spread_w6(acc, idx, w, v);
-  else if (W == 5) taps_spread_w5(acc, idx, w, v);
-  else taps_spread_w4(acc, idx, w, v);
+__device__ __forceinline__ void taps_spread(u64 (&acc)[NACC], unsigned idx, const u64 (&P)[4],
+                                            const u64 (&A)[4]) {
+  if (W == 7) taps_spread_w7(acc, idx, P, A);
+  else if (W == 6) taps_spread_w6(acc, idx, P, A);
+  else if (W == 5) taps_spread_w5(acc, idx, P, A);
+  else taps_spread_w4(acc, idx, P, A);
 }
 template <int W>
-__device__ __forceinline__ u64 taps_interp(const u64 (&acc)[CX], unsigned idx, const u64 (&w)[8]) {
-  if (W == 7) return taps_interp_w7(acc, idx, w);
-  if (W == 6) return taps_interp_w6(acc, idx, w);
-  if (W == 5) return taps_interp_w5(acc, idx, w);
-  return taps_interp_w4(acc, idx, w);
+__device__ __forceinline__ void taps_interp(u64 (&S)[4], const u64 (&acc)[NACC], unsigned idx,
+                                            const u64 (&P)[4]) {
+  if (W == 7) taps_interp_w7(S, acc, idx, P);
+  else if (W == 6) taps_interp_w6(S, acc, idx, P);
+  else if (W == 5) taps_interp_w5(S, acc, idx, P);
+  else taps_interp_w4(S, acc, idx, P);
 }
 
 __device__ __forceinline__ u64 pack2(float lo, float hi) {
@@ -384,6 +392,9 @@ struct Staged {
   int left_len;  // 0, or the length of the left tile for left-crossing visits
 };
 
+__device__ __forceinline__ float lo32(u64 v) { return __uint_as_float((unsigned)v); }
+__device__ __forceinline__ float hi32(u64 v) { return __uint_as_float((unsigned)(v >> 32)); }
+
 template <int DIM, int W, bool SPREAD>
 __global__ void __launch_bounds__(THREADS, 4)
 k_rows(Geom g, int T, long long nitems, const int2* __restrict__ items,
@@ -393,10 +404,11 @@ k_rows(Geom g, int T, long long nitems, const int2* __restrict__ items,
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   unsigned char* wsm = smem_raw + (size_t)warp * SM_WARP;
   u64* vbuf = reinterpret_cast<u64*>(wsm);                              // [2][BLK][32] (re, im)
-  ulonglong2* meta = reinterpret_cast<ulonglong2*>(wsm + SM_VBUF);      // [2][BLK][4]
+  uint4* meta = reinterpret_cast<uint4*>(wsm + SM_VBUF);                // [2][BLK][3]
   int* s_pre = reinterpret_cast<int*>(wsm + SM_VBUF + SM_META);         // [NSLOT]
   int* s_beg = s_pre + NSLOT;                                           // [NSLOT]
   u64* tbuf = reinterpret_cast<u64*>(wsm);                              // [32][33] transpose (aliases)
+  constexpr int JB0 = W / 2;  // idx = floor(off / 2) + JB0
 
   const int nfx = g.nf[DIM - 1];
   const int nfy = g.nf[DIM - 2];
@@ -415,19 +427,20 @@ k_rows(Geom g, int T, long long nitems, const int2* __restrict__ items,
       const int2 it = __ldg(items + item);
       RowCoord rc;
       if (!decode_row<DIM>(g, it.x, &rc)) continue;
-      const int x = rc.bx * CX + lane;
+      // flush / load role of this lane: row (lane >> 4) of the pair, cell (lane & 15)
+      const int x = rc.bx * CX + (lane & 15);
+      u64* gtile = fw64 + rc.rowbase + (long long)(lane >> 4) * nfx + x;
       const bool split = (it.y != ITEM_EMPTY) && (it.y & ITEM_SPLIT);
 
       if (it.y == ITEM_EMPTY) {
         if (SPREAD && x < nfx) {
-          u64* dst = fw64 + rc.rowbase + x;
-          for (int t = 0; t < T; ++t) dst[(long long)t * g.nftot] = 0ull;
+          for (int t = 0; t < T; ++t) gtile[(long long)t * g.nftot] = 0ull;
         }
         continue;
       }
       const int chunk = it.y & (ITEM_SPLIT - 1);
 
-      // ---- ranges of this row: 2 slots per lane, exclusive prefix sum over the 64 slots
+      // ---- ranges of this tile: 2 slots per lane, exclusive prefix sum over the 64 slots
       int b0, l0, b1, l1;
       slot_range<DIM, W>(g, rc, lane, bin_start, &b0, &l0);
       slot_range<DIM, W>(g, rc, lane + 32, bin_start, &b1, &l1);
@@ -454,23 +467,28 @@ k_rows(Geom g, int T, long long nitems, const int2* __restrict__ items,
       const int nblk = (v_hi - v_lo + BLK - 1) / BLK;
       const int left_len = (rc.bx == 0) ? (nfx - (nbx - 1) * CX) : CX;
 
-      // ---- accumulators: acc[i] = packed (re, im) of cell i for this lane's coil
-      u64 acc[CX];
+      // ---- accumulators: acc[r*16 + c*8 + j] = (cell 2j, cell 2j+1) of row r, c = re / im
+      u64 acc[NACC];
       if (SPREAD) {
 #pragma unroll
-        for (int i = 0; i < CX; ++i) acc[i] = 0ull;
+        for (int i = 0; i < NACC; ++i) acc[i] = 0ull;
       } else {
-        // load the row: coalesced per coil -> smem -> registers (lane = coil)
-        const u64* src = fw64 + rc.rowbase + x;
+        // load the tile: coalesced per coil (128 B per row) -> smem -> registers (lane = coil)
 #pragma unroll 8
         for (int t = 0; t < 32; ++t) {
           u64 v = 0ull;
-          if (t < T && x < nfx) v = __ldg(src + (long long)t * g.nftot);
+          if (t < T && x < nfx) v = __ldg(gtile + (long long)t * g.nftot);
           tbuf[t * 33 + lane] = v;
         }
         __syncwarp();
 #pragma unroll
-        for (int i = 0; i < CX; ++i) acc[i] = tbuf[lane * 33 + i];
+        for (int r = 0; r < 2; ++r)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const u64 c0 = tbuf[lane * 33 + r * 16 + 2 * j], c1 = tbuf[lane * 33 + r * 16 + 2 * j + 1];
+            acc[r * 16 + j] = pack2(lo32(c0), lo32(c1));      // real parts
+            acc[r * 16 + 8 + j] = pack2(hi32(c0), hi32(c1));  // imaginary parts
+          }
         __syncwarp();
       }
 
@@ -511,24 +529,37 @@ k_rows(Geom g, int T, long long nitems, const int2* __restrict__ items,
       };
       auto stage_finish = [&](int buf, const Staged& st) {
         if (st.s >= 0) {
+          // row scales: row y takes wy[dy], row y+1 takes wy[dy+1]  (dy = y - y0 in [-1, W-1])
           int dy = rc.y - __float_as_int(st.d.w);
-          if (dy < 0) dy += nfy;
-          float wy = st.c.x;
-          wy = dy == 1 ? st.c.y : wy;
-          wy = dy == 2 ? st.c.z : wy;
-          wy = dy == 3 ? st.c.w : wy;
-          wy = dy == 4 ? st.d.x : wy;
-          wy = dy == 5 ? st.d.y : wy;
-          wy = dy == 6 ? st.d.z : wy;
-          const float wyz = wy * st.wz;
-          const unsigned idx = (unsigned)(__float_as_int(st.b.w) - st.left_len + (W - 1));
-          const float w0 = st.a.x * wyz, w1 = st.a.y * wyz, w2 = st.a.z * wyz, w3 = st.a.w * wyz;
-          const float w4 = st.b.x * wyz, w5 = st.b.y * wyz, w6 = st.b.z * wyz;
-          ulonglong2* m = meta + (buf * BLK + lane) * 4;
-          m[0] = make_ulonglong2(pack2(w0, w0), pack2(w1, w1));
-          m[1] = make_ulonglong2(pack2(w2, w2), pack2(w3, w3));
-          m[2] = make_ulonglong2(pack2(w4, w4), pack2(w5, w5));
-          m[3] = make_ulonglong2(pack2(w6, w6), ((u64)(unsigned)st.s << 32) | (u64)idx);
+          if (dy < -1) dy += nfy;
+          const float wy[8] = {st.c.x, st.c.y, st.c.z, st.c.w, st.d.x, st.d.y, st.d.z, 0.f};
+          float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+          for (int i = 0; i < W; ++i) {
+            s0 = dy == i ? wy[i] : s0;
+            s1 = dy + 1 == i ? wy[i] : s1;
+          }
+          s0 *= st.wz;
+          s1 *= st.wz;
+          // pair-packed x weights: P_q = (w[2q - par], w[2q + 1 - par])
+          const int off = __float_as_int(st.b.w) - st.left_len;
+          const int jb = off >> 1;
+          const bool odd = off & 1;
+          const float w[9] = {0.f, st.a.x, st.a.y, st.a.z, st.a.w, st.b.x, st.b.y, st.b.z, 0.f};
+          float pw[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            // even: pw[i] = wx[i] ; odd: pw[i] = wx[i - 1]   (wx[i] = w[i + 1], zero outside [0, W))
+            const float we = (i < W) ? w[i + 1] : 0.f;
+            const float wo = (i >= 1 && i - 1 < W) ? w[i] : 0.f;
+            pw[i] = odd ? wo : we;
+          }
+          uint4* m = meta + (buf * BLK + lane) * 3;
+          m[0] = make_uint4(__float_as_uint(pw[0]), __float_as_uint(pw[1]), __float_as_uint(pw[2]),
+                            __float_as_uint(pw[3]));
+          m[1] = make_uint4(__float_as_uint(pw[4]), __float_as_uint(pw[5]), __float_as_uint(pw[6]),
+                            __float_as_uint(pw[7]));
+          m[2] = make_uint4(__float_as_uint(s0), __float_as_uint(s1), (unsigned)(jb + JB0), (unsigned)st.s);
         }
       };
 
@@ -547,19 +578,26 @@ k_rows(Geom g, int T, long long nitems, const int2* __restrict__ items,
         }
         __syncwarp();
         const int n = min(BLK, v_hi - v_lo - blk * BLK);
-        const ulonglong2* m = meta + cur * BLK * 4;
+        const uint4* m = meta + cur * BLK * 3;
         const u64* vb = vbuf + cur * (BLK * 32) + lane;
 #pragma unroll 1
         for (int k = 0; k < n; ++k) {
-          const ulonglong2 m0 = m[4 * k], m1 = m[4 * k + 1], m2 = m[4 * k + 2], m3 = m[4 * k + 3];
-          const u64 wx[8] = {m0.x, m0.y, m1.x, m1.y, m2.x, m2.y, m3.x, 0ull};
-          const unsigned idx = (unsigned)m3.y;
+          const uint4 m0 = m[3 * k], m1 = m[3 * k + 1], m2 = m[3 * k + 2];
+          const u64 P[4] = {((u64)m0.y << 32) | m0.x, ((u64)m0.w << 32) | m0.z,
+                            ((u64)m1.y << 32) | m1.x, ((u64)m1.w << 32) | m1.z};
+          const float s0 = __uint_as_float(m2.x), s1 = __uint_as_float(m2.y);
           if (SPREAD) {
-            taps_spread<W>(acc, idx, wx, vb[k * 32]);
+            const u64 v = vb[k * 32];
+            const float vx = lo32(v), vy = hi32(v);
+            const float a0x = vx * s0, a0y = vy * s0, a1x = vx * s1, a1y = vy * s1;
+            const u64 A[4] = {pack2(a0x, a0x), pack2(a0y, a0y), pack2(a1x, a1x), pack2(a1y, a1y)};
+            taps_spread<W>(acc, m2.z, P, A);
           } else {
-            const u64 p = taps_interp<W>(acc, idx, wx);
-            const long long s = (long long)(m3.y >> 32);
-            red_add_f32x2(kt + s * 32 + lane, p, lane < T);
+            u64 S[4];
+            taps_interp<W>(S, acc, m2.z, P);
+            const float px = s0 * (lo32(S[0]) + hi32(S[0])) + s1 * (lo32(S[2]) + hi32(S[2]));
+            const float py = s0 * (lo32(S[1]) + hi32(S[1])) + s1 * (lo32(S[3]) + hi32(S[3]));
+            red_add_f32x2(kt + (long long)m2.w * 32 + lane, pack2(px, py), lane < T);
           }
         }
         if (more) stage_finish(cur ^ 1, st);
@@ -567,18 +605,23 @@ k_rows(Geom g, int T, long long nitems, const int2* __restrict__ items,
       }
 
       if (SPREAD) {
-        // flush: registers (lane = coil, i = cell) -> smem transpose -> coalesced rows per coil
+        // flush: registers (lane = coil) -> smem transpose -> coalesced 128-byte rows per coil
 #pragma unroll
-        for (int i = 0; i < CX; ++i) tbuf[lane * 33 + i] = acc[i];
+        for (int r = 0; r < 2; ++r)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const u64 re = acc[r * 16 + j], im = acc[r * 16 + 8 + j];
+            tbuf[lane * 33 + r * 16 + 2 * j] = pack2(lo32(re), lo32(im));
+            tbuf[lane * 33 + r * 16 + 2 * j + 1] = pack2(hi32(re), hi32(im));
+          }
         __syncwarp();
         if (x < nfx) {
-          u64* dst = fw64 + rc.rowbase + x;
           if (split) {
             for (int t = 0; t < T; ++t)
-              red_add_f32x2(reinterpret_cast<float2*>(dst + (long long)t * g.nftot), tbuf[t * 33 + lane], 1);
+              red_add_f32x2(reinterpret_cast<float2*>(gtile + (long long)t * g.nftot), tbuf[t * 33 + lane], 1);
           } else {
 #pragma unroll 4
-            for (int t = 0; t < T; ++t) dst[(long long)t * g.nftot] = tbuf[t * 33 + lane];
+            for (int t = 0; t < T; ++t) gtile[(long long)t * g.nftot] = tbuf[t * 33 + lane];
           }
         }
         __syncwarp();

@@ -124,7 +124,7 @@ def test_bin_sort_is_stable_and_ordered():
     assert np.all(np.diff(ks) >= 0)
     same = np.diff(ks) == 0
     assert np.all(np.diff(r["perm"])[same] > 0)
-    assert r["key"].max() < 64 * 48 * 3 * 2 and r["key"].min() >= 0
+    assert r["key"].max() < 64 * 48 * (80 // E.BIN_X) * 2 and r["key"].min() >= 0
 
 
 def test_empty_and_single_point():
