@@ -70,7 +70,8 @@ constexpr int SM_VBUF = 2 * BLK * 32 * 8;   // double-buffered coil values of BL
 constexpr int SM_META = 2 * BLK * 48;       // double-buffered packets {P0..P3, s0, s1, idx, s}
 constexpr int SM_SLOT = 2 * NSLOT * 4;      // pre[], begin[]
 constexpr int SM_WARP = SM_VBUF + SM_META + SM_SLOT;
-static_assert(SM_VBUF + SM_META >= 32 * 33 * 8, "transpose buffer must fit in vbuf+meta");
+constexpr int TS = 34;          // row stride (floats) of the transpose planes
+static_assert(SM_VBUF + SM_META >= 2 * 32 * TS * 4, "transpose buffers must fit in vbuf+meta");
 
 struct RowsState {
   float* d_rec = nullptr;        // [M][REC] per sorted point
@@ -348,7 +349,7 @@ __device__ __forceinline__ void taps_spread(u64 (&acc)[NACC], unsigned idx, cons
   else taps_spread_w4(acc, idx, P, A);
 }
 template <int W>
-__device__ __forceinline__ void taps_interp(u64 (&S)[4], const u64 (&acc)[NACC], unsigned idx,
+__device__ __forceinline__ void taps_interp(u64 (&S)[4], u64 (&acc)[NACC], unsigned idx,
                                             const u64 (&P)[4]) {
   if (W == 7) taps_interp_w7(S, acc, idx, P);
   else if (W == 6) taps_interp_w6(S, acc, idx, P);
@@ -407,7 +408,10 @@ k_rows(Geom g, int T, long long nitems, const int2* __restrict__ items,
   uint4* meta = reinterpret_cast<uint4*>(wsm + SM_VBUF);                // [2][BLK][3]
   int* s_pre = reinterpret_cast<int*>(wsm + SM_VBUF + SM_META);         // [NSLOT]
   int* s_beg = s_pre + NSLOT;                                           // [NSLOT]
-  u64* tbuf = reinterpret_cast<u64*>(wsm);                              // [32][33] transpose (aliases)
+  // transpose buffers (alias vbuf/meta): real and imaginary planes [32 coils][34] floats, so that a
+  // lane reads / writes its (cell 2j, cell 2j+1) register pairs with one conflict-free 64-bit access
+  float* tre = reinterpret_cast<float*>(wsm);
+  float* tim = tre + 32 * TS;
   constexpr int JB0 = W / 2;  // idx = floor(off / 2) + JB0
 
   const int nfx = g.nf[DIM - 1];
@@ -478,16 +482,16 @@ k_rows(Geom g, int T, long long nitems, const int2* __restrict__ items,
         for (int t = 0; t < 32; ++t) {
           u64 v = 0ull;
           if (t < T && x < nfx) v = __ldg(gtile + (long long)t * g.nftot);
-          tbuf[t * 33 + lane] = v;
+          tre[t * TS + lane] = lo32(v);
+          tim[t * TS + lane] = hi32(v);
         }
         __syncwarp();
 #pragma unroll
         for (int r = 0; r < 2; ++r)
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            const u64 c0 = tbuf[lane * 33 + r * 16 + 2 * j], c1 = tbuf[lane * 33 + r * 16 + 2 * j + 1];
-            acc[r * 16 + j] = pack2(lo32(c0), lo32(c1));      // real parts
-            acc[r * 16 + 8 + j] = pack2(hi32(c0), hi32(c1));  // imaginary parts
+            acc[r * 16 + j] = *reinterpret_cast<const u64*>(tre + lane * TS + r * 16 + 2 * j);
+            acc[r * 16 + 8 + j] = *reinterpret_cast<const u64*>(tim + lane * TS + r * 16 + 2 * j);
           }
         __syncwarp();
       }
@@ -610,18 +614,19 @@ k_rows(Geom g, int T, long long nitems, const int2* __restrict__ items,
         for (int r = 0; r < 2; ++r)
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            const u64 re = acc[r * 16 + j], im = acc[r * 16 + 8 + j];
-            tbuf[lane * 33 + r * 16 + 2 * j] = pack2(lo32(re), lo32(im));
-            tbuf[lane * 33 + r * 16 + 2 * j + 1] = pack2(hi32(re), hi32(im));
+            *reinterpret_cast<u64*>(tre + lane * TS + r * 16 + 2 * j) = acc[r * 16 + j];
+            *reinterpret_cast<u64*>(tim + lane * TS + r * 16 + 2 * j) = acc[r * 16 + 8 + j];
           }
         __syncwarp();
         if (x < nfx) {
           if (split) {
             for (int t = 0; t < T; ++t)
-              red_add_f32x2(reinterpret_cast<float2*>(gtile + (long long)t * g.nftot), tbuf[t * 33 + lane], 1);
+              red_add_f32x2(reinterpret_cast<float2*>(gtile + (long long)t * g.nftot),
+                            pack2(tre[t * TS + lane], tim[t * TS + lane]), 1);
           } else {
 #pragma unroll 4
-            for (int t = 0; t < T; ++t) gtile[(long long)t * g.nftot] = tbuf[t * 33 + lane];
+            for (int t = 0; t < T; ++t)
+              gtile[(long long)t * g.nftot] = pack2(tre[t * TS + lane], tim[t * TS + lane]);
           }
         }
         __syncwarp();
