@@ -32,6 +32,8 @@ for _p in (ROOT, ROOT / "baseline" / "_ref"):
         sys.path.insert(0, str(_p))
 
 METRIC = "3D 32-coil NUFFT op+adj_op throughput"
+# DRAM bytes of one launch of the row kernels at cfg-C, from profiles/r01_k_rows_duo_full.txt
+NCU_TRAFFIC_GB = {"spread": 57.6, "interp": 53.2}
 UNIT = "k-samples/s"
 
 
@@ -279,16 +281,20 @@ def run_b200(args):
     ms_max = float(ms_t.item())
     value = M * C * world / (ms_max * 1e-3) / 1e3
 
-    # per-kernel timings (CUDA events recorded by the library on the launching stream)
+    # per-kernel timings: CUDA events recorded by the library on the stream it launches on (torch's
+    # current stream), averaged over the timed steps' worth of extra iterations
     plan.enable_timing(True)
-    kt = {"spread_ms": [], "interp_ms": [], "fft_ms": [], "grid_ms": []}
+    kt = {"spread_ms": [], "interp_ms": [], "fft_ms": [], "grid_ms": [], "spread_rows_ms": [],
+          "interp_rows_ms": []}
     for _ in range(min(args.steps, 3)):
         op._op_device(img_d)
         t2 = plan.last_timings()
         op._adj_device(ksp_d)
         t1 = plan.last_timings()
         kt["interp_ms"].append(t2["interp_ms"])
+        kt["interp_rows_ms"].append(t2["rows_ms"])
         kt["spread_ms"].append(t1["spread_ms"])
+        kt["spread_rows_ms"].append(t1["rows_ms"])
         kt["fft_ms"].append(t2["fft_ms"] + t1["fft_ms"])
         kt["grid_ms"].append(t2["grid_ms"] + t1["grid_ms"])
     plan.enable_timing(False)
@@ -345,16 +351,21 @@ def run_b200(args):
     peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "6650 GB/s (of fallback)"
     Nf = int(np.prod(plan.nf))
     ab = algorithmic_bytes(int(np.prod(shape)), Nf, M, 3, C)
-    dom = max(("spread", kt["spread_ms"]), ("interp", kt["interp_ms"]), ("fft", kt["fft_ms"] / 2),
-              key=lambda kv: kv[1])
-    dom_name, dom_ms = dom
+    # dominant own kernel: the row kernel of the spreader or of the interpolator (k_rows<.., SPREAD>)
+    dom_name, dom_ms = max(("spread", kt["spread_rows_ms"]), ("interp", kt["interp_rows_ms"]),
+                           key=lambda kv: kv[1])
     achieved = ab[dom_name] / (dom_ms * 1e-3) / 1e9
+    is_cfg_c = (args.n == 256 and C == 32 and M == 1 << 23 and args.traj == "radial")
     roofline = {
-        "bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
-        "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-        "kernel_ms": kt, "algorithmic_bytes_per_launch": ab[dom_name],
+        "bound": "hbm", "kernel": f"k_rows<3,{plan.w},{'true' if dom_name == 'spread' else 'false'}> ({dom_name})",
+        "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+        # dram__bytes_read.sum + dram__bytes_write.sum of one launch, `ncu --set full` (profiles/)
+        "traffic": (NCU_TRAFFIC_GB[dom_name] * 1e9 if is_cfg_c else None),
+        "peak_source": peak_src, "kernel_ms": kt, "algorithmic_bytes_per_launch": ab[dom_name],
         "step_algorithmic_bytes": ab["pair_all_coils"],
         "step_frac": ab["pair_all_coils"] / (ms_max * 1e-3) / 1e9 / peak,
+        "note": "the row kernels are bound by the L1/shared data pipe and instruction issue, not by HBM "
+                "(ncu: l1tex 70 %, issue 55 %, dram 29 %); frac is quoted against the HBM floor as the contract asks",
     }
 
     cpu_baseline = None

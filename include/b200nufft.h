@@ -185,7 +185,8 @@ int b200_plan_set_option(b200_plan* plan, int key, int64_t value);
 /*
  * Timing hooks for the roofline report: the plan records CUDA events around its
  * dominant kernels.  out[0] = spread ms, out[1] = interp ms, out[2] = fft ms,
- * out[3] = pad/crop ms of the LAST execute call (synchronises the stream).
+ * out[3] = pad/crop ms, out[4] = the row kernel alone (inside spread or interp) of the LAST execute
+ * call (synchronises the stream).  With the fused FFT passes out[2] includes pad/crop and out[3] = 0.
  */
 int b200_plan_last_timings(b200_plan* plan, float out[8]);
 int b200_plan_enable_timing(b200_plan* plan, int on);

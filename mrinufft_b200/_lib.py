@@ -199,7 +199,8 @@ class Plan:
     def last_timings(self):
         out = (C.c_float * 8)()
         check(self._lib.b200_plan_last_timings(self._h, out), "b200_plan_last_timings")
-        return {"spread_ms": out[0], "interp_ms": out[1], "fft_ms": out[2], "grid_ms": out[3]}
+        return {"spread_ms": out[0], "interp_ms": out[1], "fft_ms": out[2], "grid_ms": out[3],
+                "rows_ms": out[4]}
 
 
 def header_symbols(header: Path | None = None):

@@ -410,7 +410,7 @@ int b200_plan_last_timings(b200_plan* p, float out[8]) {
   }
   DeviceGuard guard(p->device);
   for (int i = 0; i < 8; ++i) out[i] = 0.f;
-  for (int s = 0; s < 4; ++s) {
+  for (int s = 0; s < 5; ++s) {
     if (!p->ev_used[s]) continue;
     CUDA_TRY(cudaEventSynchronize(p->ev[2 * s + 1]));
     float ms = 0.f;

@@ -732,8 +732,15 @@ int launch_rows(b200_plan* p, RowsState* ts, float2* fw, int T, cudaStream_t st)
   const long long want = (ts->nitems + GROUP * WARPS - 1) / (GROUP * WARPS);
   const long long cap = (long long)p->num_sms * ctas_per_sm;
   const int grid = (int)(want < cap ? (want > 0 ? want : 1) : cap);
+  // slot 4 of the plan's timing events brackets the row kernel alone (bench.py roofline)
+  const bool timed = p->timing && p->ev_ok;
+  if (timed) cudaEventRecord(p->ev[8], st);
   kern<<<grid, THREADS, smem, st>>>(p->g, T, ts->nitems, ts->d_items, p->d_bin_start, ts->d_rec,
                                     ts->d_kt, fw, ts->d_counters);
+  if (timed) {
+    cudaEventRecord(p->ev[9], st);
+    p->ev_used[4] = 1;
+  }
   CHECK_LAUNCH();
   return B200_OK;
 }
