@@ -79,7 +79,10 @@ int do_spread(b200_plan* p, const float2* ksp, const float* density, float2* fw,
   int method = p->spread_method;
   if (method == 0) method = tiled_supported(p, T) ? 2 : 1;
   if (method == 2 && !tiled_supported(p, T)) method = 1;
-  if (method == 2) return spread_tiled(p, ksp, density, fw, T, st);
+  if (method == 2) {
+    const int rc = spread_tiled(p, ksp, density, fw, T, st);
+    if (rc != 1) return rc;  // 1: the row kernels cannot serve this trajectory
+  }
   CUDA_TRY(cudaMemsetAsync(fw, 0, (size_t)T * p->g.nftot * sizeof(float2), st));
   return spread_point_driven(p, ksp, density, fw, T, st);
 }
@@ -90,7 +93,10 @@ int do_interp(b200_plan* p, const float2* fw, float2* ksp, int T, float scale, c
   int method = p->interp_method;
   if (method == 0) method = tiled_supported(p, T) ? 2 : 1;
   if (method == 2 && !tiled_supported(p, T)) method = 1;
-  if (method == 2) return interp_tiled(p, fw, ksp, T, scale, obs, st);
+  if (method == 2) {
+    const int rc = interp_tiled(p, fw, ksp, T, scale, obs, st);
+    if (rc != 1) return rc;
+  }
   return interp_point_driven(p, fw, ksp, T, scale, obs, st);
 }
 
@@ -386,6 +392,7 @@ int b200_plan_set_option(b200_plan* p, int key, int64_t value) {
     case 0: p->spread_method = (int)value; break;
     case 1: p->interp_method = (int)value; break;
     case 2: p->fft_method = (int)value; break;
+    case 3: p->rows_bulk = (int)value; break;
     default:
       b200_set_error("unknown option key %d", key);
       return B200_EINVAL;

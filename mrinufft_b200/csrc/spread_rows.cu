@@ -52,24 +52,34 @@
 
 namespace {
 
+typedef unsigned long long u64;
+
 constexpr int CX = 16;          // cells per tile row (== pencil-bin width, B200_BIN_X)
 constexpr int NACC = 32;        // 64-bit accumulator registers per lane: [row 2][re/im 2][cell pair 8]
-constexpr int REC = 24;         // floats per point record: wx[7] xo | wy[7] y0 | wz[7] z0
-constexpr int BLK = 16;         // visits staged per block
+constexpr int REC = 28;         // floats per point record (112 B):
+constexpr int R_WY = 8;         //   [0..7]  pair-packed x weights P | [8..16] 0, wy[0..6], 0
+constexpr int R_WZ = 17;        //   [17..23] wz[0..6] | [24] (xo >> 1) + W/2 | [25] y0 | [26..27] pad
+constexpr int R_JY = 24;
+constexpr int VBLK = 16;        // visits per value block (cp.async / bulk-copy granularity)
+constexpr int MBLK = 32;        // visits per packet block (one lane stages one visit)
 constexpr int WARPS = 4;        // warps per CTA
 constexpr int THREADS = WARPS * 32;
 constexpr int CHUNK = 4096;     // visits per work item
-constexpr int NSLOT = 64;       // range slots per row (2 per lane)
 constexpr int GROUP = 4;        // work items fetched per atomic
 
-constexpr int ITEM_EMPTY = -1;        // chunk field: row without visits
-constexpr int ITEM_SPLIT = 1 << 30;   // chunk flag: row is shared by several items
+constexpr int ITEM_EMPTY = 1;   // item flags: tile without visits
+constexpr int ITEM_SPLIT = 2;   //             tile shared by several items
+
+// visit word: sorted point index | dz << 27 | (visit comes from the left neighbour's crossing bin) << 30
+constexpr unsigned VIS_SBITS = 27;
+constexpr unsigned VIS_SMASK = (1u << VIS_SBITS) - 1;
+constexpr unsigned VIS_NONE = 0xffffffffu;
 
 // per-warp shared memory (bytes)
-constexpr int SM_VBUF = 2 * BLK * 32 * 8;   // double-buffered coil values of BLK points
-constexpr int SM_META = 2 * BLK * 48;       // double-buffered packets {P0..P3, s0, s1, idx, s}
-constexpr int SM_SLOT = 2 * NSLOT * 4;      // pre[], begin[]
-constexpr int SM_WARP = SM_VBUF + SM_META + SM_SLOT;
+constexpr int SM_VBUF = 2 * VBLK * 32 * 8;  // double-buffered coil values of VBLK points
+constexpr int SM_META = 2 * MBLK * 48;      // double-buffered packets {P0..P3, s0, s1, idx, s}
+constexpr int SM_MBAR = 16;                 // two mbarriers (bulk-copy variant)
+constexpr int SM_WARP = SM_VBUF + SM_META + SM_MBAR;
 constexpr int TS = 34;          // row stride (floats) of the transpose planes
 static_assert(SM_VBUF + SM_META >= 2 * 32 * TS * 4, "transpose buffers must fit in vbuf+meta");
 
@@ -77,16 +87,20 @@ struct RowsState {
   float* d_rec = nullptr;        // [M][REC] per sorted point
   float2* d_kt = nullptr;        // [M][32] transposed (sorted point, coil) k-space batch
   size_t kt_bytes = 0;
-  int32_t* d_nchunks = nullptr;  // [nrows + 1]
+  int32_t* d_iperm = nullptr;    // [M] point index -> sorted position
+  int32_t* d_tot = nullptr;      // [nrows + 1] visits per tile
+  uint32_t* d_vis_start = nullptr;  // [nrows + 1] first visit word of a tile
   int32_t* d_item_start = nullptr;  // [nrows + 1]
-  int2* d_items = nullptr;       // [nitems] {row, chunk | flags}
+  int4* d_items = nullptr;       // [nitems] {tile, flags, first visit word, visit count}
+  uint32_t* d_vis = nullptr;     // [nvis] visit words, tile by tile
   int32_t* d_split_rows = nullptr;
-  int* d_counters = nullptr;     // [0] work counter, [1] split-row counter
+  int* d_counters = nullptr;     // [0] work counter, [1] split-row counter, [2..3] total visits (u64)
   void* d_scan_tmp = nullptr;
   size_t scan_tmp_bytes = 0;
-  long long nrows = 0, nitems = 0, nsplit = 0;
+  long long nrows = 0, nitems = 0, nsplit = 0, nvis = 0;
   long long M = -1;
   bool valid = false;
+  bool unsupported = false;      // too many visits / points for the 32-bit visit words
 };
 
 RowsState* state(b200_plan* p) {
@@ -179,6 +193,10 @@ __device__ __forceinline__ void slot_range(const Geom& g, const RowCoord& rc, in
 }
 
 // ------------------------------------------------------------------------------ pre-passes
+// Per-point record, computed once per trajectory: everything of a visit that does not depend on
+// the visiting tile.  The x weights are stored pair-packed for the parity of the point's offset
+// inside its tile (tile lengths are even, so the parity is the same seen from the right
+// neighbour): P_q = (w[2q - par], w[2q + 1 - par]).
 template <int W>
 __global__ void __launch_bounds__(256)
 k_point_records(Geom g, long long M, const float* __restrict__ poly,
@@ -194,14 +212,15 @@ k_point_records(Geom g, long long M, const float* __restrict__ poly,
   // axis roles: x = fastest axis (dim-1), y = dim-2, z = dim-3
   const int32_t* op[3] = {o0, o1, o2};
   const float* fp[3] = {f0, f1, f2};
-  float out[REC];
-#pragma unroll
-  for (int i = 0; i < REC; ++i) out[i] = 0.f;
+  float wgt[3][8];
+  int org[3] = {0, 0, 0};
 #pragma unroll
   for (int r = 0; r < 3; ++r) {  // r = 0: x, 1: y, 2: z
+#pragma unroll
+    for (int i = 0; i < 8; ++i) wgt[r][i] = 0.f;
     const int a = g.dim - 1 - r;
     if (a < 0) {
-      out[r * 8] = 1.f;  // unused axis: single unit tap
+      wgt[r][0] = 1.f;  // unused axis: single unit tap
       continue;
     }
     const float z = fmaf(2.f, fp[a][s], (float)(W - 1));
@@ -209,111 +228,218 @@ k_point_records(Geom g, long long M, const float* __restrict__ poly,
     for (int i = 0; i < W; ++i) {
       float acc = spoly[g.deg * W + i];
       for (int k = g.deg - 1; k >= 0; --k) acc = fmaf(acc, z, spoly[k * W + i]);
-      out[r * 8 + i] = acc;
+      wgt[r][i] = acc;
     }
-    int o = op[a][s];
-    if (r == 0) o = o % CX;  // x: offset inside the point's own tile
-    out[r * 8 + 7] = __int_as_float(o);
+    org[r] = op[a][s];
   }
+  const int xo = org[0] % CX;  // offset inside the point's own tile
+  const bool odd = xo & 1;
+  float out[REC];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float we = wgt[0][i];                    // W <= 7: wgt[0][7] = 0
+    const float wo = i >= 1 ? wgt[0][i - 1] : 0.f;
+    out[i] = odd ? wo : we;
+  }
+  out[R_WY] = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) out[R_WY + 1 + i] = wgt[1][i];
+#pragma unroll
+  for (int i = 0; i < 7; ++i) out[R_WZ + i] = wgt[2][i];
+  out[R_JY] = __int_as_float((xo >> 1) + W / 2);
+  out[R_JY + 1] = __int_as_float(org[1]);
+  out[26] = out[27] = 0.f;
   float4* dst = reinterpret_cast<float4*>(rec + s * REC);
 #pragma unroll
   for (int q = 0; q < REC / 4; ++q)
     dst[q] = make_float4(out[4 * q], out[4 * q + 1], out[4 * q + 2], out[4 * q + 3]);
 }
 
-// visits per row -> number of work items of the row (0 for ids outside the grid)
+__global__ void __launch_bounds__(256)
+k_invert_perm(long long M, const int32_t* __restrict__ perm, int32_t* __restrict__ iperm) {
+  const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s < M) iperm[perm[s]] = (int32_t)s;
+}
+
+// visits per tile (0 for ids outside the grid) and their grand total
 template <int DIM, int W>
 __global__ void __launch_bounds__(256)
-k_row_chunks(Geom g, long long nrows, const int32_t* __restrict__ bin_start,
-             int32_t* __restrict__ nchunks) {
+k_row_totals(Geom g, long long nrows, const int32_t* __restrict__ bin_start,
+             int32_t* __restrict__ tot, unsigned long long* __restrict__ grand) {
   const long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (row > nrows) return;
-  if (row == nrows) {
-    nchunks[row] = 0;
-    return;
-  }
-  RowCoord rc;
-  if (!decode_row<DIM>(g, row, &rc)) {
-    nchunks[row] = 0;
-    return;
-  }
-  constexpr int NZ = (DIM == 3) ? W : 1;
   long long total = 0;
-  for (int slot = 0; slot < NZ * 6; ++slot) {
-    int b, l;
-    slot_range<DIM, W>(g, rc, slot, bin_start, &b, &l);
-    total += l;
-  }
-  // rows without visits still get one (empty) item, flagged -1: the spreader writes their zeros
-  nchunks[row] = total == 0 ? -1 : (int32_t)((total + CHUNK - 1) / CHUNK);
-}
-
-__global__ void __launch_bounds__(256)
-k_abs_chunks(long long n, const int32_t* __restrict__ in, int32_t* __restrict__ out) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) out[i] = in[i] < 0 ? 1 : in[i];
-}
-
-__global__ void __launch_bounds__(256)
-k_fill_items(long long nrows, const int32_t* __restrict__ nchunks,
-             const int32_t* __restrict__ item_start, int2* __restrict__ items,
-             int32_t* __restrict__ split_rows, int* __restrict__ split_counter) {
-  const long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (row >= nrows) return;
-  const int n = nchunks[row];
-  const int at = item_start[row];
-  if (n < 0) {
-    items[at] = make_int2((int)row, ITEM_EMPTY);
-  } else if (n == 1) {
-    items[at] = make_int2((int)row, 0);
-  } else if (n > 1) {
-    for (int c = 0; c < n; ++c) items[at + c] = make_int2((int)row, c | ITEM_SPLIT);
-    split_rows[atomicAdd(split_counter, 1)] = (int32_t)row;
-  }
-}
-
-// kt[s][t] = ksp[t][perm[s]] * density[perm[s]]   (t < T; lanes t >= T are zero-filled)
-__global__ void __launch_bounds__(256)
-k_gather_kspace(long long M, int T, const int32_t* __restrict__ perm,
-                const float2* __restrict__ ksp, const float* __restrict__ density,
-                float2* __restrict__ kt) {
-  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  long long s = idx >> 5;
-  int t = (int)(idx & 31);
-  if (s >= M) return;
-  float2 v = make_float2(0.f, 0.f);
-  if (t < T) {
-    const int j = perm[s];
-    v = ksp[(long long)t * M + j];
-    if (density) {
-      const float d = density[j];
-      v.x *= d;
-      v.y *= d;
+  RowCoord rc;
+  if (row < nrows && decode_row<DIM>(g, row, &rc)) {
+    constexpr int NZ = (DIM == 3) ? W : 1;
+    for (int slot = 0; slot < NZ * 6; ++slot) {
+      int b, l;
+      slot_range<DIM, W>(g, rc, slot, bin_start, &b, &l);
+      total += l;
     }
   }
-  kt[s * 32 + t] = v;
+  // tiles outside the grid get -1: no item at all
+  if (row <= nrows)
+    tot[row] = (row == nrows || !decode_row<DIM>(g, row, &rc)) ? -1 : (int32_t)min(total, (long long)INT32_MAX);
+  long long wsum = total;
+#pragma unroll
+  for (int d = 16; d >= 1; d >>= 1) wsum += __shfl_down_sync(0xffffffffu, wsum, d);
+  if ((threadIdx.x & 31) == 0 && wsum > 0) atomicAdd(grand, (unsigned long long)wsum);
 }
 
-// ksp[t][perm[s]] = scale * kt[s][t] (- obs[t][perm[s]])
+// per tile: (visits, items) as inputs of the two exclusive scans
 __global__ void __launch_bounds__(256)
-k_scatter_kspace(long long M, int T, const int32_t* __restrict__ perm,
+k_scan_inputs(long long n, const int32_t* __restrict__ tot, uint32_t* __restrict__ nvis,
+              int32_t* __restrict__ nitem) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int t = tot[i];
+  nvis[i] = t > 0 ? (uint32_t)t : 0u;
+  nitem[i] = t < 0 ? 0 : (t == 0 ? 1 : (t + CHUNK - 1) / CHUNK);  // an empty tile still owns one item
+}
+
+__global__ void __launch_bounds__(256)
+k_fill_items(long long nrows, const int32_t* __restrict__ tot,
+             const uint32_t* __restrict__ vis_start, const int32_t* __restrict__ item_start,
+             int4* __restrict__ items, int32_t* __restrict__ split_rows,
+             int* __restrict__ split_counter) {
+  const long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= nrows) return;
+  const int t = tot[row];
+  if (t < 0) return;
+  const int at = item_start[row];
+  if (t == 0) {
+    items[at] = make_int4((int)row, ITEM_EMPTY, 0, 0);
+    return;
+  }
+  const int n = (t + CHUNK - 1) / CHUNK;
+  const int flags = n > 1 ? ITEM_SPLIT : 0;
+  for (int c = 0; c < n; ++c)
+    items[at + c] = make_int4((int)row, flags, (int)(vis_start[row] + (uint32_t)c * CHUNK),
+                              min(CHUNK, t - c * CHUNK));
+  if (n > 1) split_rows[atomicAdd(split_counter, 1)] = (int32_t)row;
+}
+
+// The visit list of every tile, written once per trajectory: one warp per tile concatenates the
+// tile's key ranges (slot order = dz-major, as the prefix sums of k_row_totals assume).
+template <int DIM, int W>
+__global__ void __launch_bounds__(256)
+k_build_visits(Geom g, long long nrows, const int32_t* __restrict__ bin_start,
+               const int32_t* __restrict__ tot, const uint32_t* __restrict__ vis_start,
+               uint32_t* __restrict__ vis) {
+  const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= nrows || tot[row] <= 0) return;
+  RowCoord rc;
+  decode_row<DIM>(g, row, &rc);
+  uint32_t* out = vis + vis_start[row];
+  int b[2], l[2];
+  slot_range<DIM, W>(g, rc, lane, bin_start, &b[0], &l[0]);
+  slot_range<DIM, W>(g, rc, lane + 32, bin_start, &b[1], &l[1]);
+  int inc0 = l[0], inc1 = l[1];
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const int u0 = __shfl_up_sync(0xffffffffu, inc0, d);
+    const int u1 = __shfl_up_sync(0xffffffffu, inc1, d);
+    if (lane >= d) {
+      inc0 += u0;
+      inc1 += u1;
+    }
+  }
+  const int tot0 = __shfl_sync(0xffffffffu, inc0, 31);
+  const int pre[2] = {inc0 - l[0], tot0 + inc1 - l[1]};
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int slot = lane + 32 * h;
+    const unsigned tag = ((unsigned)((slot >> 1) / 3) << VIS_SBITS) | ((((slot >> 1) % 3) == 2 ? 1u : 0u) << 30);
+    // short ranges: written by the owning lane; long ranges (dense k-space centre): by the whole warp
+    const bool is_long = l[h] > 64;
+    if (!is_long)
+      for (int i = 0; i < l[h]; ++i) out[pre[h] + i] = (unsigned)(b[h] + i) | tag;
+    unsigned longs = __ballot_sync(0xffffffffu, is_long);
+    while (longs) {
+      const int src = __ffs(longs) - 1;
+      longs &= longs - 1;
+      const int bb = __shfl_sync(0xffffffffu, b[h], src);
+      const int ll = __shfl_sync(0xffffffffu, l[h], src);
+      const int pp = __shfl_sync(0xffffffffu, pre[h], src);
+      const unsigned tg = __shfl_sync(0xffffffffu, tag, src);
+      for (int i = lane; i < ll; i += 32) out[pp + i] = (unsigned)(bb + i) | tg;
+    }
+  }
+}
+
+// Transposes between the caller's k-space batch ksp[t][j] and the row kernels' kt[s][t]
+// (s = sorted position of sample j).  A warp moves 32 consecutive samples x 32 coils: coalesced
+// 256-byte rows per coil on the ksp side, one full 256-byte line per sample on the kt side.
+constexpr int KT_WARPS = 4;
+constexpr int KT_STRIDE = 33;  // u64 row stride of the transpose tile
+
+// kt[iperm[j]][t] = ksp[t][j] * density[j]   (t < T; coils t >= T are zero-filled)
+__global__ void __launch_bounds__(KT_WARPS * 32)
+k_gather_kspace(long long M, int T, const int32_t* __restrict__ iperm,
+                const float2* __restrict__ ksp, const float* __restrict__ density,
+                float2* __restrict__ kt) {
+  __shared__ u64 tile[KT_WARPS][32 * KT_STRIDE];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long j0 = ((long long)blockIdx.x * KT_WARPS + warp) * 32;
+  if (j0 >= M) return;
+  const long long j = j0 + lane;
+  const bool live = j < M;
+  const float d = (live && density) ? density[j] : 1.f;
+  const int s = live ? iperm[j] : -1;
+  u64* tl = tile[warp];
+  const u64* src = reinterpret_cast<const u64*>(ksp);
+#pragma unroll 8
+  for (int t = 0; t < 32; ++t) {
+    float2 v = make_float2(0.f, 0.f);
+    if (t < T && live) {
+      const u64 raw = __ldg(src + (long long)t * M + j);
+      v = make_float2(__uint_as_float((unsigned)raw) * d, __uint_as_float((unsigned)(raw >> 32)) * d);
+    }
+    tl[lane * KT_STRIDE + t] = ((u64)__float_as_uint(v.y) << 32) | (u64)__float_as_uint(v.x);
+  }
+  __syncwarp();
+  u64* dst = reinterpret_cast<u64*>(kt);
+#pragma unroll 8
+  for (int i = 0; i < 32; ++i) {
+    const int si = __shfl_sync(0xffffffffu, s, i);
+    if (si >= 0) dst[(long long)si * 32 + lane] = tl[i * KT_STRIDE + lane];
+  }
+}
+
+// ksp[t][j] = scale * kt[iperm[j]][t] (- obs[t][j])
+__global__ void __launch_bounds__(KT_WARPS * 32)
+k_scatter_kspace(long long M, int T, const int32_t* __restrict__ iperm,
                  const float2* __restrict__ kt, float2* __restrict__ ksp, float scale,
                  const float2* __restrict__ obs) {
-  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  long long s = idx >> 5;
-  int t = (int)(idx & 31);
-  if (s >= M || t >= T) return;
-  const int j = perm[s];
-  float2 v = kt[s * 32 + t];
-  v.x *= scale;
-  v.y *= scale;
-  const long long oi = (long long)t * M + j;
-  if (obs) {
-    const float2 y = obs[oi];
-    v.x -= y.x;
-    v.y -= y.y;
+  __shared__ u64 tile[KT_WARPS][32 * KT_STRIDE];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long j0 = ((long long)blockIdx.x * KT_WARPS + warp) * 32;
+  if (j0 >= M) return;
+  const long long j = j0 + lane;
+  const bool live = j < M;
+  const int s = live ? iperm[j] : -1;
+  u64* tl = tile[warp];
+  const u64* src = reinterpret_cast<const u64*>(kt);
+#pragma unroll 8
+  for (int i = 0; i < 32; ++i) {
+    const int si = __shfl_sync(0xffffffffu, s, i);
+    tl[i * KT_STRIDE + lane] = si >= 0 ? __ldg(src + (long long)si * 32 + lane) : 0ull;
   }
-  ksp[oi] = v;
+  __syncwarp();
+  if (!live) return;
+#pragma unroll 8
+  for (int t = 0; t < T; ++t) {
+    const u64 raw = tl[lane * KT_STRIDE + t];
+    float2 v = make_float2(__uint_as_float((unsigned)raw) * scale, __uint_as_float((unsigned)(raw >> 32)) * scale);
+    const long long oi = (long long)t * M + j;
+    if (obs) {
+      const float2 y = __ldg(obs + oi);
+      v.x -= y.x;
+      v.y -= y.y;
+    }
+    ksp[oi] = v;
+  }
 }
 
 // rows shared by several work items are accumulated with red.add: zero them first
@@ -337,7 +463,6 @@ k_zero_split_rows(Geom g, int T, long long nsplit, const int32_t* __restrict__ s
 // Per-visit tap kernels: generated inline PTX (tools/gen_taps.py) -- one `brx.idx` on the x offset,
 // then w packed `fma.rn.f32x2` (SASS FFMA2) on statically indexed 64-bit (re, im) accumulators.
 // A C++ `switch` is lowered by nvcc to a compare/branch tree that cost 17 issue slots per visit.
-typedef unsigned long long u64;
 #include "taps_generated.inc"
 
 template <int W>
@@ -360,6 +485,8 @@ __device__ __forceinline__ void taps_interp(u64 (&S)[4], u64 (&acc)[NACC], unsig
 __device__ __forceinline__ u64 pack2(float lo, float hi) {
   return ((u64)__float_as_uint(hi) << 32) | (u64)__float_as_uint(lo);
 }
+__device__ __forceinline__ float lo32(u64 v) { return __uint_as_float((unsigned)v); }
+__device__ __forceinline__ float hi32(u64 v) { return __uint_as_float((unsigned)(v >> 32)); }
 
 // kt[addr] += p for lanes with pred != 0 (vector reduction, no branch)
 __device__ __forceinline__ void red_add_f32x2(float2* addr, u64 p, int pred) {
@@ -374,9 +501,10 @@ __device__ __forceinline__ void red_add_f32x2(float2* addr, u64 p, int pred) {
       : "memory");
 }
 
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
-  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gsrc) : "memory");
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void cp_async16(unsigned smem_dst, const void* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;\n" ::"r"(smem_dst), "l"(gsrc) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 template <int N>
@@ -384,40 +512,89 @@ __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
 }
 
-// registers of one lane's visit between "issue" (loads in flight) and "finish" (meta written)
+// bulk-copy (TMA) variant of the value staging: one 256-byte copy per visit, completion on an mbarrier
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@!p bra WAIT_LOOP;\n"
+      "}\n" ::"r"(bar), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(unsigned smem_dst, const void* gsrc, unsigned bytes, unsigned bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smem_dst),
+      "l"(gsrc), "r"(bytes), "r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
+
+// one staged visit as the consume loop sees it: 48-byte packet, read with warp-broadcast loads
+struct Packet {
+  u64 P[4];     // pair-packed x weights
+  float s0, s1; // row scales wy[dy] wz[dz], wy[dy + 1] wz[dz]
+  unsigned idx; // tap-kernel case: floor(off / 2) + W / 2
+  unsigned s;   // sorted point index
+};
+__device__ __forceinline__ void load_packet(unsigned addr, Packet& p) {
+  asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];\n" : "=l"(p.P[0]), "=l"(p.P[1]) : "r"(addr));
+  asm volatile("ld.shared.v2.b64 {%0, %1}, [%2+16];\n" : "=l"(p.P[2]), "=l"(p.P[3]) : "r"(addr));
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4+32];\n"
+               : "=f"(p.s0), "=f"(p.s1), "=r"(p.idx), "=r"(p.s)
+               : "r"(addr));
+}
+__device__ __forceinline__ u64 lds64(unsigned addr) {
+  u64 v;
+  asm volatile("ld.shared.b64 %0, [%1];\n" : "=l"(v) : "r"(addr));
+  return v;
+}
+
+// registers of one lane's visit between "issue" (record loads in flight) and "finish" (packet written)
 struct Staged {
-  float4 a, b;   // wx[0..6], xo
-  float4 c, d;   // wy[0..6], y0
+  float4 p0, p1;  // pair-packed x weights
   float wz;
-  int s;         // sorted point index, -1 if this lane has no visit in the block
-  int left_len;  // 0, or the length of the left tile for left-crossing visits
+  int jbi, y0;
+  const float* r;
 };
 
-__device__ __forceinline__ float lo32(u64 v) { return __uint_as_float((unsigned)v); }
-__device__ __forceinline__ float hi32(u64 v) { return __uint_as_float((unsigned)(v >> 32)); }
-
-template <int DIM, int W, bool SPREAD>
+template <int DIM, int W, bool SPREAD, bool BULK>
 __global__ void __launch_bounds__(THREADS, 4)
-k_rows(Geom g, int T, long long nitems, const int2* __restrict__ items,
-       const int32_t* __restrict__ bin_start, const float* __restrict__ rec,
+k_rows(Geom g, int T, long long nitems, const int4* __restrict__ items,
+       const uint32_t* __restrict__ vis, const float* __restrict__ rec,
        float2* __restrict__ kt, float2* __restrict__ fw, int* __restrict__ counter) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   unsigned char* wsm = smem_raw + (size_t)warp * SM_WARP;
-  u64* vbuf = reinterpret_cast<u64*>(wsm);                              // [2][BLK][32] (re, im)
-  uint4* meta = reinterpret_cast<uint4*>(wsm + SM_VBUF);                // [2][BLK][3]
-  int* s_pre = reinterpret_cast<int*>(wsm + SM_VBUF + SM_META);         // [NSLOT]
-  int* s_beg = s_pre + NSLOT;                                           // [NSLOT]
+  const unsigned vbuf_a = smem_u32(wsm);               // [2][VBLK][32] (re, im)
+  const unsigned meta_a = smem_u32(wsm + SM_VBUF);     // [2][MBLK] packets of 48 bytes
+  const unsigned mbar_a = smem_u32(wsm + SM_VBUF + SM_META);
+  uint4* meta = reinterpret_cast<uint4*>(wsm + SM_VBUF);
   // transpose buffers (alias vbuf/meta): real and imaginary planes [32 coils][34] floats, so that a
   // lane reads / writes its (cell 2j, cell 2j+1) register pairs with one conflict-free 64-bit access
   float* tre = reinterpret_cast<float*>(wsm);
   float* tim = tre + 32 * TS;
-  constexpr int JB0 = W / 2;  // idx = floor(off / 2) + JB0
 
   const int nfx = g.nf[DIM - 1];
   const int nfy = g.nf[DIM - 2];
   const int nbx = num_xtiles<DIM>(g);
   u64* fw64 = reinterpret_cast<u64*>(fw);
+  unsigned phase = 0;  // bit b: parity the next wait on mbarrier b expects
+  if (SPREAD && BULK) {
+    if (lane == 0) {
+      mbar_init(mbar_a, 1);
+      mbar_init(mbar_a + 8, 1);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    __syncwarp();
+  }
 
   for (;;) {
     long long item0 = 0;
@@ -428,48 +605,24 @@ k_rows(Geom g, int T, long long nitems, const int2* __restrict__ items,
     for (int gi = 0; gi < GROUP; ++gi) {
       const long long item = item0 + gi;
       if (item >= nitems) break;
-      const int2 it = __ldg(items + item);
+      const int4 it = __ldg(items + item);
       RowCoord rc;
-      if (!decode_row<DIM>(g, it.x, &rc)) continue;
+      decode_row<DIM>(g, it.x, &rc);
       // flush / load role of this lane: row (lane >> 4) of the pair, cell (lane & 15)
       const int x = rc.bx * CX + (lane & 15);
       u64* gtile = fw64 + rc.rowbase + (long long)(lane >> 4) * nfx + x;
-      const bool split = (it.y != ITEM_EMPTY) && (it.y & ITEM_SPLIT);
-
-      if (it.y == ITEM_EMPTY) {
+      if (it.y & ITEM_EMPTY) {
         if (SPREAD && x < nfx) {
           for (int t = 0; t < T; ++t) gtile[(long long)t * g.nftot] = 0ull;
         }
         continue;
       }
-      const int chunk = it.y & (ITEM_SPLIT - 1);
-
-      // ---- ranges of this tile: 2 slots per lane, exclusive prefix sum over the 64 slots
-      int b0, l0, b1, l1;
-      slot_range<DIM, W>(g, rc, lane, bin_start, &b0, &l0);
-      slot_range<DIM, W>(g, rc, lane + 32, bin_start, &b1, &l1);
-      int inc0 = l0, inc1 = l1;
-#pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-        const int u0 = __shfl_up_sync(0xffffffffu, inc0, d);
-        const int u1 = __shfl_up_sync(0xffffffffu, inc1, d);
-        if (lane >= d) {
-          inc0 += u0;
-          inc1 += u1;
-        }
-      }
-      const int tot0 = __shfl_sync(0xffffffffu, inc0, 31);
-      const int total = tot0 + __shfl_sync(0xffffffffu, inc1, 31);
-      __syncwarp();
-      s_pre[lane] = inc0 - l0;
-      s_pre[lane + 32] = tot0 + inc1 - l1;
-      s_beg[lane] = b0;
-      s_beg[lane + 32] = b1;
-      __syncwarp();
-      const int v_lo = chunk * CHUNK;
-      const int v_hi = min(total, v_lo + CHUNK);
-      const int nblk = (v_hi - v_lo + BLK - 1) / BLK;
-      const int left_len = (rc.bx == 0) ? (nfx - (nbx - 1) * CX) : CX;
+      const bool split = it.y & ITEM_SPLIT;
+      const uint32_t* v = vis + (uint32_t)it.z;
+      const int nvis = it.w;
+      const int nsub = (nvis + VBLK - 1) / VBLK;
+      // a left neighbour's crossing point lands at x offset (xo - length of the left tile)
+      const int lhalf = ((rc.bx == 0) ? (nfx - (nbx - 1) * CX) : CX) >> 1;
 
       // ---- accumulators: acc[r*16 + c*8 + j] = (cell 2j, cell 2j+1) of row r, c = re / im
       u64 acc[NACC];
@@ -480,10 +633,10 @@ k_rows(Geom g, int T, long long nitems, const int2* __restrict__ items,
         // load the tile: coalesced per coil (128 B per row) -> smem -> registers (lane = coil)
 #pragma unroll 8
         for (int t = 0; t < 32; ++t) {
-          u64 v = 0ull;
-          if (t < T && x < nfx) v = __ldg(gtile + (long long)t * g.nftot);
-          tre[t * TS + lane] = lo32(v);
-          tim[t * TS + lane] = hi32(v);
+          u64 q = 0ull;
+          if (t < T && x < nfx) q = __ldg(gtile + (long long)t * g.nftot);
+          tre[t * TS + lane] = lo32(q);
+          tim[t * TS + lane] = hi32(q);
         }
         __syncwarp();
 #pragma unroll
@@ -496,120 +649,137 @@ k_rows(Geom g, int T, long long nitems, const int2* __restrict__ items,
         __syncwarp();
       }
 
-      // ---- staging helpers
-      auto stage_issue = [&](int blk, int buf, Staged& st) {
-        const int v = v_lo + blk * BLK + lane;
-        st.s = -1;
-        st.left_len = 0;
-        int dz = 0;
-        if (lane < BLK && v < v_hi) {
-          int pos = 0;
-#pragma unroll
-          for (int step = NSLOT / 2; step >= 1; step >>= 1)
-            if (s_pre[pos + step] <= v) pos += step;
-          st.s = s_beg[pos] + (v - s_pre[pos]);
-          const int sub = (pos >> 1) % 3;
-          dz = (pos >> 1) / 3;
-          if (sub == 2) st.left_len = left_len;
-          const float4* r = reinterpret_cast<const float4*>(rec + (long long)st.s * REC);
-          st.a = __ldg(r);
-          st.b = __ldg(r + 1);
-          st.c = __ldg(r + 2);
-          st.d = __ldg(r + 3);
-          st.wz = (DIM == 3) ? __ldg(rec + (long long)st.s * REC + 16 + dz) : 1.f;
+      // ---- staging: packets in blocks of 32 visits (one lane = one visit), values in blocks of 16
+      auto meta_issue = [&](unsigned w, Staged& st) {
+        if (w != VIS_NONE) {
+          const float* r = rec + (long long)(w & VIS_SMASK) * REC;
+          st.r = r;
+          st.p0 = __ldg(reinterpret_cast<const float4*>(r));
+          st.p1 = __ldg(reinterpret_cast<const float4*>(r) + 1);
+          const int2 jy = __ldg(reinterpret_cast<const int2*>(r + R_JY));
+          st.jbi = jy.x - (int)(w >> 30) * lhalf;
+          st.y0 = jy.y;
+          st.wz = (DIM == 3) ? __ldg(r + R_WZ + ((w >> VIS_SBITS) & 7u)) : 1.f;
         }
-        if (SPREAD) {
-          // coil values of the block's points: 2 points per instruction, 16 bytes per lane
-          u64* vb = vbuf + buf * (BLK * 32);
+      };
+      auto meta_finish = [&](int mb, unsigned w, const Staged& st) {
+        if (w != VIS_NONE) {
+          // row scales: row y takes wy[dy], row y+1 takes wy[dy+1]  (dy = y - y0 in [-1, W-1];
+          // the record stores 0, wy[0..6], 0 so that both loads are unconditional)
+          int dy = rc.y - st.y0;
+          if (dy < -1) dy += nfy;
+          const float s0 = __ldg(st.r + R_WY + 1 + dy) * st.wz;
+          const float s1 = __ldg(st.r + R_WY + 2 + dy) * st.wz;
+          uint4* m = meta + ((mb & 1) * MBLK + lane) * 3;
+          m[0] = make_uint4(__float_as_uint(st.p0.x), __float_as_uint(st.p0.y), __float_as_uint(st.p0.z),
+                            __float_as_uint(st.p0.w));
+          m[1] = make_uint4(__float_as_uint(st.p1.x), __float_as_uint(st.p1.y), __float_as_uint(st.p1.z),
+                            __float_as_uint(st.p1.w));
+          m[2] = make_uint4(__float_as_uint(s0), __float_as_uint(s1), (unsigned)st.jbi, w & VIS_SMASK);
+        }
+      };
+      // coil values of value block j (visits 16 j .. 16 j + 15; their words sit in lanes
+      // 16 (j & 1) .. of `w`, the word register of packet block j >> 1)
+      auto values_issue = [&](int j, unsigned w) {
+        const int buf = j & 1;
+        if (BULK) {
+          const int n = min(VBLK, nvis - j * VBLK);
+          fence_proxy_async();
+          if (lane == 0) mbar_expect_tx(mbar_a + 8 * buf, (unsigned)n * 256u);
+          __syncwarp();
+          if ((lane >> 4) == buf && w != VIS_NONE)
+            bulk_g2s(vbuf_a + (unsigned)(buf * VBLK + (lane & 15)) * 256u,
+                     kt + (long long)(w & VIS_SMASK) * 32, 256u, mbar_a + 8 * buf);
+        } else {
+          // 2 points per instruction, 16 bytes per lane
 #pragma unroll
-          for (int i = 0; i < BLK / 2; ++i) {
+          for (int i = 0; i < VBLK / 2; ++i) {
             const int kk = 2 * i + (lane >> 4);
-            const int sk = __shfl_sync(0xffffffffu, st.s, kk);
-            if (sk >= 0)
-              cp_async16(vb + kk * 32 + (lane & 15) * 2, kt + (long long)sk * 32 + (lane & 15) * 2);
+            const unsigned wk = __shfl_sync(0xffffffffu, w, buf * VBLK + kk);
+            if (wk != VIS_NONE)
+              cp_async16(vbuf_a + (unsigned)((buf * VBLK + kk) * 32 + (lane & 15) * 2) * 8u,
+                         kt + (long long)(wk & VIS_SMASK) * 32 + (lane & 15) * 2);
           }
           cp_async_commit();
         }
       };
-      auto stage_finish = [&](int buf, const Staged& st) {
-        if (st.s >= 0) {
-          // row scales: row y takes wy[dy], row y+1 takes wy[dy+1]  (dy = y - y0 in [-1, W-1])
-          int dy = rc.y - __float_as_int(st.d.w);
-          if (dy < -1) dy += nfy;
-          const float wy[8] = {st.c.x, st.c.y, st.c.z, st.c.w, st.d.x, st.d.y, st.d.z, 0.f};
-          float s0 = 0.f, s1 = 0.f;
-#pragma unroll
-          for (int i = 0; i < W; ++i) {
-            s0 = dy == i ? wy[i] : s0;
-            s1 = dy + 1 == i ? wy[i] : s1;
-          }
-          s0 *= st.wz;
-          s1 *= st.wz;
-          // pair-packed x weights: P_q = (w[2q - par], w[2q + 1 - par])
-          const int off = __float_as_int(st.b.w) - st.left_len;
-          const int jb = off >> 1;
-          const bool odd = off & 1;
-          const float w[9] = {0.f, st.a.x, st.a.y, st.a.z, st.a.w, st.b.x, st.b.y, st.b.z, 0.f};
-          float pw[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            // even: pw[i] = wx[i] ; odd: pw[i] = wx[i - 1]   (wx[i] = w[i + 1], zero outside [0, W))
-            const float we = (i < W) ? w[i + 1] : 0.f;
-            const float wo = (i >= 1 && i - 1 < W) ? w[i] : 0.f;
-            pw[i] = odd ? wo : we;
-          }
-          uint4* m = meta + (buf * BLK + lane) * 3;
-          m[0] = make_uint4(__float_as_uint(pw[0]), __float_as_uint(pw[1]), __float_as_uint(pw[2]),
-                            __float_as_uint(pw[3]));
-          m[1] = make_uint4(__float_as_uint(pw[4]), __float_as_uint(pw[5]), __float_as_uint(pw[6]),
-                            __float_as_uint(pw[7]));
-          m[2] = make_uint4(__float_as_uint(s0), __float_as_uint(s1), (unsigned)(jb + JB0), (unsigned)st.s);
-        }
+      auto load_word = [&](int mb) -> unsigned {
+        const int i = mb * MBLK + lane;
+        return i < nvis ? __ldg(v + i) : VIS_NONE;
       };
 
+      unsigned w_cur = load_word(0);   // words of the packet block being consumed / staged
+      unsigned w_nxt = load_word(1);   // prefetched one block ahead
       Staged st;
-      if (nblk > 0) {
-        stage_issue(0, 0, st);
-        stage_finish(0, st);
-      }
-      for (int blk = 0; blk < nblk; ++blk) {
-        const int cur = blk & 1;
-        const bool more = blk + 1 < nblk;
-        if (more) stage_issue(blk + 1, cur ^ 1, st);
-        if (SPREAD) {
-          if (more) cp_async_wait<1>();
-          else cp_async_wait<0>();
-        }
-        __syncwarp();
-        const int n = min(BLK, v_hi - v_lo - blk * BLK);
-        const uint4* m = meta + cur * BLK * 3;
-        const u64* vb = vbuf + cur * (BLK * 32) + lane;
+      meta_issue(w_cur, st);
+      meta_finish(0, w_cur, st);
+      if (SPREAD) values_issue(0, w_cur);
+      unsigned w_val = w_cur;          // words of the packet block the next value block belongs to
+
 #pragma unroll 1
-        for (int k = 0; k < n; ++k) {
-          const uint4 m0 = m[3 * k], m1 = m[3 * k + 1], m2 = m[3 * k + 2];
-          const u64 P[4] = {((u64)m0.y << 32) | m0.x, ((u64)m0.w << 32) | m0.z,
-                            ((u64)m1.y << 32) | m1.x, ((u64)m1.w << 32) | m1.z};
-          const float s0 = __uint_as_float(m2.x), s1 = __uint_as_float(m2.y);
-          if (SPREAD) {
-            const u64 v = vb[k * 32];
-            const float vx = lo32(v), vy = hi32(v);
-            const float a0x = vx * s0, a0y = vy * s0, a1x = vx * s1, a1y = vy * s1;
-            const u64 A[4] = {pack2(a0x, a0x), pack2(a0y, a0y), pack2(a1x, a1x), pack2(a1y, a1y)};
-            taps_spread<W>(acc, m2.z, P, A);
+      for (int j = 0; j < nsub; ++j) {
+        const bool more = j + 1 < nsub;
+        const bool new_block = more && ((j + 1) & 1) == 0;
+        if (new_block) {
+          w_val = w_nxt;
+          w_nxt = load_word(((j + 1) >> 1) + 1);
+          meta_issue(w_val, st);
+        }
+        if (SPREAD) {
+          if (more) values_issue(j + 1, w_val);
+          if (BULK) {
+            mbar_wait(mbar_a + 8 * (j & 1), (phase >> (j & 1)) & 1u);
+            phase ^= 1u << (j & 1);
           } else {
-            u64 S[4];
-            taps_interp<W>(S, acc, m2.z, P);
-            const float px = s0 * (lo32(S[0]) + hi32(S[0])) + s1 * (lo32(S[2]) + hi32(S[2]));
-            const float py = s0 * (lo32(S[1]) + hi32(S[1])) + s1 * (lo32(S[3]) + hi32(S[3]));
-            red_add_f32x2(kt + (long long)m2.w * 32 + lane, pack2(px, py), lane < T);
+            if (more) cp_async_wait<1>();
+            else cp_async_wait<0>();
           }
         }
-        if (more) stage_finish(cur ^ 1, st);
+        __syncwarp();
+        const int n = min(VBLK, nvis - j * VBLK);
+        const unsigned pk_a = meta_a + (unsigned)((((j >> 1) & 1) * MBLK + (j & 1) * VBLK) * 48);
+        const unsigned vb_a = vbuf_a + (unsigned)((j & 1) * VBLK * 32 + lane) * 8u;
+
+        auto apply = [&](const Packet& p, u64 val) {
+          if (SPREAD) {
+            const float vx = lo32(val), vy = hi32(val);
+            const float a0x = vx * p.s0, a0y = vy * p.s0, a1x = vx * p.s1, a1y = vy * p.s1;
+            const u64 A[4] = {pack2(a0x, a0x), pack2(a0y, a0y), pack2(a1x, a1x), pack2(a1y, a1y)};
+            taps_spread<W>(acc, p.idx, p.P, A);
+          } else {
+            u64 S[4];
+            taps_interp<W>(S, acc, p.idx, p.P);
+            const float px = p.s0 * (lo32(S[0]) + hi32(S[0])) + p.s1 * (lo32(S[2]) + hi32(S[2]));
+            const float py = p.s0 * (lo32(S[1]) + hi32(S[1])) + p.s1 * (lo32(S[3]) + hi32(S[3]));
+            red_add_f32x2(kt + (long long)p.s * 32 + lane, pack2(px, py), lane < T);
+          }
+        };
+        // software-pipelined by hand: the packet (and value) of visit k + 1 is in flight while
+        // the taps of visit k execute
+        Packet pa, pb;
+        u64 va = 0ull, vb = 0ull;
+        load_packet(pk_a, pa);
+        if (SPREAD) va = lds64(vb_a);
+        int k = 0;
+#pragma unroll 1
+        for (; k + 1 < n; k += 2) {
+          load_packet(pk_a + (unsigned)(k + 1) * 48u, pb);
+          if (SPREAD) vb = lds64(vb_a + (unsigned)(k + 1) * 256u);
+          apply(pa, va);
+          const unsigned k2 = (unsigned)(k + 2) & (VBLK - 1);
+          load_packet(pk_a + k2 * 48u, pa);
+          if (SPREAD) va = lds64(vb_a + k2 * 256u);
+          apply(pb, vb);
+        }
+        if (k < n) apply(pa, va);
+
+        if (new_block) meta_finish((j + 1) >> 1, w_val, st);
         __syncwarp();
       }
 
       if (SPREAD) {
         // flush: registers (lane = coil) -> smem transpose -> coalesced 128-byte rows per coil
+        if (BULK) fence_proxy_async();
 #pragma unroll
         for (int r = 0; r < 2; ++r)
 #pragma unroll
@@ -635,32 +805,48 @@ k_rows(Geom g, int T, long long nitems, const int2* __restrict__ items,
   }
 }
 
+constexpr int EFALLBACK = 1;  // internal: the row kernels cannot serve this trajectory
+
 template <int DIM, int W>
 int build_items(b200_plan* p, RowsState* ts, cudaStream_t st) {
   const long long nrows = num_rows<DIM>(p->g);
-  if (nrows >= (1LL << 31) - 2) {
-    b200_set_error("too many grid rows (%lld) for the row kernels", nrows);
-    return B200_EINVAL;
-  }
   auto fr = [](void* q) {
     if (q) cudaFree(q);
   };
+  ts->unsupported = false;
+  if (nrows >= (1LL << 31) - 2 || p->M >= (long long)VIS_SMASK) {
+    ts->unsupported = true;
+    return B200_OK;
+  }
   if (ts->nrows != nrows) {
-    fr(ts->d_nchunks);
+    fr(ts->d_tot);
+    fr(ts->d_vis_start);
     fr(ts->d_item_start);
-    ts->d_nchunks = ts->d_item_start = nullptr;
-    CUDA_TRY(cudaMalloc(&ts->d_nchunks, (size_t)(nrows + 1) * 4));
+    ts->d_tot = ts->d_item_start = nullptr;
+    ts->d_vis_start = nullptr;
+    CUDA_TRY(cudaMalloc(&ts->d_tot, (size_t)(nrows + 1) * 4));
+    CUDA_TRY(cudaMalloc(&ts->d_vis_start, (size_t)(nrows + 1) * 4));
     CUDA_TRY(cudaMalloc(&ts->d_item_start, (size_t)(nrows + 1) * 4));
     ts->nrows = nrows;
   }
-  k_row_chunks<DIM, W><<<ceil_div(nrows + 1, 256), 256, 0, st>>>(p->g, nrows, p->d_bin_start,
-                                                                 ts->d_nchunks);
+  CUDA_TRY(cudaMemsetAsync(ts->d_counters, 0, 64, st));
+  k_row_totals<DIM, W><<<ceil_div(nrows + 1, 256), 256, 0, st>>>(
+      p->g, nrows, p->d_bin_start, ts->d_tot, reinterpret_cast<unsigned long long*>(ts->d_counters + 2));
   CHECK_LAUNCH();
-  // item_start = exclusive scan of |nchunks| (an empty row still owns one item)
-  k_abs_chunks<<<ceil_div(nrows + 1, 256), 256, 0, st>>>(nrows + 1, ts->d_nchunks, ts->d_item_start);
+  unsigned long long grand = 0;
+  CUDA_TRY(cudaMemcpyAsync(&grand, ts->d_counters + 2, 8, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  if (grand >= (1ULL << 31)) {
+    ts->unsupported = true;
+    return B200_OK;
+  }
+  k_scan_inputs<<<ceil_div(nrows + 1, 256), 256, 0, st>>>(nrows + 1, ts->d_tot, ts->d_vis_start,
+                                                          ts->d_item_start);
   CHECK_LAUNCH();
-  size_t need = 0;
+  size_t need = 0, need2 = 0;
   cub::DeviceScan::ExclusiveSum(nullptr, need, ts->d_item_start, ts->d_item_start, (int)(nrows + 1), st);
+  cub::DeviceScan::ExclusiveSum(nullptr, need2, ts->d_vis_start, ts->d_vis_start, (int)(nrows + 1), st);
+  if (need2 > need) need = need2;
   if (need > ts->scan_tmp_bytes) {
     fr(ts->d_scan_tmp);
     ts->d_scan_tmp = nullptr;
@@ -669,26 +855,40 @@ int build_items(b200_plan* p, RowsState* ts, cudaStream_t st) {
   }
   CUDA_TRY(cub::DeviceScan::ExclusiveSum(ts->d_scan_tmp, need, ts->d_item_start, ts->d_item_start,
                                          (int)(nrows + 1), st));
-  g_kernel_launches += 2;
+  CUDA_TRY(cub::DeviceScan::ExclusiveSum(ts->d_scan_tmp, need, ts->d_vis_start, ts->d_vis_start,
+                                         (int)(nrows + 1), st));
+  g_kernel_launches += 4;
   int32_t nitems = 0;
   CUDA_TRY(cudaMemcpyAsync(&nitems, ts->d_item_start + nrows, 4, cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaStreamSynchronize(st));
   fr(ts->d_items);
   fr(ts->d_split_rows);
+  fr(ts->d_vis);
   ts->d_items = nullptr;
   ts->d_split_rows = nullptr;
-  CUDA_TRY(cudaMalloc(&ts->d_items, (size_t)(nitems > 0 ? nitems : 1) * sizeof(int2)));
+  ts->d_vis = nullptr;
+  CUDA_TRY(cudaMalloc(&ts->d_items, (size_t)(nitems > 0 ? nitems : 1) * sizeof(int4)));
   CUDA_TRY(cudaMalloc(&ts->d_split_rows, (size_t)(nitems / 2 + 1) * 4));
-  CUDA_TRY(cudaMemsetAsync(ts->d_counters, 0, 64, st));
-  k_fill_items<<<ceil_div(nrows, 256), 256, 0, st>>>(nrows, ts->d_nchunks, ts->d_item_start,
-                                                     ts->d_items, ts->d_split_rows,
-                                                     ts->d_counters + 1);
+  // + 64 words of slack: the kernel prefetches one packet block of words ahead (guarded, but cheap)
+  if (cudaMalloc(&ts->d_vis, (size_t)(grand + 64) * 4) != cudaSuccess) {
+    cudaGetLastError();
+    ts->d_vis = nullptr;
+    ts->unsupported = true;
+    return B200_OK;
+  }
+  k_fill_items<<<ceil_div(nrows, 256), 256, 0, st>>>(nrows, ts->d_tot, ts->d_vis_start,
+                                                     ts->d_item_start, ts->d_items,
+                                                     ts->d_split_rows, ts->d_counters + 1);
+  CHECK_LAUNCH();
+  k_build_visits<DIM, W><<<ceil_div(nrows * 32, 256), 256, 0, st>>>(p->g, nrows, p->d_bin_start, ts->d_tot,
+                                                                    ts->d_vis_start, ts->d_vis);
   CHECK_LAUNCH();
   int nsplit = 0;
   CUDA_TRY(cudaMemcpyAsync(&nsplit, ts->d_counters + 1, 4, cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaStreamSynchronize(st));
   ts->nitems = nitems;
   ts->nsplit = nsplit;
+  ts->nvis = (long long)grand;
   return B200_OK;
 }
 
@@ -697,12 +897,17 @@ int prepare(b200_plan* p, RowsState* ts, cudaStream_t st) {
   const long long M = p->M;
   if (!ts->d_counters) CUDA_TRY(cudaMalloc(&ts->d_counters, 64));
   if (ts->d_rec) cudaFree(ts->d_rec);
+  if (ts->d_iperm) cudaFree(ts->d_iperm);
   ts->d_rec = nullptr;
+  ts->d_iperm = nullptr;
   CUDA_TRY(cudaMalloc(&ts->d_rec, (size_t)(M > 0 ? M : 1) * REC * sizeof(float)));
+  CUDA_TRY(cudaMalloc(&ts->d_iperm, (size_t)(M > 0 ? M : 1) * 4));
   if (M > 0) {
     k_point_records<W><<<ceil_div(M, 256), 256, 0, st>>>(
         p->g, M, p->d_poly, p->d_org_s[0], p->d_org_s[1], p->d_org_s[2], p->d_x1_s[0],
         p->d_x1_s[1], p->d_x1_s[2], ts->d_rec);
+    CHECK_LAUNCH();
+    k_invert_perm<<<ceil_div(M, 256), 256, 0, st>>>(M, p->d_perm, ts->d_iperm);
     CHECK_LAUNCH();
   }
   B200_TRY((build_items<DIM, W>(p, ts, st)));
@@ -713,15 +918,18 @@ int prepare(b200_plan* p, RowsState* ts, cudaStream_t st) {
 
 template <int DIM, int W, bool SPREAD>
 int launch_rows(b200_plan* p, RowsState* ts, float2* fw, int T, cudaStream_t st) {
-  auto kern = k_rows<DIM, W, SPREAD>;
+  const bool bulk = SPREAD && p->rows_bulk != 0;
+  auto kern = SPREAD ? (bulk ? k_rows<DIM, W, SPREAD, true> : k_rows<DIM, W, SPREAD, false>)
+                     : k_rows<DIM, W, false, false>;
   const size_t smem = (size_t)WARPS * SM_WARP;
-  static bool attr_done = false;
-  static int ctas_per_sm = 1;
-  if (!attr_done) {
+  static bool attr_done[2] = {false, false};
+  static int ctas_per_sm[2] = {1, 1};
+  const int v = bulk ? 1 : 0;
+  if (!attr_done[v]) {
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, THREADS, smem));
-    if (ctas_per_sm < 1) ctas_per_sm = 1;
-    attr_done = true;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm[v], kern, THREADS, smem));
+    if (ctas_per_sm[v] < 1) ctas_per_sm[v] = 1;
+    attr_done[v] = true;
   }
   if (SPREAD && ts->nsplit > 0) {
     k_zero_split_rows<DIM><<<ceil_div(ts->nsplit * 32, 128), 128, 0, st>>>(p->g, T, ts->nsplit,
@@ -730,12 +938,12 @@ int launch_rows(b200_plan* p, RowsState* ts, float2* fw, int T, cudaStream_t st)
   }
   CUDA_TRY(cudaMemsetAsync(ts->d_counters, 0, sizeof(int), st));
   const long long want = (ts->nitems + GROUP * WARPS - 1) / (GROUP * WARPS);
-  const long long cap = (long long)p->num_sms * ctas_per_sm;
+  const long long cap = (long long)p->num_sms * ctas_per_sm[v];
   const int grid = (int)(want < cap ? (want > 0 ? want : 1) : cap);
   // slot 4 of the plan's timing events brackets the row kernel alone (bench.py roofline)
   const bool timed = p->timing && p->ev_ok;
   if (timed) cudaEventRecord(p->ev[8], st);
-  kern<<<grid, THREADS, smem, st>>>(p->g, T, ts->nitems, ts->d_items, p->d_bin_start, ts->d_rec,
+  kern<<<grid, THREADS, smem, st>>>(p->g, T, ts->nitems, ts->d_items, ts->d_vis, ts->d_rec,
                                     ts->d_kt, fw, ts->d_counters);
   if (timed) {
     cudaEventRecord(p->ev[9], st);
@@ -764,6 +972,9 @@ bool tiled_supported(const b200_plan* p, int T) {
   if (g.dim < 2 || g.dim > 3) return false;
   if (g.w < 4 || g.w > 7) return false;
   if (T > 32) return false;
+  if (p->tiled && ((RowsState*)p->tiled)->valid && ((RowsState*)p->tiled)->M == p->M &&
+      ((RowsState*)p->tiled)->unsupported)
+    return false;
   const int nfx = g.nf[g.dim - 1];
   const int rem = nfx % CX;
   if (rem != 0 && rem < g.w - 1) return false;  // a footprint may touch at most two tiles
@@ -780,9 +991,12 @@ void tiled_free(b200_plan* p) {
   };
   fr(ts->d_rec);
   fr(ts->d_kt);
-  fr(ts->d_nchunks);
+  fr(ts->d_iperm);
+  fr(ts->d_tot);
+  fr(ts->d_vis_start);
   fr(ts->d_item_start);
   fr(ts->d_items);
+  fr(ts->d_vis);
   fr(ts->d_split_rows);
   fr(ts->d_counters);
   fr(ts->d_scan_tmp);
@@ -828,14 +1042,18 @@ static int ensure_state(b200_plan* p, cudaStream_t st) {
   DISPATCH_DW(prepare, p, ts, st);
 }
 
+// Both entry points return 1 (not an error) when the row kernels cannot serve this trajectory
+// (more than 2^31 visits or 2^27 points): the caller then uses the point-driven kernels.
 int spread_tiled(b200_plan* p, const float2* ksp, const float* density, float2* fw, int T,
                  cudaStream_t st) {
   B200_TRY(ensure_state(p, st));
   RowsState* ts = state(p);
+  if (ts->unsupported) return EFALLBACK;
   const long long M = p->M;
   B200_TRY(ensure_kt(ts, M));
   if (M > 0) {
-    k_gather_kspace<<<ceil_div(M * 32, 256), 256, 0, st>>>(M, T, p->d_perm, ksp, density, ts->d_kt);
+    k_gather_kspace<<<ceil_div(M, 32 * KT_WARPS), KT_WARPS * 32, 0, st>>>(M, T, ts->d_iperm, ksp, density,
+                                                                          ts->d_kt);
     CHECK_LAUNCH();
   }
   DISPATCH_DWS(launch_rows, true, p, ts, fw, T, st);
@@ -845,13 +1063,15 @@ int interp_tiled(b200_plan* p, const float2* fw, float2* ksp, int T, float scale
                  const float2* obs, cudaStream_t st) {
   B200_TRY(ensure_state(p, st));
   RowsState* ts = state(p);
+  if (ts->unsupported) return EFALLBACK;
   const long long M = p->M;
   if (M == 0) return B200_OK;
   B200_TRY(ensure_kt(ts, M));
   CUDA_TRY(cudaMemsetAsync(ts->d_kt, 0, (size_t)M * 32 * sizeof(float2), st));
   int rc = [&]() -> int { DISPATCH_DWS(launch_rows, false, p, ts, const_cast<float2*>(fw), T, st); }();
   if (rc != B200_OK) return rc;
-  k_scatter_kspace<<<ceil_div(M * 32, 256), 256, 0, st>>>(M, T, p->d_perm, ts->d_kt, ksp, scale, obs);
+  k_scatter_kspace<<<ceil_div(M, 32 * KT_WARPS), KT_WARPS * 32, 0, st>>>(M, T, ts->d_iperm, ts->d_kt, ksp,
+                                                                         scale, obs);
   CHECK_LAUNCH();
   return B200_OK;
 }
