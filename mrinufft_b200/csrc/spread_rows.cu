@@ -561,7 +561,7 @@ __device__ __forceinline__ u64 lds64(unsigned addr) {
 struct Staged {
   float4 p0, p1;  // pair-packed x weights
   float wz;
-  int jbi, y0;
+  int2 jy;        // (xo >> 1) + W / 2, y0
   const float* r;
 };
 
@@ -656,9 +656,7 @@ k_rows(Geom g, int T, long long nitems, const int4* __restrict__ items,
           st.r = r;
           st.p0 = __ldg(reinterpret_cast<const float4*>(r));
           st.p1 = __ldg(reinterpret_cast<const float4*>(r) + 1);
-          const int2 jy = __ldg(reinterpret_cast<const int2*>(r + R_JY));
-          st.jbi = jy.x - (int)(w >> 30) * lhalf;
-          st.y0 = jy.y;
+          st.jy = __ldg(reinterpret_cast<const int2*>(r + R_JY));
           st.wz = (DIM == 3) ? __ldg(r + R_WZ + ((w >> VIS_SBITS) & 7u)) : 1.f;
         }
       };
@@ -666,7 +664,7 @@ k_rows(Geom g, int T, long long nitems, const int4* __restrict__ items,
         if (w != VIS_NONE) {
           // row scales: row y takes wy[dy], row y+1 takes wy[dy+1]  (dy = y - y0 in [-1, W-1];
           // the record stores 0, wy[0..6], 0 so that both loads are unconditional)
-          int dy = rc.y - st.y0;
+          int dy = rc.y - st.jy.y;
           if (dy < -1) dy += nfy;
           const float s0 = __ldg(st.r + R_WY + 1 + dy) * st.wz;
           const float s1 = __ldg(st.r + R_WY + 2 + dy) * st.wz;
@@ -675,7 +673,7 @@ k_rows(Geom g, int T, long long nitems, const int4* __restrict__ items,
                             __float_as_uint(st.p0.w));
           m[1] = make_uint4(__float_as_uint(st.p1.x), __float_as_uint(st.p1.y), __float_as_uint(st.p1.z),
                             __float_as_uint(st.p1.w));
-          m[2] = make_uint4(__float_as_uint(s0), __float_as_uint(s1), (unsigned)st.jbi, w & VIS_SMASK);
+          m[2] = make_uint4(__float_as_uint(s0), __float_as_uint(s1), (unsigned)(st.jy.x - (int)(w >> 30) * lhalf), w & VIS_SMASK);
         }
       };
       // coil values of value block j (visits 16 j .. 16 j + 15; their words sit in lanes
@@ -751,7 +749,8 @@ k_rows(Geom g, int T, long long nitems, const int4* __restrict__ items,
             taps_interp<W>(S, acc, p.idx, p.P);
             const float px = p.s0 * (lo32(S[0]) + hi32(S[0])) + p.s1 * (lo32(S[2]) + hi32(S[2]));
             const float py = p.s0 * (lo32(S[1]) + hi32(S[1])) + p.s1 * (lo32(S[3]) + hi32(S[3]));
-            red_add_f32x2(kt + (long long)p.s * 32 + lane, pack2(px, py), lane < T);
+            // coils t >= T hold an all-zero tile: they add zero to their (unused) kt slot
+            red_add_f32x2(kt + (long long)p.s * 32 + lane, pack2(px, py), 1);
           }
         };
         // software-pipelined by hand: the packet (and value) of visit k + 1 is in flight while
