@@ -46,6 +46,7 @@
 // Replaces finufft's spread/interp stage (call sites
 // src/mrinufft/operators/interfaces/finufft.py:69,76; algorithm docs/explanations/nufft.rst:253-309).
 #include <cub/device/device_scan.cuh>
+#include <type_traits>
 
 #include "common.cuh"
 #include "device_utils.cuh"
@@ -60,47 +61,46 @@ constexpr int REC = 28;         // floats per point record (112 B):
 constexpr int R_WY = 8;         //   [0..7]  pair-packed x weights P | [8..16] 0, wy[0..6], 0
 constexpr int R_WZ = 17;        //   [17..23] wz[0..6] | [24] (xo >> 1) + W/2 | [25] y0 | [26..27] pad
 constexpr int R_JY = 24;
-constexpr int VBLK = 16;        // visits per value block (cp.async / bulk-copy granularity)
+constexpr int VBLK = 16;        // visits per value block (cp.async granularity)
 constexpr int MBLK = 32;        // visits per packet block (one lane stages one visit)
 constexpr int WARPS = 4;        // warps per CTA
 constexpr int THREADS = WARPS * 32;
-constexpr int CHUNK = 4096;     // visits per work item
-constexpr int GROUP = 4;        // work items fetched per atomic
+constexpr int LCH = 2048;       // stream entries per chunk (= one unit of dynamically scheduled work)
 
-constexpr int ITEM_EMPTY = 1;   // item flags: tile without visits
-constexpr int ITEM_SPLIT = 2;   //             tile shared by several items
-
-// visit word: sorted point index | dz << 27 | (visit comes from the left neighbour's crossing bin) << 30
-constexpr unsigned VIS_SBITS = 27;
-constexpr unsigned VIS_SMASK = (1u << VIS_SBITS) - 1;
-constexpr unsigned VIS_NONE = 0xffffffffu;
+// The visit stream: 16-byte entries {s0, s1, idx, s}, tile after tile in tile-id order.
+//   visit entry  : row scales s0, s1, tap-kernel case idx (small), sorted point index s
+//   header entry : idx = IDX_HDR, s = tile id -- "the following visits belong to this tile"
+//   padding      : all ones (behind the end of the stream; reads as a header)
+constexpr unsigned IDX_HDR = 0xffffffffu;
+constexpr unsigned IDX_NONE = 0xfffffffeu;  // in registers only: lane beyond the end of the chunk
 
 // per-warp shared memory (bytes)
-constexpr int SM_VBUF = 2 * VBLK * 32 * 8;  // double-buffered coil values of VBLK points
+constexpr int SM_VBUF = 2 * VBLK * 32 * 8;  // double-buffered coil values of VBLK points (spreader only)
 constexpr int SM_META = 2 * MBLK * 48;      // double-buffered packets {P0..P3, s0, s1, idx, s}
-constexpr int SM_MBAR = 16;                 // two mbarriers (bulk-copy variant)
-constexpr int SM_WARP = SM_VBUF + SM_META + SM_MBAR;
-constexpr int TS = 34;          // row stride (floats) of the transpose planes
-static_assert(SM_VBUF + SM_META >= 2 * 32 * TS * 4, "transpose buffers must fit in vbuf+meta");
+constexpr int TBS = 10;                     // float stride of the transpose planes [32 coils][8 cells]
+constexpr int SM_TBUF = 2 * 32 * TBS * 4;   // real + imaginary plane of half a grid row (8 cells), 32 coils
+__host__ __device__ constexpr int smem_per_warp(bool spread) { return (spread ? SM_VBUF : 0) + SM_META + SM_TBUF; }
 
 struct RowsState {
   float* d_rec = nullptr;        // [M][REC] per sorted point
   float2* d_kt = nullptr;        // [M][32] transposed (sorted point, coil) k-space batch
   size_t kt_bytes = 0;
   int32_t* d_iperm = nullptr;    // [M] point index -> sorted position
-  int32_t* d_tot = nullptr;      // [nrows + 1] visits per tile
-  uint32_t* d_vis_start = nullptr;  // [nrows + 1] first visit word of a tile
-  int32_t* d_item_start = nullptr;  // [nrows + 1]
-  int4* d_items = nullptr;       // [nitems] {tile, flags, first visit word, visit count}
-  uint32_t* d_vis = nullptr;     // [nvis] visit words, tile by tile
-  int32_t* d_split_rows = nullptr;
+  int32_t* d_tot = nullptr;      // [nrows + 1] visits per tile (-1: tile id outside the grid)
+  uint32_t* d_start = nullptr;   // [nrows + 1] stream position of a tile's header word
+  uint4* d_ent = nullptr;        // [S + slack] the visit stream
+  float* d_ptab = nullptr;       // [M][8] pair-packed x weights per sorted point
+  int32_t* d_chunk_row = nullptr;  // [nchunks] tile owning the first word of a chunk
+  int32_t* d_split_rows = nullptr; // tiles cut by a chunk boundary (accumulated with red.add)
   int* d_counters = nullptr;     // [0] work counter, [1] split-row counter, [2..3] total visits (u64)
   void* d_scan_tmp = nullptr;
   size_t scan_tmp_bytes = 0;
-  long long nrows = 0, nitems = 0, nsplit = 0, nvis = 0;
+  long long nrows = 0, nsplit = 0, nvis = 0;
+  unsigned S = 0;                // stream length in entries
+  int nchunks = 0;
   long long M = -1;
   bool valid = false;
-  bool unsupported = false;      // too many visits / points for the 32-bit visit words
+  bool unsupported = false;      // too many visits / points for the 32-bit stream words
 };
 
 RowsState* state(b200_plan* p) {
@@ -203,7 +203,7 @@ k_point_records(Geom g, long long M, const float* __restrict__ poly,
                 const int32_t* __restrict__ o0, const int32_t* __restrict__ o1,
                 const int32_t* __restrict__ o2, const float* __restrict__ f0,
                 const float* __restrict__ f1, const float* __restrict__ f2,
-                float* __restrict__ rec) {
+                float* __restrict__ rec, float* __restrict__ ptab) {
   __shared__ float spoly[(B200_MAX_DEG + 1) * B200_MAX_W];
   for (int i = threadIdx.x; i < (g.deg + 1) * W; i += blockDim.x) spoly[i] = poly[i];
   __syncthreads();
@@ -253,6 +253,9 @@ k_point_records(Geom g, long long M, const float* __restrict__ poly,
 #pragma unroll
   for (int q = 0; q < REC / 4; ++q)
     dst[q] = make_float4(out[4 * q], out[4 * q + 1], out[4 * q + 2], out[4 * q + 3]);
+  float4* pd = reinterpret_cast<float4*>(ptab + s * 8);
+  pd[0] = make_float4(out[0], out[1], out[2], out[3]);
+  pd[1] = make_float4(out[4], out[5], out[6], out[7]);
 }
 
 __global__ void __launch_bounds__(256)
@@ -286,52 +289,57 @@ k_row_totals(Geom g, long long nrows, const int32_t* __restrict__ bin_start,
   if ((threadIdx.x & 31) == 0 && wsum > 0) atomicAdd(grand, (unsigned long long)wsum);
 }
 
-// per tile: (visits, items) as inputs of the two exclusive scans
+// stream words per tile: header + visits (0 for tile ids outside the grid)
 __global__ void __launch_bounds__(256)
-k_scan_inputs(long long n, const int32_t* __restrict__ tot, uint32_t* __restrict__ nvis,
-              int32_t* __restrict__ nitem) {
+k_scan_inputs(long long n, const int32_t* __restrict__ tot, uint32_t* __restrict__ words) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const int t = tot[i];
-  nvis[i] = t > 0 ? (uint32_t)t : 0u;
-  nitem[i] = t < 0 ? 0 : (t == 0 ? 1 : (t + CHUNK - 1) / CHUNK);  // an empty tile still owns one item
+  words[i] = t < 0 ? 0u : (uint32_t)t + 1u;
 }
 
+// The visit stream, written once per trajectory: 16-byte entries {s0, s1, idx, s}, tile after tile.
+// One warp per tile writes the tile's header entry {0, 0, IDX_HDR, tile id} and, behind it, one entry
+// per visit with everything the row kernels need: the two row scales wy[dy] wz[dz], wy[dy+1] wz[dz],
+// the tap-kernel case idx and the sorted point index.  It also records which tile owns the first
+// entry of every chunk and which tiles are cut by a chunk boundary.
+template <int DIM, int W>
 __global__ void __launch_bounds__(256)
-k_fill_items(long long nrows, const int32_t* __restrict__ tot,
-             const uint32_t* __restrict__ vis_start, const int32_t* __restrict__ item_start,
-             int4* __restrict__ items, int32_t* __restrict__ split_rows,
-             int* __restrict__ split_counter) {
-  const long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+k_build_stream(Geom g, long long nrows, const int32_t* __restrict__ bin_start,
+               const int32_t* __restrict__ tot, const uint32_t* __restrict__ start,
+               const float* __restrict__ rec, uint4* __restrict__ ent,
+               int32_t* __restrict__ chunk_row, int32_t* __restrict__ split_rows,
+               int* __restrict__ split_counter) {
+  const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
   if (row >= nrows) return;
   const int t = tot[row];
   if (t < 0) return;
-  const int at = item_start[row];
-  if (t == 0) {
-    items[at] = make_int4((int)row, ITEM_EMPTY, 0, 0);
-    return;
+  const uint32_t hs = start[row], he = hs + 1u + (uint32_t)t;
+  if (lane == 0) {
+    ent[hs] = make_uint4(0u, 0u, IDX_HDR, (uint32_t)row);
+    for (uint32_t c = (hs + LCH - 1) / LCH; c * (uint32_t)LCH < he; ++c) chunk_row[c] = (int32_t)row;
+    if (hs / LCH != (he - 1) / LCH) split_rows[atomicAdd(split_counter, 1)] = (int32_t)row;
   }
-  const int n = (t + CHUNK - 1) / CHUNK;
-  const int flags = n > 1 ? ITEM_SPLIT : 0;
-  for (int c = 0; c < n; ++c)
-    items[at + c] = make_int4((int)row, flags, (int)(vis_start[row] + (uint32_t)c * CHUNK),
-                              min(CHUNK, t - c * CHUNK));
-  if (n > 1) split_rows[atomicAdd(split_counter, 1)] = (int32_t)row;
-}
-
-// The visit list of every tile, written once per trajectory: one warp per tile concatenates the
-// tile's key ranges (slot order = dz-major, as the prefix sums of k_row_totals assume).
-template <int DIM, int W>
-__global__ void __launch_bounds__(256)
-k_build_visits(Geom g, long long nrows, const int32_t* __restrict__ bin_start,
-               const int32_t* __restrict__ tot, const uint32_t* __restrict__ vis_start,
-               uint32_t* __restrict__ vis) {
-  const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (row >= nrows || tot[row] <= 0) return;
+  if (t == 0) return;
   RowCoord rc;
   decode_row<DIM>(g, row, &rc);
-  uint32_t* out = vis + vis_start[row];
+  const int nfx = g.nf[DIM - 1], nfy = g.nf[DIM - 2];
+  const int nbx = num_xtiles<DIM>(g);
+  // a left neighbour's crossing point lands at x offset (xo - length of the left tile)
+  const int lhalf = ((rc.bx == 0) ? (nfx - (nbx - 1) * CX) : CX) >> 1;
+  uint4* out = ent + hs + 1;
+  auto entry = [&](int s, int dz, int left) -> uint4 {
+    const float* r = rec + (long long)s * REC;
+    const int2 jy = *reinterpret_cast<const int2*>(r + R_JY);
+    // row y takes wy[dy], row y+1 takes wy[dy+1]  (dy = y - y0 in [-1, W-1]; the record stores
+    // 0, wy[0..6], 0 so that both loads are unconditional)
+    int dy = rc.y - jy.y;
+    if (dy < -1) dy += nfy;
+    const float wz = (DIM == 3) ? r[R_WZ + dz] : 1.f;
+    return make_uint4(__float_as_uint(r[R_WY + 1 + dy] * wz), __float_as_uint(r[R_WY + 2 + dy] * wz),
+                      (unsigned)(jy.x - left * lhalf), (unsigned)s);
+  };
   int b[2], l[2];
   slot_range<DIM, W>(g, rc, lane, bin_start, &b[0], &l[0]);
   slot_range<DIM, W>(g, rc, lane + 32, bin_start, &b[1], &l[1]);
@@ -350,11 +358,11 @@ k_build_visits(Geom g, long long nrows, const int32_t* __restrict__ bin_start,
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
     const int slot = lane + 32 * h;
-    const unsigned tag = ((unsigned)((slot >> 1) / 3) << VIS_SBITS) | ((((slot >> 1) % 3) == 2 ? 1u : 0u) << 30);
+    const int dz = (slot >> 1) / 3, left = ((slot >> 1) % 3) == 2 ? 1 : 0;
     // short ranges: written by the owning lane; long ranges (dense k-space centre): by the whole warp
     const bool is_long = l[h] > 64;
     if (!is_long)
-      for (int i = 0; i < l[h]; ++i) out[pre[h] + i] = (unsigned)(b[h] + i) | tag;
+      for (int i = 0; i < l[h]; ++i) out[pre[h] + i] = entry(b[h] + i, dz, left);
     unsigned longs = __ballot_sync(0xffffffffu, is_long);
     while (longs) {
       const int src = __ffs(longs) - 1;
@@ -362,8 +370,9 @@ k_build_visits(Geom g, long long nrows, const int32_t* __restrict__ bin_start,
       const int bb = __shfl_sync(0xffffffffu, b[h], src);
       const int ll = __shfl_sync(0xffffffffu, l[h], src);
       const int pp = __shfl_sync(0xffffffffu, pre[h], src);
-      const unsigned tg = __shfl_sync(0xffffffffu, tag, src);
-      for (int i = lane; i < ll; i += 32) out[pp + i] = (unsigned)(bb + i) | tg;
+      const int sdz = __shfl_sync(0xffffffffu, dz, src);
+      const int sl = __shfl_sync(0xffffffffu, left, src);
+      for (int i = lane; i < ll; i += 32) out[pp + i] = entry(bb + i, sdz, sl);
     }
   }
 }
@@ -466,20 +475,18 @@ k_zero_split_rows(Geom g, int T, long long nsplit, const int32_t* __restrict__ s
 #include "taps_generated.inc"
 
 template <int W>
-__device__ __forceinline__ void taps_spread(u64 (&acc)[NACC], unsigned idx, const u64 (&P)[4],
-                                            const u64 (&A)[4]) {
-  if (W == 7) taps_spread_w7(acc, idx, P, A);
-  else if (W == 6) taps_spread_w6(acc, idx, P, A);
-  else if (W == 5) taps_spread_w5(acc, idx, P, A);
-  else taps_spread_w4(acc, idx, P, A);
+__device__ __forceinline__ void rows_loop_spread(u64 (&acc)[NACC], unsigned pk, int n, unsigned vb) {
+  if (W == 7) rows_loop_spread_w7(acc, pk, n, vb);
+  else if (W == 6) rows_loop_spread_w6(acc, pk, n, vb);
+  else if (W == 5) rows_loop_spread_w5(acc, pk, n, vb);
+  else rows_loop_spread_w4(acc, pk, n, vb);
 }
 template <int W>
-__device__ __forceinline__ void taps_interp(u64 (&S)[4], u64 (&acc)[NACC], unsigned idx,
-                                            const u64 (&P)[4]) {
-  if (W == 7) taps_interp_w7(S, acc, idx, P);
-  else if (W == 6) taps_interp_w6(S, acc, idx, P);
-  else if (W == 5) taps_interp_w5(S, acc, idx, P);
-  else taps_interp_w4(S, acc, idx, P);
+__device__ __forceinline__ void rows_loop_interp(u64 (&acc)[NACC], unsigned pk, int n, const void* ktl) {
+  if (W == 7) rows_loop_interp_w7(acc, pk, n, ktl);
+  else if (W == 6) rows_loop_interp_w6(acc, pk, n, ktl);
+  else if (W == 5) rows_loop_interp_w5(acc, pk, n, ktl);
+  else rows_loop_interp_w4(acc, pk, n, ktl);
 }
 
 __device__ __forceinline__ u64 pack2(float lo, float hi) {
@@ -504,7 +511,7 @@ __device__ __forceinline__ void red_add_f32x2(float2* addr, u64 p, int pred) {
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ void cp_async16(unsigned smem_dst, const void* gsrc) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;\n" ::"r"(smem_dst), "l"(gsrc) : "memory");
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem_dst), "l"(gsrc) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 template <int N>
@@ -512,293 +519,289 @@ __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
 }
 
-// bulk-copy (TMA) variant of the value staging: one 256-byte copy per visit, completion on an mbarrier
-__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "WAIT_LOOP:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@!p bra WAIT_LOOP;\n"
-      "}\n" ::"r"(bar), "r"(parity)
-      : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(unsigned smem_dst, const void* gsrc, unsigned bytes, unsigned bar) {
-  asm volatile(
-      "cp.async.bulk.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smem_dst),
-      "l"(gsrc), "r"(bytes), "r"(bar)
-      : "memory");
-}
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
-
-// one staged visit as the consume loop sees it: 48-byte packet, read with warp-broadcast loads
-struct Packet {
-  u64 P[4];     // pair-packed x weights
-  float s0, s1; // row scales wy[dy] wz[dz], wy[dy + 1] wz[dz]
-  unsigned idx; // tap-kernel case: floor(off / 2) + W / 2
-  unsigned s;   // sorted point index
-};
-__device__ __forceinline__ void load_packet(unsigned addr, Packet& p) {
-  asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];\n" : "=l"(p.P[0]), "=l"(p.P[1]) : "r"(addr));
-  asm volatile("ld.shared.v2.b64 {%0, %1}, [%2+16];\n" : "=l"(p.P[2]), "=l"(p.P[3]) : "r"(addr));
-  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4+32];\n"
-               : "=f"(p.s0), "=f"(p.s1), "=r"(p.idx), "=r"(p.s)
-               : "r"(addr));
-}
-__device__ __forceinline__ u64 lds64(unsigned addr) {
-  u64 v;
-  asm volatile("ld.shared.b64 %0, [%1];\n" : "=l"(v) : "r"(addr));
+// A staged visit is a 48-byte packet {P0..P3 | s0, s1, idx, s} (tools/gen_taps.py): the first 32
+// bytes are the point's pair-packed x weights, copied from `ptab` with cp.async, the last 16 bytes
+// are the visit's stream entry.  idx = IDX_HDR marks a tile header, with s = tile id.
+__device__ __forceinline__ unsigned lds32(unsigned addr) {
+  unsigned v;
+  asm volatile("ld.shared.b32 %0, [%1];\n" : "=r"(v) : "r"(addr));
   return v;
 }
+__device__ __forceinline__ void sts128(unsigned addr, uint4 v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
+               : "memory");
+}
+__device__ __forceinline__ void prefetch_l2(const void* p) {
+  asm volatile("prefetch.global.L2 [%0];\n" ::"l"(p));
+}
 
-// registers of one lane's visit between "issue" (record loads in flight) and "finish" (packet written)
-struct Staged {
-  float4 p0, p1;  // pair-packed x weights
-  float wz;
-  int2 jy;        // (xo >> 1) + W / 2, y0
-  const float* r;
-};
-
-template <int DIM, int W, bool SPREAD, bool BULK>
+// The row kernel.  A warp consumes one chunk of the visit stream at a time; the tile whose
+// accumulators it holds changes whenever a header entry comes by.  Staging is pure data movement:
+// entries are read one packet block ahead (coalesced), the x weights and the coil values of their
+// points arrive through cp.async, and their cache lines are pulled into L2 another block earlier.
+template <int DIM, int W, bool SPREAD>
 __global__ void __launch_bounds__(THREADS, 4)
-k_rows(Geom g, int T, long long nitems, const int4* __restrict__ items,
-       const uint32_t* __restrict__ vis, const float* __restrict__ rec,
-       float2* __restrict__ kt, float2* __restrict__ fw, int* __restrict__ counter) {
+k_rows(Geom g, int T, int nchunks, unsigned S, long long M, const uint4* __restrict__ ent,
+       const int32_t* __restrict__ chunk_row, const float* __restrict__ ptab,
+       float2* __restrict__ kt, float2* __restrict__ fw, int* __restrict__ counter, int dbg) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
+  constexpr int SMW = smem_per_warp(SPREAD);
+  constexpr unsigned FULL = 0xffffffffu;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  unsigned char* wsm = smem_raw + (size_t)warp * SM_WARP;
-  const unsigned vbuf_a = smem_u32(wsm);               // [2][VBLK][32] (re, im)
-  const unsigned meta_a = smem_u32(wsm + SM_VBUF);     // [2][MBLK] packets of 48 bytes
-  const unsigned mbar_a = smem_u32(wsm + SM_VBUF + SM_META);
-  uint4* meta = reinterpret_cast<uint4*>(wsm + SM_VBUF);
-  // transpose buffers (alias vbuf/meta): real and imaginary planes [32 coils][34] floats, so that a
-  // lane reads / writes its (cell 2j, cell 2j+1) register pairs with one conflict-free 64-bit access
-  float* tre = reinterpret_cast<float*>(wsm);
-  float* tim = tre + 32 * TS;
+  const int hl = lane >> 4, cl = lane & 15;
+  unsigned char* wsm = smem_raw + (size_t)warp * SMW;
+  // (made opaque: nvcc otherwise re-derives these addresses from %tid at every use)
+  asm volatile("" : "+l"(wsm));
+  const unsigned vbuf_a = smem_u32(wsm);                         // [2][VBLK][32] (re, im); spreader only
+  unsigned char* metap = wsm + (SPREAD ? SM_VBUF : 0);
+  const unsigned meta_a = smem_u32(metap);                       // [2][MBLK] packets of 48 bytes
+  // transpose planes [32 coils][TBS]: lane = coil on the register side; on the grid side a warp
+  // instruction moves 8 cells (64 contiguous bytes) of 4 coils
+  float* tre = reinterpret_cast<float*>(metap + SM_META);
+  float* tim = tre + 32 * TBS;
+  const int g4 = lane >> 3, c8 = lane & 7;  // grid-side role: coil 4 i + g4, cell 8 h + c8
+  const char* ktl = reinterpret_cast<const char*>(kt) + (SPREAD ? cl * 16 : lane * 8);
+  asm volatile("" : "+l"(ktl));
 
   const int nfx = g.nf[DIM - 1];
   const int nfy = g.nf[DIM - 2];
   const int nbx = num_xtiles<DIM>(g);
   u64* fw64 = reinterpret_cast<u64*>(fw);
-  unsigned phase = 0;  // bit b: parity the next wait on mbarrier b expects
-  if (SPREAD && BULK) {
-    if (lane == 0) {
-      mbar_init(mbar_a, 1);
-      mbar_init(mbar_a + 8, 1);
-    }
-    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
-    __syncwarp();
-  }
 
   for (;;) {
-    long long item0 = 0;
-    if (lane == 0) item0 = (long long)atomicAdd(counter, GROUP);
-    item0 = __shfl_sync(0xffffffffu, item0, 0);
-    if (item0 >= nitems) break;
-#pragma unroll 1
-    for (int gi = 0; gi < GROUP; ++gi) {
-      const long long item = item0 + gi;
-      if (item >= nitems) break;
-      const int4 it = __ldg(items + item);
-      RowCoord rc;
-      decode_row<DIM>(g, it.x, &rc);
-      // flush / load role of this lane: row (lane >> 4) of the pair, cell (lane & 15)
-      const int x = rc.bx * CX + (lane & 15);
-      u64* gtile = fw64 + rc.rowbase + (long long)(lane >> 4) * nfx + x;
-      if (it.y & ITEM_EMPTY) {
-        if (SPREAD && x < nfx) {
-          for (int t = 0; t < T; ++t) gtile[(long long)t * g.nftot] = 0ull;
-        }
-        continue;
-      }
-      const bool split = it.y & ITEM_SPLIT;
-      const uint32_t* v = vis + (uint32_t)it.z;
-      const int nvis = it.w;
-      const int nsub = (nvis + VBLK - 1) / VBLK;
-      // a left neighbour's crossing point lands at x offset (xo - length of the left tile)
-      const int lhalf = ((rc.bx == 0) ? (nfx - (nbx - 1) * CX) : CX) >> 1;
+    int c = 0;
+    if (lane == 0) c = atomicAdd(counter, 1);
+    c = __shfl_sync(FULL, c, 0);
+    if (c >= nchunks) break;
+    const unsigned base = (unsigned)c * LCH;
+    const uint4* v = ent + base;
+    const int nw = (int)min((unsigned)LCH, S - base);
+    const int nsub = (nw + VBLK - 1) / VBLK;
+    // is the entry behind the chunk a header (or the end of the stream)?  Then the last tile ends here.
+    const bool tail_whole = __ldg(reinterpret_cast<const unsigned*>(v + nw) + 2) == IDX_HDR;
 
-      // ---- accumulators: acc[r*16 + c*8 + j] = (cell 2j, cell 2j+1) of row r, c = re / im
-      u64 acc[NACC];
-      if (SPREAD) {
+    // ---- the tile in the accumulators
+    u64* gbase = nullptr;  // grid-side role of this lane: cell c8 of coil g4, row 0 of the tile
+    int xlim = 0;          // cells of this tile inside the grid (16, less for a short last tile)
+    auto tile_setup = [&](int row) {
+      // 32-bit version of decode_row (tile ids are below 2^30 here)
+      const int nz = DIM == 3 ? g.nf[0] : 1;
+      const int ps = row & 3;
+      int r = row >> 2;
+      const int bx = r % nbx;
+      r /= nbx;
+      const int pg = r % (YB / 8);
+      r /= (YB / 8);
+      const int z = r % nz;
+      const int yb = r / nz;
+      const int y = yb * YB + pg * 8 + ps * 2;
+      xlim = nfx - bx * CX;
+      gbase = fw64 + ((long long)z * nfy + y) * nfx + bx * CX + c8 + (long long)g4 * g.nftot;
+    };
+    tile_setup(__ldg(chunk_row + c));
+    bool started = false;  // the tile's header came by in this chunk
+    bool loaded = false;   // interpolator: the tile is in the registers
+    bool dirty = false;    // some visit was applied to the tile
+
+    // accumulators: acc[r*16 + c*8 + j] = (cell 2j, cell 2j+1) of row r, c = re / im
+    u64 acc[NACC];
 #pragma unroll
-        for (int i = 0; i < NACC; ++i) acc[i] = 0ull;
-      } else {
-        // load the tile: coalesced per coil (128 B per row) -> smem -> registers (lane = coil)
-#pragma unroll 8
-        for (int t = 0; t < 32; ++t) {
-          u64 q = 0ull;
-          if (t < T && x < nfx) q = __ldg(gtile + (long long)t * g.nftot);
-          tre[t * TS + lane] = lo32(q);
-          tim[t * TS + lane] = hi32(q);
-        }
-        __syncwarp();
+    for (int i = 0; i < NACC; ++i) acc[i] = 0ull;
+
+    // registers (lane = coil) -> grid rows: 8 cells of one row of all coils at a time go through the
+    // transpose planes; a store instruction writes 64 contiguous bytes of 4 coils.
+    // MODE 0: plain stores (the tile is complete), 1: red.add (tile shared with other chunks)
+    auto flush = [&](auto mode) {
+      constexpr int MODE = decltype(mode)::value;
 #pragma unroll
-        for (int r = 0; r < 2; ++r)
+      for (int r = 0; r < 2; ++r)
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            acc[r * 16 + j] = *reinterpret_cast<const u64*>(tre + lane * TS + r * 16 + 2 * j);
-            acc[r * 16 + 8 + j] = *reinterpret_cast<const u64*>(tim + lane * TS + r * 16 + 2 * j);
+        for (int h = 0; h < 2; ++h) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            *reinterpret_cast<u64*>(tre + lane * TBS + 2 * j) = acc[r * 16 + 4 * h + j];
+            *reinterpret_cast<u64*>(tim + lane * TBS + 2 * j) = acc[r * 16 + 8 + 4 * h + j];
           }
-        __syncwarp();
-      }
-
-      // ---- staging: packets in blocks of 32 visits (one lane = one visit), values in blocks of 16
-      auto meta_issue = [&](unsigned w, Staged& st) {
-        if (w != VIS_NONE) {
-          const float* r = rec + (long long)(w & VIS_SMASK) * REC;
-          st.r = r;
-          st.p0 = __ldg(reinterpret_cast<const float4*>(r));
-          st.p1 = __ldg(reinterpret_cast<const float4*>(r) + 1);
-          st.jy = __ldg(reinterpret_cast<const int2*>(r + R_JY));
-          st.wz = (DIM == 3) ? __ldg(r + R_WZ + ((w >> VIS_SBITS) & 7u)) : 1.f;
-        }
-      };
-      auto meta_finish = [&](int mb, unsigned w, const Staged& st) {
-        if (w != VIS_NONE) {
-          // row scales: row y takes wy[dy], row y+1 takes wy[dy+1]  (dy = y - y0 in [-1, W-1];
-          // the record stores 0, wy[0..6], 0 so that both loads are unconditional)
-          int dy = rc.y - st.jy.y;
-          if (dy < -1) dy += nfy;
-          const float s0 = __ldg(st.r + R_WY + 1 + dy) * st.wz;
-          const float s1 = __ldg(st.r + R_WY + 2 + dy) * st.wz;
-          uint4* m = meta + ((mb & 1) * MBLK + lane) * 3;
-          m[0] = make_uint4(__float_as_uint(st.p0.x), __float_as_uint(st.p0.y), __float_as_uint(st.p0.z),
-                            __float_as_uint(st.p0.w));
-          m[1] = make_uint4(__float_as_uint(st.p1.x), __float_as_uint(st.p1.y), __float_as_uint(st.p1.z),
-                            __float_as_uint(st.p1.w));
-          m[2] = make_uint4(__float_as_uint(s0), __float_as_uint(s1), (unsigned)(st.jy.x - (int)(w >> 30) * lhalf), w & VIS_SMASK);
-        }
-      };
-      // coil values of value block j (visits 16 j .. 16 j + 15; their words sit in lanes
-      // 16 (j & 1) .. of `w`, the word register of packet block j >> 1)
-      auto values_issue = [&](int j, unsigned w) {
-        const int buf = j & 1;
-        if (BULK) {
-          const int n = min(VBLK, nvis - j * VBLK);
-          fence_proxy_async();
-          if (lane == 0) mbar_expect_tx(mbar_a + 8 * buf, (unsigned)n * 256u);
           __syncwarp();
-          if ((lane >> 4) == buf && w != VIS_NONE)
-            bulk_g2s(vbuf_a + (unsigned)(buf * VBLK + (lane & 15)) * 256u,
-                     kt + (long long)(w & VIS_SMASK) * 32, 256u, mbar_a + 8 * buf);
-        } else {
-          // 2 points per instruction, 16 bytes per lane
+          if (8 * h + c8 < xlim) {
+            u64* dst = gbase + (long long)r * nfx + 8 * h;
 #pragma unroll
-          for (int i = 0; i < VBLK / 2; ++i) {
-            const int kk = 2 * i + (lane >> 4);
-            const unsigned wk = __shfl_sync(0xffffffffu, w, buf * VBLK + kk);
-            if (wk != VIS_NONE)
-              cp_async16(vbuf_a + (unsigned)((buf * VBLK + kk) * 32 + (lane & 15) * 2) * 8u,
-                         kt + (long long)(wk & VIS_SMASK) * 32 + (lane & 15) * 2);
+            for (int i = 0; i < 8; ++i) {
+              const int t = 4 * i + g4;
+              if (T == 32 || t < T) {
+                const u64 val = pack2(tre[t * TBS + c8], tim[t * TBS + c8]);
+                u64* a = dst + (long long)(4 * i) * g.nftot;
+                if (MODE == 0) *a = val;
+                else red_add_f32x2(reinterpret_cast<float2*>(a), val, 1);
+              }
+            }
           }
-          cp_async_commit();
+          __syncwarp();
         }
-      };
-      auto load_word = [&](int mb) -> unsigned {
-        const int i = mb * MBLK + lane;
-        return i < nvis ? __ldg(v + i) : VIS_NONE;
-      };
-
-      unsigned w_cur = load_word(0);   // words of the packet block being consumed / staged
-      unsigned w_nxt = load_word(1);   // prefetched one block ahead
-      Staged st;
-      meta_issue(w_cur, st);
-      meta_finish(0, w_cur, st);
-      if (SPREAD) values_issue(0, w_cur);
-      unsigned w_val = w_cur;          // words of the packet block the next value block belongs to
-
-#pragma unroll 1
-      for (int j = 0; j < nsub; ++j) {
-        const bool more = j + 1 < nsub;
-        const bool new_block = more && ((j + 1) & 1) == 0;
-        if (new_block) {
-          w_val = w_nxt;
-          w_nxt = load_word(((j + 1) >> 1) + 1);
-          meta_issue(w_val, st);
+    };
+    // a tile without visits: plain zero stores
+    auto store_zero = [&]() {
+#pragma unroll
+      for (int r = 0; r < 2; ++r)
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+          if (8 * h + c8 < xlim)
+            for (int t = g4; t < T; t += 4)
+              gbase[(long long)r * nfx + 8 * h + (long long)(t - g4) * g.nftot] = 0ull;
+    };
+    // grid rows -> registers
+    auto load_tile = [&]() {
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        u64 q[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const int h = i >> 3, t = 4 * (i & 7) + g4;
+          q[i] = (8 * h + c8 < xlim && t < T)
+                     ? __ldg(gbase + (long long)r * nfx + 8 * h + (long long)(t - g4) * g.nftot)
+                     : 0ull;
         }
-        if (SPREAD) {
-          if (more) values_issue(j + 1, w_val);
-          if (BULK) {
-            mbar_wait(mbar_a + 8 * (j & 1), (phase >> (j & 1)) & 1u);
-            phase ^= 1u << (j & 1);
-          } else {
-            if (more) cp_async_wait<1>();
-            else cp_async_wait<0>();
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            tre[(4 * i + g4) * TBS + c8] = lo32(q[h * 8 + i]);
+            tim[(4 * i + g4) * TBS + c8] = hi32(q[h * 8 + i]);
           }
-        }
-        __syncwarp();
-        const int n = min(VBLK, nvis - j * VBLK);
-        const unsigned pk_a = meta_a + (unsigned)((((j >> 1) & 1) * MBLK + (j & 1) * VBLK) * 48);
-        const unsigned vb_a = vbuf_a + (unsigned)((j & 1) * VBLK * 32 + lane) * 8u;
-
-        auto apply = [&](const Packet& p, u64 val) {
-          if (SPREAD) {
-            const float vx = lo32(val), vy = hi32(val);
-            const float a0x = vx * p.s0, a0y = vy * p.s0, a1x = vx * p.s1, a1y = vy * p.s1;
-            const u64 A[4] = {pack2(a0x, a0x), pack2(a0y, a0y), pack2(a1x, a1x), pack2(a1y, a1y)};
-            taps_spread<W>(acc, p.idx, p.P, A);
-          } else {
-            u64 S[4];
-            taps_interp<W>(S, acc, p.idx, p.P);
-            const float px = p.s0 * (lo32(S[0]) + hi32(S[0])) + p.s1 * (lo32(S[2]) + hi32(S[2]));
-            const float py = p.s0 * (lo32(S[1]) + hi32(S[1])) + p.s1 * (lo32(S[3]) + hi32(S[3]));
-            // coils t >= T hold an all-zero tile: they add zero to their (unused) kt slot
-            red_add_f32x2(kt + (long long)p.s * 32 + lane, pack2(px, py), 1);
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            acc[r * 16 + 4 * h + j] = *reinterpret_cast<const u64*>(tre + lane * TBS + 2 * j);
+            acc[r * 16 + 8 + 4 * h + j] = *reinterpret_cast<const u64*>(tim + lane * TBS + 2 * j);
           }
-        };
-        // software-pipelined by hand: the packet (and value) of visit k + 1 is in flight while
-        // the taps of visit k execute
-        Packet pa, pb;
-        u64 va = 0ull, vb = 0ull;
-        load_packet(pk_a, pa);
-        if (SPREAD) va = lds64(vb_a);
-        int k = 0;
-#pragma unroll 1
-        for (; k + 1 < n; k += 2) {
-          load_packet(pk_a + (unsigned)(k + 1) * 48u, pb);
-          if (SPREAD) vb = lds64(vb_a + (unsigned)(k + 1) * 256u);
-          apply(pa, va);
-          const unsigned k2 = (unsigned)(k + 2) & (VBLK - 1);
-          load_packet(pk_a + k2 * 48u, pa);
-          if (SPREAD) va = lds64(vb_a + k2 * 256u);
-          apply(pb, vb);
+          __syncwarp();
         }
-        if (k < n) apply(pa, va);
-
-        if (new_block) meta_finish((j + 1) >> 1, w_val, st);
-        __syncwarp();
       }
+    };
 
-      if (SPREAD) {
-        // flush: registers (lane = coil) -> smem transpose -> coalesced 128-byte rows per coil
-        if (BULK) fence_proxy_async();
+    // ---- staging: packets in blocks of 32 entries (one lane = one entry), values in blocks of 16.
+    // Pure data movement: a lane only ever holds the {idx, s} half of its entry in registers.
+    auto load_is = [&](int mb) -> uint2 {  // {idx, s} of this lane's entry of packet block mb
+      const int i = mb * MBLK + lane;
+      return i < nw ? __ldg(reinterpret_cast<const uint2*>(v + i) + 1) : make_uint2(IDX_NONE, 0u);
+    };
+    // pull the x-weight and coil-value lines of a block's points into L2 ahead of the cp.async copies
+    auto prefetch_points = [&](const uint2& is) {
+      if (is.x < IDX_NONE) {
+        prefetch_l2(ptab + (long long)is.y * 8);
+        if (SPREAD) {
+          const char* q = reinterpret_cast<const char*>(kt + (long long)is.y * 32);
+          prefetch_l2(q);
+          prefetch_l2(q + 128);
+        }
+      }
+    };
+    // ... and the stream itself, three packet blocks (1.5 KB) ahead
+    auto prefetch_stream = [&](int mb) {
+      const int i = mb * MBLK + lane * 8;
+      if (lane < 4 && i < nw) prefetch_l2(v + i);
+    };
+    // packet block mb: entry -> last 16 bytes of the packet, x weights -> first 32 bytes (cp.async);
+    // returns the header mask of the block
+    auto stage_block = [&](int mb, const uint2& is) -> unsigned {
+      const unsigned row_a = meta_a + (unsigned)(((mb & 1) * MBLK + lane) * 48);
+      if (is.x != IDX_NONE) cp_async16(row_a + 32u, v + mb * MBLK + lane);
+      if (is.x < IDX_NONE) {
+        const float* pw = ptab + (long long)is.y * 8;
+        cp_async16(row_a, pw);
+        cp_async16(row_a + 16u, pw + 4);
+      }
+      return __ballot_sync(FULL, is.x == IDX_HDR);
+    };
+    // coil values of value block j (entries 16 j .. 16 j + 15 sit in lanes 16 (j & 1) .. of `is`, the
+    // registers of packet block j >> 1): 2 points per instruction, 16 bytes per lane
+    auto values_issue = [&](int j, const uint2& is) {
+      const int buf = j & 1;
+      const unsigned sv = is.x < IDX_NONE ? is.y : IDX_NONE;
 #pragma unroll
-        for (int r = 0; r < 2; ++r)
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            *reinterpret_cast<u64*>(tre + lane * TS + r * 16 + 2 * j) = acc[r * 16 + j];
-            *reinterpret_cast<u64*>(tim + lane * TS + r * 16 + 2 * j) = acc[r * 16 + 8 + j];
+      for (int i = 0; i < VBLK / 2; ++i) {
+        const int kk = 2 * i + hl;
+        const unsigned sk = __shfl_sync(FULL, sv, buf * VBLK + kk);
+        if (sk != IDX_NONE)
+          cp_async16(vbuf_a + (unsigned)((buf * VBLK + kk) * 32 + cl * 2) * 8u,
+                     ktl + (unsigned long long)sk * 256u);
+      }
+    };
+
+    uint2 is_val = load_is(0);   // {idx, s} of the packet block being staged / whose values are fetched
+    uint2 is_nxt = load_is(1);   // one block ahead (prefetched into L2 half a block before its staging)
+    prefetch_stream(2);
+    prefetch_stream(3);
+    unsigned hb_cur = stage_block(0, is_val);
+    unsigned hb_nxt = 0;
+    if (SPREAD) values_issue(0, is_val);
+    cp_async_commit();
+
+#pragma unroll 1
+    for (int j = 0; j < nsub; ++j) {
+      const bool more = j + 1 < nsub;
+      const bool new_block = more && ((j + 1) & 1) == 0;
+      if (new_block) {
+        const int nb = (j + 1) >> 1;
+        is_val = is_nxt;
+        is_nxt = load_is(nb + 1);
+        prefetch_stream(nb + 3);
+        hb_nxt = stage_block(nb, is_val);
+      } else {
+        prefetch_points(is_nxt);
+      }
+      if (SPREAD && more && !(dbg & 2)) values_issue(j + 1, is_val);
+      cp_async_commit();
+      if (more) cp_async_wait<1>();
+      else cp_async_wait<0>();
+      __syncwarp();
+      const int n = min(VBLK, nw - j * VBLK);
+      const unsigned pk_a = meta_a + (unsigned)((((j >> 1) & 1) * MBLK + (j & 1) * VBLK) * 48);
+      const unsigned vb_a = vbuf_a + (unsigned)((j & 1) * VBLK * 32 + lane) * 8u;
+
+      // the sub-block is a sequence of visit runs separated by header entries
+      unsigned hm = (hb_cur >> ((j & 1) * VBLK)) & 0xffffu;
+      int k0 = 0;
+      for (;;) {
+        const int k1 = hm ? (__ffs(hm) - 1) : n;
+        if (k1 > k0) {
+          if (!SPREAD && !loaded) {
+            load_tile();
+            loaded = true;
           }
-        __syncwarp();
-        if (x < nfx) {
-          if (split) {
-            for (int t = 0; t < T; ++t)
-              red_add_f32x2(reinterpret_cast<float2*>(gtile + (long long)t * g.nftot),
-                            pack2(tre[t * TS + lane], tim[t * TS + lane]), 1);
-          } else {
-#pragma unroll 4
-            for (int t = 0; t < T; ++t)
-              gtile[(long long)t * g.nftot] = pack2(tre[t * TS + lane], tim[t * TS + lane]);
+          dirty = true;
+          if (SPREAD) rows_loop_spread<W>(acc, pk_a + (unsigned)k0 * 48u, k1 - k0, vb_a + (unsigned)k0 * 256u);
+          else rows_loop_interp<W>(acc, pk_a + (unsigned)k0 * 48u, k1 - k0, ktl);
+        }
+        if (k1 >= n) break;
+        hm &= hm - 1;
+        // a header: the tile in the registers is complete if its own header came by in this chunk
+        if (SPREAD && !(dbg & 1)) {
+          if (dirty) {
+            if (started) flush(std::integral_constant<int, 0>());
+            else flush(std::integral_constant<int, 1>());
+#pragma unroll
+            for (int i = 0; i < NACC; ++i) acc[i] = 0ull;
+          } else if (started) {
+            store_zero();
           }
         }
-        __syncwarp();
+        tile_setup((int)lds32(pk_a + (unsigned)k1 * 48u + 44u));
+        started = true;
+        loaded = false;
+        dirty = false;
+        k0 = k1 + 1;
+      }
+      if (new_block) hb_cur = hb_nxt;
+      __syncwarp();
+    }
+
+    if (SPREAD && !(dbg & 1)) {
+      if (dirty) {
+        if (started && tail_whole) flush(std::integral_constant<int, 0>());
+        else flush(std::integral_constant<int, 1>());
+      } else if (started && tail_whole) {
+        store_zero();
       }
     }
   }
@@ -807,25 +810,23 @@ k_rows(Geom g, int T, long long nitems, const int4* __restrict__ items,
 constexpr int EFALLBACK = 1;  // internal: the row kernels cannot serve this trajectory
 
 template <int DIM, int W>
-int build_items(b200_plan* p, RowsState* ts, cudaStream_t st) {
+int build_stream(b200_plan* p, RowsState* ts, cudaStream_t st) {
   const long long nrows = num_rows<DIM>(p->g);
   auto fr = [](void* q) {
     if (q) cudaFree(q);
   };
   ts->unsupported = false;
-  if (nrows >= (1LL << 31) - 2 || p->M >= (long long)VIS_SMASK) {
+  if (nrows >= (1LL << 30) || p->M >= (1LL << 31) - 2) {
     ts->unsupported = true;
     return B200_OK;
   }
   if (ts->nrows != nrows) {
     fr(ts->d_tot);
-    fr(ts->d_vis_start);
-    fr(ts->d_item_start);
-    ts->d_tot = ts->d_item_start = nullptr;
-    ts->d_vis_start = nullptr;
+    fr(ts->d_start);
+    ts->d_tot = nullptr;
+    ts->d_start = nullptr;
     CUDA_TRY(cudaMalloc(&ts->d_tot, (size_t)(nrows + 1) * 4));
-    CUDA_TRY(cudaMalloc(&ts->d_vis_start, (size_t)(nrows + 1) * 4));
-    CUDA_TRY(cudaMalloc(&ts->d_item_start, (size_t)(nrows + 1) * 4));
+    CUDA_TRY(cudaMalloc(&ts->d_start, (size_t)(nrows + 1) * 4));
     ts->nrows = nrows;
   }
   CUDA_TRY(cudaMemsetAsync(ts->d_counters, 0, 64, st));
@@ -835,57 +836,52 @@ int build_items(b200_plan* p, RowsState* ts, cudaStream_t st) {
   unsigned long long grand = 0;
   CUDA_TRY(cudaMemcpyAsync(&grand, ts->d_counters + 2, 8, cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaStreamSynchronize(st));
-  if (grand >= (1ULL << 31)) {
+  if (grand + (unsigned long long)nrows >= (1ULL << 31)) {
     ts->unsupported = true;
     return B200_OK;
   }
-  k_scan_inputs<<<ceil_div(nrows + 1, 256), 256, 0, st>>>(nrows + 1, ts->d_tot, ts->d_vis_start,
-                                                          ts->d_item_start);
+  k_scan_inputs<<<ceil_div(nrows + 1, 256), 256, 0, st>>>(nrows + 1, ts->d_tot, ts->d_start);
   CHECK_LAUNCH();
-  size_t need = 0, need2 = 0;
-  cub::DeviceScan::ExclusiveSum(nullptr, need, ts->d_item_start, ts->d_item_start, (int)(nrows + 1), st);
-  cub::DeviceScan::ExclusiveSum(nullptr, need2, ts->d_vis_start, ts->d_vis_start, (int)(nrows + 1), st);
-  if (need2 > need) need = need2;
+  size_t need = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, need, ts->d_start, ts->d_start, (int)(nrows + 1), st);
   if (need > ts->scan_tmp_bytes) {
     fr(ts->d_scan_tmp);
     ts->d_scan_tmp = nullptr;
     CUDA_TRY(cudaMalloc(&ts->d_scan_tmp, need));
     ts->scan_tmp_bytes = need;
   }
-  CUDA_TRY(cub::DeviceScan::ExclusiveSum(ts->d_scan_tmp, need, ts->d_item_start, ts->d_item_start,
-                                         (int)(nrows + 1), st));
-  CUDA_TRY(cub::DeviceScan::ExclusiveSum(ts->d_scan_tmp, need, ts->d_vis_start, ts->d_vis_start,
-                                         (int)(nrows + 1), st));
-  g_kernel_launches += 4;
-  int32_t nitems = 0;
-  CUDA_TRY(cudaMemcpyAsync(&nitems, ts->d_item_start + nrows, 4, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cub::DeviceScan::ExclusiveSum(ts->d_scan_tmp, need, ts->d_start, ts->d_start, (int)(nrows + 1), st));
+  g_kernel_launches += 2;
+  uint32_t S = 0;
+  CUDA_TRY(cudaMemcpyAsync(&S, ts->d_start + nrows, 4, cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaStreamSynchronize(st));
-  fr(ts->d_items);
+  const int nchunks = (int)((S + LCH - 1) / LCH);
+  fr(ts->d_ent);
+  fr(ts->d_chunk_row);
   fr(ts->d_split_rows);
-  fr(ts->d_vis);
-  ts->d_items = nullptr;
+  ts->d_ent = nullptr;
+  ts->d_chunk_row = nullptr;
   ts->d_split_rows = nullptr;
-  ts->d_vis = nullptr;
-  CUDA_TRY(cudaMalloc(&ts->d_items, (size_t)(nitems > 0 ? nitems : 1) * sizeof(int4)));
-  CUDA_TRY(cudaMalloc(&ts->d_split_rows, (size_t)(nitems / 2 + 1) * 4));
-  // + 64 words of slack: the kernel prefetches one packet block of words ahead (guarded, but cheap)
-  if (cudaMalloc(&ts->d_vis, (size_t)(grand + 64) * 4) != cudaSuccess) {
+  // + 64 entries of all-ones padding: the kernel looks one entry past the last chunk
+  if (cudaMalloc(&ts->d_ent, ((size_t)S + 64) * 16) != cudaSuccess) {
     cudaGetLastError();
-    ts->d_vis = nullptr;
+    ts->d_ent = nullptr;
     ts->unsupported = true;
     return B200_OK;
   }
-  k_fill_items<<<ceil_div(nrows, 256), 256, 0, st>>>(nrows, ts->d_tot, ts->d_vis_start,
-                                                     ts->d_item_start, ts->d_items,
-                                                     ts->d_split_rows, ts->d_counters + 1);
-  CHECK_LAUNCH();
-  k_build_visits<DIM, W><<<ceil_div(nrows * 32, 256), 256, 0, st>>>(p->g, nrows, p->d_bin_start, ts->d_tot,
-                                                                    ts->d_vis_start, ts->d_vis);
+  CUDA_TRY(cudaMalloc(&ts->d_chunk_row, (size_t)(nchunks + 1) * 4));
+  CUDA_TRY(cudaMalloc(&ts->d_split_rows, (size_t)(nchunks + 1) * 4));
+  CUDA_TRY(cudaMemsetAsync(ts->d_ent, 0xff, ((size_t)S + 64) * 16, st));
+  CUDA_TRY(cudaMemsetAsync(ts->d_chunk_row, 0, (size_t)(nchunks + 1) * 4, st));
+  k_build_stream<DIM, W><<<ceil_div(nrows * 32, 256), 256, 0, st>>>(
+      p->g, nrows, p->d_bin_start, ts->d_tot, ts->d_start, ts->d_rec, ts->d_ent, ts->d_chunk_row,
+      ts->d_split_rows, ts->d_counters + 1);
   CHECK_LAUNCH();
   int nsplit = 0;
   CUDA_TRY(cudaMemcpyAsync(&nsplit, ts->d_counters + 1, 4, cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaStreamSynchronize(st));
-  ts->nitems = nitems;
+  ts->S = S;
+  ts->nchunks = nchunks;
   ts->nsplit = nsplit;
   ts->nvis = (long long)grand;
   return B200_OK;
@@ -897,19 +893,26 @@ int prepare(b200_plan* p, RowsState* ts, cudaStream_t st) {
   if (!ts->d_counters) CUDA_TRY(cudaMalloc(&ts->d_counters, 64));
   if (ts->d_rec) cudaFree(ts->d_rec);
   if (ts->d_iperm) cudaFree(ts->d_iperm);
+  if (ts->d_ptab) cudaFree(ts->d_ptab);
   ts->d_rec = nullptr;
   ts->d_iperm = nullptr;
+  ts->d_ptab = nullptr;
+  CUDA_TRY(cudaMalloc(&ts->d_ptab, (size_t)(M > 0 ? M : 1) * 8 * sizeof(float)));
   CUDA_TRY(cudaMalloc(&ts->d_rec, (size_t)(M > 0 ? M : 1) * REC * sizeof(float)));
   CUDA_TRY(cudaMalloc(&ts->d_iperm, (size_t)(M > 0 ? M : 1) * 4));
   if (M > 0) {
     k_point_records<W><<<ceil_div(M, 256), 256, 0, st>>>(
         p->g, M, p->d_poly, p->d_org_s[0], p->d_org_s[1], p->d_org_s[2], p->d_x1_s[0],
-        p->d_x1_s[1], p->d_x1_s[2], ts->d_rec);
+        p->d_x1_s[1], p->d_x1_s[2], ts->d_rec, ts->d_ptab);
     CHECK_LAUNCH();
     k_invert_perm<<<ceil_div(M, 256), 256, 0, st>>>(M, p->d_perm, ts->d_iperm);
     CHECK_LAUNCH();
   }
-  B200_TRY((build_items<DIM, W>(p, ts, st)));
+  B200_TRY((build_stream<DIM, W>(p, ts, st)));
+  // the records only feed the stream builder
+  CUDA_TRY(cudaStreamSynchronize(st));
+  cudaFree(ts->d_rec);
+  ts->d_rec = nullptr;
   ts->M = M;
   ts->valid = true;
   return B200_OK;
@@ -917,18 +920,15 @@ int prepare(b200_plan* p, RowsState* ts, cudaStream_t st) {
 
 template <int DIM, int W, bool SPREAD>
 int launch_rows(b200_plan* p, RowsState* ts, float2* fw, int T, cudaStream_t st) {
-  const bool bulk = SPREAD && p->rows_bulk != 0;
-  auto kern = SPREAD ? (bulk ? k_rows<DIM, W, SPREAD, true> : k_rows<DIM, W, SPREAD, false>)
-                     : k_rows<DIM, W, false, false>;
-  const size_t smem = (size_t)WARPS * SM_WARP;
-  static bool attr_done[2] = {false, false};
-  static int ctas_per_sm[2] = {1, 1};
-  const int v = bulk ? 1 : 0;
-  if (!attr_done[v]) {
+  auto kern = k_rows<DIM, W, SPREAD>;
+  const size_t smem = (size_t)WARPS * smem_per_warp(SPREAD);
+  static bool attr_done = false;
+  static int ctas_per_sm = 1;
+  if (!attr_done) {
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm[v], kern, THREADS, smem));
-    if (ctas_per_sm[v] < 1) ctas_per_sm[v] = 1;
-    attr_done[v] = true;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, THREADS, smem));
+    if (ctas_per_sm < 1) ctas_per_sm = 1;
+    attr_done = true;
   }
   if (SPREAD && ts->nsplit > 0) {
     k_zero_split_rows<DIM><<<ceil_div(ts->nsplit * 32, 128), 128, 0, st>>>(p->g, T, ts->nsplit,
@@ -936,14 +936,14 @@ int launch_rows(b200_plan* p, RowsState* ts, float2* fw, int T, cudaStream_t st)
     CHECK_LAUNCH();
   }
   CUDA_TRY(cudaMemsetAsync(ts->d_counters, 0, sizeof(int), st));
-  const long long want = (ts->nitems + GROUP * WARPS - 1) / (GROUP * WARPS);
-  const long long cap = (long long)p->num_sms * ctas_per_sm[v];
+  const long long want = (ts->nchunks + WARPS - 1) / WARPS;
+  const long long cap = (long long)p->num_sms * ctas_per_sm;
   const int grid = (int)(want < cap ? (want > 0 ? want : 1) : cap);
   // slot 4 of the plan's timing events brackets the row kernel alone (bench.py roofline)
   const bool timed = p->timing && p->ev_ok;
   if (timed) cudaEventRecord(p->ev[8], st);
-  kern<<<grid, THREADS, smem, st>>>(p->g, T, ts->nitems, ts->d_items, ts->d_vis, ts->d_rec,
-                                    ts->d_kt, fw, ts->d_counters);
+  kern<<<grid, THREADS, smem, st>>>(p->g, T, ts->nchunks, ts->S, p->M, ts->d_ent, ts->d_chunk_row,
+                                    ts->d_ptab, ts->d_kt, fw, ts->d_counters, p->rows_bulk);
   if (timed) {
     cudaEventRecord(p->ev[9], st);
     p->ev_used[4] = 1;
@@ -992,10 +992,9 @@ void tiled_free(b200_plan* p) {
   fr(ts->d_kt);
   fr(ts->d_iperm);
   fr(ts->d_tot);
-  fr(ts->d_vis_start);
-  fr(ts->d_item_start);
-  fr(ts->d_items);
-  fr(ts->d_vis);
+  fr(ts->d_start);
+  fr(ts->d_ent);
+  fr(ts->d_chunk_row);
   fr(ts->d_split_rows);
   fr(ts->d_counters);
   fr(ts->d_scan_tmp);

@@ -1,23 +1,29 @@
 #!/usr/bin/env python
-"""Generate csrc/taps_generated.inc: the per-visit tap kernels of spread_rows.cu as inline PTX.
+"""Generate csrc/taps_generated.inc: the visit loops of spread_rows.cu as inline PTX.
 
-Why generated PTX: the row accumulators live in statically indexed registers, so a visit must jump
+Why generated PTX: the tile accumulators live in statically indexed registers, so a visit must jump
 to straight-line code specialised for its x offset.  nvcc lowers a many-way C++ `switch` to a
 compare/branch tree (17 issue slots per visit, measured with ncu); PTX `brx.idx` gives one indexed
-branch.  The FMAs are Blackwell's packed `fma.rn.f32x2` (SASS FFMA2).
+branch.  The whole loop over a run of staged visits is one asm block: with the loop in C++ and only
+the taps in asm, nvcc re-assigned the 32 accumulator pairs between the asm instances of the
+pipelined loop and paid ~9 register moves per visit (ncu, round 1).  The FMAs are Blackwell's
+packed `fma.rn.f32x2` (SASS FFMA2).
 
 Register layout of a warp's tile (2 grid rows x 16 cells, lane = coil):
     acc[r*16 + c*8 + j]   r = row (0, 1), c = 0 real / 1 imaginary part,
                           j = cell pair: 64-bit register = (cell 2j, cell 2j+1)
-A visit with x offset `off` (first tap lands on cell `off`, -(W-1) <= off <= 15) is staged as
-    jb  = floor(off / 2), idx = jb + W//2  (>= 0)
-    P_q = (w[2q - par], w[2q + 1 - par]),  par = off & 1, q < NP = W//2 + 1   (unscaled x weights)
-and applied to cell pairs j = jb + q.
+A visit is staged in shared memory as a 48-byte packet (read with warp-broadcast loads)
+    P_0..P_3 : pair-packed x weights, P_q = (w[2q - par], w[2q + 1 - par]), par = x offset & 1
+    s0, s1   : row scales wy[dy] wz[dz], wy[dy + 1] wz[dz]
+    idx      : floor(x offset / 2) + W // 2  (>= 0): which cell pairs j = idx - W//2 + q are hit
+    s        : sorted point index
+and, for the spreader, the point's coil values in a [visit][32 coils] (re, im) array.
 
-spread:  acc[r][c][j] += P_q * A_rc        A_rc = (a, a), a = (re|im of the coil value) * s_r
-         operands: %0..%31 acc ("+l"), %32 idx, %33..%36 P, %37..%40 A00 A01 A10 A11
-interp:  S_rc = sum_q acc[r][c][j] * P_q   (lane-wise pair sums, reduced by the caller)
-         operands: %0..%3 S ("=l"), %4..%35 acc ("+l", read only), %36 idx, %37..%40 P
+spread:  acc[r][c][j] += P_q * (a, a),  a = (re | im of this lane's coil value) * s_r
+interp:  kt[s][lane] += sum_r s_r * sum_{q, lanes of the pair} acc[r][c][j] * P_q   (red.global.add.v2.f32)
+
+The loop is software-pipelined by hand over two register sets (A, B): the packet (and value) of
+visit k + 1 is loaded before the taps of visit k execute.
 """
 import sys
 
@@ -29,18 +35,28 @@ def cases(W):
     return jb0, NJ + jb0  # idx offset, number of cases (jb = -jb0 .. NJ-1)
 
 
-def gen_spread(W):
+def load_set(X, off_pk, off_vb, pred, spread):
+    p = f"@!{pred} " if pred else ""
+    L = [f"{p}ld.shared.v2.b64 {{P{X}0, P{X}1}}, [pk+{off_pk}];",
+         f"{p}ld.shared.v2.b64 {{P{X}2, P{X}3}}, [pk+{off_pk + 16}];",
+         f"{p}ld.shared.v4.b32 {{s{X}0, s{X}1, i{X}, n{X}}}, [pk+{off_pk + 32}];"]
+    if spread:
+        L.append(f"{p}ld.shared.b64 v{X}, [vb+{off_vb}];")
+    return L
+
+
+def taps_spread(W, X):
     jb0, ncase = cases(W)
     NP = W // 2 + 1
-    L = [f"__device__ __forceinline__ void taps_spread_w{W}(",
-         "    unsigned long long (&acc)[32], unsigned idx, const unsigned long long (&P)[4],",
-         "    const unsigned long long (&A)[4]) {",
-         "  asm volatile("]
-    body = ["{\\n", "tbl: .branchtargets " + ", ".join(f"C{i}" for i in range(ncase)) + ";\\n",
-            "brx.idx.uni %32, tbl;\\n"]
+    L = [f"mov.b64 {{vx, vy}}, v{X};",
+         f"mul.f32 t0, vx, s{X}0;", f"mul.f32 t1, vy, s{X}0;",
+         f"mul.f32 t2, vx, s{X}1;", f"mul.f32 t3, vy, s{X}1;",
+         "mov.b64 A0, {t0, t0};", "mov.b64 A1, {t1, t1};", "mov.b64 A2, {t2, t2};", "mov.b64 A3, {t3, t3};",
+         f"tbl{X}: .branchtargets " + ", ".join(f"C{X}{i}" for i in range(ncase)) + ";",
+         f"brx.idx.uni i{X}, tbl{X};"]
     for c in range(ncase):
         jb = c - jb0
-        body.append(f"C{c}:\\n")
+        L.append(f"C{X}{c}:")
         for q in range(NP):
             j = jb + q
             if j < 0 or j >= NJ:
@@ -48,29 +64,20 @@ def gen_spread(W):
             for r in range(2):
                 for ri in range(2):
                     a = r * 16 + ri * 8 + j
-                    body.append(f"fma.rn.f32x2 %{a}, %{33 + q}, %{37 + r * 2 + ri}, %{a};\\n")
-        body.append("bra.uni DONE;\\n")
-    body += ["DONE:\\n", "}\\n"]
-    L += [f'      "{b}"' for b in body]
-    L.append("      : " + ", ".join(f'"+l"(acc[{i}])' for i in range(32)))
-    L.append('      : "r"(idx), ' + ", ".join(f'"l"(P[{i}])' for i in range(4)) + ", " +
-             ", ".join(f'"l"(A[{i}])' for i in range(4)) + ");")
-    L.append("}")
-    return "\n".join(L)
+                    L.append(f"fma.rn.f32x2 %{a}, P{X}{q}, A{r * 2 + ri}, %{a};")
+        L.append(f"bra.uni J{X};")
+    L.append(f"J{X}:")
+    return L
 
 
-def gen_interp(W):
+def taps_interp(W, X):
     jb0, ncase = cases(W)
     NP = W // 2 + 1
-    L = [f"__device__ __forceinline__ void taps_interp_w{W}(",
-         "    unsigned long long (&S)[4], unsigned long long (&acc)[32], unsigned idx,",
-         "    const unsigned long long (&P)[4]) {",
-         "  asm volatile("]
-    body = ["{\\n", "tbl: .branchtargets " + ", ".join(f"C{i}" for i in range(ncase)) + ";\\n",
-            "brx.idx.uni %36, tbl;\\n"]
+    L = [f"tbl{X}: .branchtargets " + ", ".join(f"C{X}{i}" for i in range(ncase)) + ";",
+         f"brx.idx.uni i{X}, tbl{X};"]
     for c in range(ncase):
         jb = c - jb0
-        body.append(f"C{c}:\\n")
+        L.append(f"C{X}{c}:")
         for r in range(2):
             for ri in range(2):
                 o = r * 2 + ri
@@ -79,30 +86,62 @@ def gen_interp(W):
                     j = jb + q
                     if j < 0 or j >= NJ:
                         continue
-                    a = 4 + r * 16 + ri * 8 + j
+                    a = r * 16 + ri * 8 + j
                     if first:
-                        body.append(f"mul.rn.f32x2 %{o}, %{a}, %{37 + q};\\n")
+                        L.append(f"mul.rn.f32x2 S{o}, %{a}, P{X}{q};")
                         first = False
                     else:
-                        body.append(f"fma.rn.f32x2 %{o}, %{a}, %{37 + q}, %{o};\\n")
-        body.append("bra.uni DONE;\\n")
-    body += ["DONE:\\n", "}\\n"]
-    L += [f'      "{b}"' for b in body]
-    # acc is declared read-write ("+l") although it is only read: as a plain input nvcc keeps the two
-    # halves of each 64-bit value in unrelated registers and re-assembles the pair with two moves
-    # before every FFMA2 (24 extra instructions per visit, measured); "+l" pins aligned pairs.
-    L.append("      : " + ", ".join(f'"=l"(S[{i}])' for i in range(4)) + ", " +
-             ", ".join(f'"+l"(acc[{i}])' for i in range(32)))
-    L.append('      : "r"(idx), ' + ", ".join(f'"l"(P[{i}])' for i in range(4)) + ");")
+                        L.append(f"fma.rn.f32x2 S{o}, %{a}, P{X}{q}, S{o};")
+        L.append(f"bra.uni J{X};")
+    L += [f"J{X}:",
+          "mov.b64 {lo, hi}, S0;", "add.f32 t0, lo, hi;",
+          "mov.b64 {lo, hi}, S1;", "add.f32 t1, lo, hi;",
+          "mov.b64 {lo, hi}, S2;", "add.f32 t2, lo, hi;",
+          "mov.b64 {lo, hi}, S3;", "add.f32 t3, lo, hi;",
+          f"mul.f32 t0, t0, s{X}0;", f"fma.rn.f32 t0, t2, s{X}1, t0;",
+          f"mul.f32 t1, t1, s{X}0;", f"fma.rn.f32 t1, t3, s{X}1, t1;",
+          f"mad.wide.u32 addr, n{X}, 256, ktl;",
+          "red.global.add.v2.f32 [addr], {t0, t1};"]
+    return L
+
+
+def gen_loop(W, spread):
+    name = f"rows_loop_{'spread' if spread else 'interp'}_w{W}"
+    taps = taps_spread if spread else taps_interp
+    body = ["{",
+            ".reg .b64 PA<4>, PB<4>, vA, vB, A<4>, S<4>, addr, ktl;",
+            ".reg .b32 sA<2>, sB<2>, iA, iB, nA, nB, vx, vy, lo, hi, t<4>, pk, vb, n;",
+            ".reg .pred p1, p2, p3;",
+            "mov.u32 pk, %32;", "mov.u32 n, %33;"]
+    body.append("mov.u32 vb, %34;" if spread else "mov.u64 ktl, %34;")
+    body += load_set("A", 0, 0, None, spread)
+    body += ["LOOP:", "setp.lt.s32 p1, n, 2;"]
+    body += load_set("B", 48, 256, "p1", spread)
+    body += taps(W, "A")
+    body += ["@p1 bra.uni DONE;", "setp.lt.s32 p2, n, 3;"]
+    body += load_set("A", 96, 512, "p2", spread)
+    body += taps(W, "B")
+    body += ["add.u32 pk, pk, 96;"]
+    if spread:
+        body.append("add.u32 vb, vb, 512;")
+    body += ["add.s32 n, n, -2;", "setp.gt.s32 p3, n, 0;", "@p3 bra.uni LOOP;", "DONE:", "}"]
+    L = [f"__device__ __forceinline__ void {name}(",
+         "    unsigned long long (&acc)[32], unsigned pk, int n, "
+         + ("unsigned vb) {" if spread else "const void* ktl) {"),
+         "  asm volatile("]
+    L += [f'      "{b}\\n"' for b in body]
+    L.append("      : " + ", ".join(f'"+l"(acc[{i}])' for i in range(32)))
+    L.append('      : "r"(pk), "r"(n), ' + ('"r"(vb)' if spread else '"l"(ktl)'))
+    L.append('      : "memory");')
     L.append("}")
     return "\n".join(L)
 
 
 def main():
-    out = ["// GENERATED by tools/gen_taps.py -- do not edit.  See that script for the operand layout.",
+    out = ["// GENERATED by tools/gen_taps.py -- do not edit.  See that script for the layout.",
            "#pragma once", ""]
     for W in (4, 5, 6, 7):
-        out += [gen_spread(W), "", gen_interp(W), ""]
+        out += [gen_loop(W, True), "", gen_loop(W, False), ""]
     path = sys.argv[1] if len(sys.argv) > 1 else "mrinufft_b200/csrc/taps_generated.inc"
     open(path, "w").write("\n".join(out))
 
