@@ -79,6 +79,8 @@ constexpr int SM_VBUF = 2 * VBLK * 32 * 8;  // double-buffered coil values of VB
 constexpr int SM_META = 2 * MBLK * 48;      // double-buffered packets {P0..P3, s0, s1, idx, s}
 constexpr int TBS = 10;                     // float stride of the transpose planes [32 coils][8 cells]
 constexpr int SM_TBUF = 2 * 32 * TBS * 4;   // real + imaginary plane of half a grid row (8 cells), 32 coils
+constexpr int TFS = 18;                     // spreader's flush: planes [16 coils][16 cells], float stride 18
+static_assert(2 * 16 * TFS * 4 <= SM_TBUF, "flush planes must fit in the transpose buffer");
 __host__ __device__ constexpr int smem_per_warp(bool spread) { return (spread ? SM_VBUF : 0) + SM_META + SM_TBUF; }
 
 struct RowsState {
@@ -558,7 +560,7 @@ k_rows(Geom g, int T, int nchunks, unsigned S, long long M, const uint4* __restr
   // transpose planes [32 coils][TBS]: lane = coil on the register side; on the grid side a warp
   // instruction moves 8 cells (64 contiguous bytes) of 4 coils
   float* tre = reinterpret_cast<float*>(metap + SM_META);
-  float* tim = tre + 32 * TBS;
+  float* tim = tre + 32 * TBS;  // (the flush's [16][TFS] planes start at the same offsets)
   const int g4 = lane >> 3, c8 = lane & 7;  // grid-side role: coil 4 i + g4, cell 8 h + c8
   const char* ktl = reinterpret_cast<const char*>(kt) + (SPREAD ? cl * 16 : lane * 8);
   asm volatile("" : "+l"(ktl));
@@ -582,6 +584,7 @@ k_rows(Geom g, int T, int nchunks, unsigned S, long long M, const uint4* __restr
 
     // ---- the tile in the accumulators
     u64* gbase = nullptr;  // grid-side role of this lane: cell c8 of coil g4, row 0 of the tile
+    u64* fbase = nullptr;  // ... in the spreader's flush: cell cl of coil hl
     int xlim = 0;          // cells of this tile inside the grid (16, less for a short last tile)
     auto tile_setup = [&](int row) {
       // 32-bit version of decode_row (tile ids are below 2^30 here)
@@ -597,6 +600,7 @@ k_rows(Geom g, int T, int nchunks, unsigned S, long long M, const uint4* __restr
       const int y = yb * YB + pg * 8 + ps * 2;
       xlim = nfx - bx * CX;
       gbase = fw64 + ((long long)z * nfy + y) * nfx + bx * CX + c8 + (long long)g4 * g.nftot;
+      if (SPREAD) fbase = fw64 + ((long long)z * nfy + y) * nfx + bx * CX + cl + (long long)hl * g.nftot;
     };
     tile_setup(__ldg(chunk_row + c));
     bool started = false;  // the tile's header came by in this chunk
@@ -608,29 +612,31 @@ k_rows(Geom g, int T, int nchunks, unsigned S, long long M, const uint4* __restr
 #pragma unroll
     for (int i = 0; i < NACC; ++i) acc[i] = 0ull;
 
-    // registers (lane = coil) -> grid rows: 8 cells of one row of all coils at a time go through the
-    // transpose planes; a store instruction writes 64 contiguous bytes of 4 coils.
+    // registers (lane = coil) -> grid rows: 16 coils of one row at a time go through the transpose
+    // planes; a store instruction writes one full 128-byte line of 2 coils.
     // MODE 0: plain stores (the tile is complete), 1: red.add (tile shared with other chunks)
     auto flush = [&](auto mode) {
       constexpr int MODE = decltype(mode)::value;
 #pragma unroll
       for (int r = 0; r < 2; ++r)
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
+        for (int half = 0; half < 2; ++half) {
+          if (hl == half) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            *reinterpret_cast<u64*>(tre + lane * TBS + 2 * j) = acc[r * 16 + 4 * h + j];
-            *reinterpret_cast<u64*>(tim + lane * TBS + 2 * j) = acc[r * 16 + 8 + 4 * h + j];
+            for (int j = 0; j < 8; ++j) {
+              *reinterpret_cast<u64*>(tre + cl * TFS + 2 * j) = acc[r * 16 + j];
+              *reinterpret_cast<u64*>(tim + cl * TFS + 2 * j) = acc[r * 16 + 8 + j];
+            }
           }
           __syncwarp();
-          if (8 * h + c8 < xlim) {
-            u64* dst = gbase + (long long)r * nfx + 8 * h;
+          if (cl < xlim) {
+            u64* dst = fbase + (long long)r * nfx + (long long)(half * 16) * g.nftot;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-              const int t = 4 * i + g4;
-              if (T == 32 || t < T) {
-                const u64 val = pack2(tre[t * TBS + c8], tim[t * TBS + c8]);
-                u64* a = dst + (long long)(4 * i) * g.nftot;
+              const int tl = 2 * i + hl;  // coil inside this half
+              if (T == 32 || half * 16 + tl < T) {
+                const u64 val = pack2(tre[tl * TFS + cl], tim[tl * TFS + cl]);
+                u64* a = dst + (long long)(2 * i) * g.nftot;
                 if (MODE == 0) *a = val;
                 else red_add_f32x2(reinterpret_cast<float2*>(a), val, 1);
               }
@@ -641,13 +647,11 @@ k_rows(Geom g, int T, int nchunks, unsigned S, long long M, const uint4* __restr
     };
     // a tile without visits: plain zero stores
     auto store_zero = [&]() {
+      if (cl < xlim) {
 #pragma unroll
-      for (int r = 0; r < 2; ++r)
-#pragma unroll
-        for (int h = 0; h < 2; ++h)
-          if (8 * h + c8 < xlim)
-            for (int t = g4; t < T; t += 4)
-              gbase[(long long)r * nfx + 8 * h + (long long)(t - g4) * g.nftot] = 0ull;
+        for (int r = 0; r < 2; ++r)
+          for (int t = hl; t < T; t += 2) fbase[(long long)r * nfx + (long long)(t - hl) * g.nftot] = 0ull;
+      }
     };
     // grid rows -> registers
     auto load_tile = [&]() {
