@@ -32,8 +32,9 @@ for _p in (ROOT, ROOT / "baseline" / "_ref"):
         sys.path.insert(0, str(_p))
 
 METRIC = "3D 32-coil NUFFT op+adj_op throughput"
-# DRAM bytes of one launch of the row kernels at cfg-C, from profiles/r01_k_rows_duo_full.txt
-NCU_TRAFFIC_GB = {"spread": 57.6, "interp": 53.2}
+# DRAM bytes (read + write) of one launch of the row kernels at cfg-C, `ncu --set full`:
+# profiles/r01_k_rows_stream_full.txt
+NCU_TRAFFIC_GB = {"spread": 61.1, "interp": 41.6}
 UNIT = "k-samples/s"
 
 
@@ -366,8 +367,9 @@ def run_b200(args):
         "peak_source": peak_src, "kernel_ms": kt, "algorithmic_bytes_per_launch": ab[dom_name],
         "step_algorithmic_bytes": ab["pair_all_coils"],
         "step_frac": ab["pair_all_coils"] / (ms_max * 1e-3) / 1e9 / peak,
-        "note": "the row kernels are bound by the L1/shared data pipe and instruction issue, not by HBM "
-                "(ncu: l1tex 70 %, issue 55 %, dram 29 %); frac is quoted against the HBM floor as the contract asks",
+        "note": "the row kernels are bound by instruction issue and the L1/shared data pipe, not by HBM "
+                "(ncu: issue 44-56 %, l1tex 49-60 %, dram 25-28 %); frac is quoted against the HBM floor as the "
+                "contract asks",
     }
 
     cpu_baseline = None

@@ -179,7 +179,8 @@ int b200_launch_count(int64_t* kernels, int64_t* ffts, int reset);
  *   key 0: spread method   (0 auto, 1 global-atomic point driven, 2 tiled)
  *   key 1: interp method   (0 auto, 1 point driven, 2 tiled)
  *   key 2: FFT method      (0 auto, 1 cuFFT + pad/crop kernels, 2 fused zero-padding-aware passes)
- *   key 3: value staging of the tiled spreader (0 cp.async, 1 TMA bulk copies + mbarrier)
+ *   key 3: timing experiments on the tiled spreader (bit 0: skip the tile flush, bit 1: skip the
+ *          coil-value copies; results are then wrong -- never set outside a profiling session)
  */
 int b200_plan_set_option(b200_plan* plan, int key, int64_t value);
 

@@ -392,7 +392,7 @@ int b200_plan_set_option(b200_plan* p, int key, int64_t value) {
     case 0: p->spread_method = (int)value; break;
     case 1: p->interp_method = (int)value; break;
     case 2: p->fft_method = (int)value; break;
-    case 3: p->rows_bulk = (int)value; break;
+    case 3: p->rows_dbg = (int)value; break;
     default:
       b200_set_error("unknown option key %d", key);
       return B200_EINVAL;

@@ -118,7 +118,7 @@ struct b200_plan {
 
   // options
   int spread_method = 0, interp_method = 0, fft_method = 0;
-  int rows_bulk = 0;  // 1: TMA bulk copies stage the coil values of the spreading row kernel
+  int rows_dbg = 0;  // option 3: timing-experiment switches of the spreading row kernel (see b200nufft.h)
 
   // timing
   bool timing = false;

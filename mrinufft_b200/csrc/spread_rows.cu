@@ -947,7 +947,7 @@ int launch_rows(b200_plan* p, RowsState* ts, float2* fw, int T, cudaStream_t st)
   const bool timed = p->timing && p->ev_ok;
   if (timed) cudaEventRecord(p->ev[8], st);
   kern<<<grid, THREADS, smem, st>>>(p->g, T, ts->nchunks, ts->S, p->M, ts->d_ent, ts->d_chunk_row,
-                                    ts->d_ptab, ts->d_kt, fw, ts->d_counters, p->rows_bulk);
+                                    ts->d_ptab, ts->d_kt, fw, ts->d_counters, p->rows_dbg);
   if (timed) {
     cudaEventRecord(p->ev[9], st);
     p->ev_used[4] = 1;
