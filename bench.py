@@ -303,6 +303,25 @@ def run_b200(args):
     plan.enable_timing(False)
     kt = {k: float(np.mean(v)) for k, v in kt.items()}
 
+    # secondary: Toeplitz Gram operator (A^H A through two zero-padding-aware FFTs per coil) against the
+    # op + adj_op pair it replaces inside CG-type solvers; device resident, not part of `value`
+    extras = {}
+    try:
+        op.compute_toeplitz_kernel()
+        for _ in range(2):
+            op._gram_device(img_d)
+        torch.cuda.synchronize()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        for _ in range(3):
+            op._gram_device(img_d)
+        g1.record()
+        torch.cuda.synchronize()
+        extras["toeplitz_gram_ms"] = g0.elapsed_time(g1) / 3
+        op._toeplitz_kernel = None
+    except Exception as exc:  # noqa: BLE001
+        extras["toeplitz_gram_error"] = str(exc)[:200]
+
     # end-to-end through the public API with HOST buffers (pinned), copies inside the timed region
     e2e = None
     if not args.no_e2e:
@@ -391,6 +410,7 @@ def run_b200(args):
         "gpu_launches_detail": {"own_kernels": int(kernels), "cufft_execs": int(ffts)},
         "roofline": roofline, "cpu_baseline": cpu_baseline,
         "kernel_width": plan.w, "fine_grid": list(plan.nf), "workspace_gb": plan.workspace_bytes / 1e9,
+        "extras": extras,
     }
     print(json.dumps(line), flush=True)
     if world > 1:

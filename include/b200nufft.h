@@ -155,6 +155,20 @@ int b200_data_consistency(b200_plan* plan, const void* img, const void* smaps,
                           int T, int accumulate, float scale, void* stream);
 
 /*
+ * Toeplitz (Gram) operator chunk  x -> sum_t conj(S_t) . crop(IFFT(K . FFT(pad(S_t . x)))): replaces
+ * `apply_toeplitz_kernel` (src/mrinufft/operators/toeplitz.py:203-269) together with the SENSE wrap
+ * of `_gram_op_sense` / `_GramOpGpuMixin` (base.py:344-356, toeplitz.py:374-430).  No trajectory is
+ * needed (the kernel `kern` carries it); the plan's oversampled grid must be exactly 2 N per axis.
+ *   img    as in b200_type2;  smaps NULL or complex64 (T, *n_modes)
+ *   kern   float32 (*2 n_modes): real spectrum of the Toeplitz embedding, FFT index order
+ *          (what `compute_toeplitz_kernel`, toeplitz.py:35-95, returns)
+ *   out    as `img` of b200_type1;  scale is multiplied into the result (1 / prod(2 N) for the
+ *          unnormalised FFT pair)
+ */
+int b200_toeplitz_apply(b200_plan* plan, const void* img, const void* smaps, const float* kern,
+                        void* out, int T, int accumulate, float scale, void* stream);
+
+/*
  * Spread / interpolate only (plans created with B200_SPREAD_ONLY): replaces the
  * `spreadinterponly=1` plan used by `MRIfinufft.pipe` (finufft.py:225-239).
  *   grid  complex64 (T, *n_modes)

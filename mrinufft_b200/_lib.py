@@ -49,6 +49,11 @@ _SIGNATURES = {
         [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
          C.c_float, C.c_void_p],
     ),
+    "b200_toeplitz_apply": (
+        C.c_int,
+        [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_float,
+         C.c_void_p],
+    ),
     "b200_spread": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "b200_interp": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "b200_pipe_iteration": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
@@ -179,6 +184,13 @@ class Plan:
             self._lib.b200_data_consistency(self._h, img, smaps, obs, density, grad, int(T),
                                             int(accumulate), float(scale), stream),
             "b200_data_consistency",
+        )
+
+    def toeplitz_apply(self, img, smaps, kern, out, T, accumulate=0, scale=1.0, stream=0):
+        check(
+            self._lib.b200_toeplitz_apply(self._h, img, smaps, kern, out, int(T), int(accumulate),
+                                          float(scale), stream),
+            "b200_toeplitz_apply",
         )
 
     def spread(self, ksp, grid, T, stream=0):

@@ -330,6 +330,7 @@ int b200_plan_destroy(b200_plan* p) {
   fr(p->d_poly);
   for (int a = 0; a < 3; ++a) {
     fr(p->d_deapod[a]);
+    fr(p->d_ones[a]);
     fr(p->d_tw[a]);
     fr(p->d_org_u[a]);
     fr(p->d_x1_u[a]);
@@ -511,6 +512,56 @@ int b200_data_consistency(b200_plan* p, const void* img, const void* smaps, cons
   B200_TRY(do_interp(p, p->d_fw, p->d_ksp_tmp, T, scale, (const float2*)obs, st));
   B200_TRY(do_spread(p, p->d_ksp_tmp, density, p->d_fw, T, st));
   return grid_to_image(p, (const float2*)smaps, (float2*)grad, T, accumulate, +1, scale, 0, st);
+}
+
+int b200_toeplitz_apply(b200_plan* p, const void* img, const void* smaps, const float* kern,
+                        void* out, int T, int accumulate, float scale, void* stream) {
+  if (!p || !img || !kern || !out) {
+    b200_set_error("b200_toeplitz_apply: null argument");
+    return B200_EINVAL;
+  }
+  if (T < 1 || T > p->ntrans_max) {
+    b200_set_error("T=%d outside [1, n_trans_max=%d]", T, p->ntrans_max);
+    return B200_EINVAL;
+  }
+  if (p->flags & B200_SPREAD_ONLY) {
+    b200_set_error("b200_toeplitz_apply needs a full (not B200_SPREAD_ONLY) plan");
+    return B200_ESTATE;
+  }
+  for (int a = 0; a < p->g.dim; ++a)
+    if (p->g.nf[a] != 2 * p->g.N[a]) {
+      b200_set_error("b200_toeplitz_apply: the oversampled grid must be exactly 2 N (axis %d: N=%d, nf=%d)",
+                     a, p->g.N[a], p->g.nf[a]);
+      return B200_EINVAL;
+    }
+  DeviceGuard guard(p->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  for (int a = 0; a < p->g.dim; ++a) {
+    if (p->d_ones[a]) continue;
+    std::vector<float> ones(p->g.N[a], 1.f);
+    CUDA_TRY(cudaMalloc(&p->d_ones[a], ones.size() * sizeof(float)));
+    CUDA_TRY(cudaMemcpy(p->d_ones[a], ones.data(), ones.size() * sizeof(float), cudaMemcpyHostToDevice));
+  }
+  // zero-pad -> FFT -> multiply by the (real) spectrum of the Toeplitz embedding -> inverse FFT ->
+  // crop, with the sensitivity-map multiplies and the coil sum fused like in type 2 / type 1.
+  // Circular convolution commutes with shifts, so padding / cropping at the mode-centred
+  // position of the NUFFT grid instead of the top-left corner gives the same values.
+  p->unit_deapod = true;
+  int rc = B200_OK;
+  if (use_fftp(p)) {
+    Timed tm(p, EV_FFT, st);
+    rc = fftp_type2(p, (const float2*)img, (const float2*)smaps, p->d_fw, T, -1, 0, st, kern);
+    if (rc == B200_OK)
+      rc = fftp_type1(p, p->d_fw, (const float2*)smaps, (float2*)out, T, accumulate, +1, scale, 0, st);
+  } else {
+    rc = k4a_pad(p, (const float2*)img, (const float2*)smaps, p->d_fw, T, 0, st);
+    if (rc == B200_OK) rc = exec_fft(p, p->d_fw, T, -1, st);
+    if (rc == B200_OK) rc = k_mul_real(p, p->d_fw, kern, T, st);
+    if (rc == B200_OK) rc = exec_fft(p, p->d_fw, T, +1, st);
+    if (rc == B200_OK) rc = k4b_crop(p, p->d_fw, (const float2*)smaps, (float2*)out, T, accumulate, scale, 0, st);
+  }
+  p->unit_deapod = false;
+  return rc;
 }
 
 int b200_spread(b200_plan* p, const void* ksp, void* grid, int T, void* stream) {

@@ -86,6 +86,9 @@ struct b200_plan {
   float* d_poly = nullptr;                       // [(deg+1)][w]: coefficient k of tap i at k*w+i
   float* d_deapod[3] = {nullptr, nullptr, nullptr};  // N[a] floats: (-1)^k / phihat(k)
   float2* d_tw[3] = {nullptr, nullptr, nullptr};     // nf[a] roots of unity (fft_pruned.cu)
+  float* d_ones[3] = {nullptr, nullptr, nullptr};    // N[a] ones: "no deapodisation" (Toeplitz apply)
+  bool unit_deapod = false;                          // grid passes use d_ones instead of d_deapod
+  const float* dvec(int a) const { return unit_deapod ? d_ones[a] : d_deapod[a]; }
 
   // points
   long long M = 0, Mcap = 0;
@@ -154,7 +157,8 @@ int k_real_to_cpx(b200_plan* p, const float* d, float2* out, cudaStream_t st);
 // fused pad/crop + zero-padding-aware FFT passes (fft_pruned.cu)
 bool fftp_supported(const b200_plan* p);
 int fftp_type2(b200_plan* p, const float2* img, const float2* smaps, float2* fw, int T, int isign,
-               int conj_smaps, cudaStream_t st);
+               int conj_smaps, cudaStream_t st, const float* mul = nullptr);
+int k_mul_real(b200_plan* p, float2* fw, const float* kern, int T, cudaStream_t st);
 int fftp_type1(b200_plan* p, float2* fw, const float2* smaps, float2* img, int T, int accumulate,
                int isign, float scale, int conj_smaps, cudaStream_t st);
 

@@ -66,6 +66,7 @@ struct StridedArgs {
   int outer_L;             // its length
   Keep outer_keep;         // which outer indices are processed (blockIdx.y enumerates them)
   Keep in, out;            // non-zero inputs / wanted outputs along the transformed axis
+  const float* mul;        // nullable: real factor per grid point applied to the outputs (Toeplitz)
 };
 
 template <int L, int DIR>
@@ -74,8 +75,8 @@ k_fft_strided(StridedArgs A, const float2* __restrict__ tw) {
   constexpr int R1 = Split<L>::R1, R2 = Split<L>::R2;
   extern __shared__ float2 S[];  // [L][TX]
   const int lo = kept_index(blockIdx.y, A.outer_L, A.outer_keep);
-  float2* g = A.base + (long long)blockIdx.z * A.coil_stride + (long long)lo * A.outer_stride +
-              (long long)blockIdx.x * TX;
+  const long long goff = (long long)lo * A.outer_stride + (long long)blockIdx.x * TX;
+  float2* g = A.base + (long long)blockIdx.z * A.coil_stride + goff;
   // step A: R1-point FFTs over n1 (n = n1 R2 + n2), twiddle W_L^(n2 k1)
   for (int item = threadIdx.x; item < R2 * TX; item += FT) {
     const int n2 = item / TX, tx = item % TX;
@@ -110,7 +111,11 @@ k_fft_strided(StridedArgs A, const float2* __restrict__ tw) {
     sfor<0, R2>([&](auto I) {
       constexpr int k2 = decltype(I)::value;
       const int k = k1 + R1 * k2;
-      if (kept(k, L, A.out)) g[(long long)k * A.stride_n + tx] = b[brev(k2, R2)];
+      if (kept(k, L, A.out)) {
+        float2 v = b[brev(k2, R2)];
+        if (A.mul) v = cscale(v, __ldg(A.mul + goff + (long long)k * A.stride_n + tx));
+        g[(long long)k * A.stride_n + tx] = v;
+      }
     });
   }
 }
@@ -471,10 +476,11 @@ int launch_rows_t1(const RowArgs& A, int nrows, const float2* tw, cudaStream_t s
 
 // pass along axis `a` (not the fastest one) of the [nf0][nf1][nf2] (or [nf0][nf1]) grid
 int strided_pass(b200_plan* p, float2* fw, int T, int a, int dir, Keep in, Keep out, Keep outer_keep,
-                 cudaStream_t st) {
+                 cudaStream_t st, const float* mul = nullptr) {
   const Geom& g = p->g;
   StridedArgs A;
   A.base = fw;
+  A.mul = mul;
   A.coil_stride = g.nftot;
   A.in = in;
   A.out = out;
@@ -519,7 +525,7 @@ bool fftp_supported(const b200_plan* p) {
 
 // K4a + FFT:  image(s) -> oversampled grid, all T coils
 int fftp_type2(b200_plan* p, const float2* img, const float2* smaps, float2* fw, int T, int isign,
-               int conj_smaps, cudaStream_t st) {
+               int conj_smaps, cudaStream_t st, const float* mul) {
   B200_TRY(ensure_twiddles(p));
   const Geom& g = p->g;
   const int dir = isign < 0 ? -1 : 1;
@@ -528,9 +534,9 @@ int fftp_type2(b200_plan* p, const float2* img, const float2* smaps, float2* fw,
   R.img_in = img;
   R.smaps = smaps;
   R.fw = fw;
-  R.d_slow0 = p->d_deapod[0];
-  R.d_slow1 = g.dim == 3 ? p->d_deapod[1] : nullptr;
-  R.d_fast = p->d_deapod[g.dim - 1];
+  R.d_slow0 = p->dvec(0);
+  R.d_slow1 = g.dim == 3 ? p->dvec(1) : nullptr;
+  R.d_fast = p->dvec(g.dim - 1);
   R.T = T;
   R.conj_smaps = conj_smaps;
   const int nrows = g.dim == 3 ? g.N[0] * g.N[1] : g.N[0];
@@ -539,9 +545,9 @@ int fftp_type2(b200_plan* p, const float2* img, const float2* smaps, float2* fw,
   if (g.dim == 3) {
     // y-pass on the N0 non-zero planes, then z-pass everywhere
     B200_TRY(strided_pass(p, fw, T, 1, dir, keep_modes(g.N[1]), keep_all(g.nf[1]), keep_modes(g.N[0]), st));
-    B200_TRY(strided_pass(p, fw, T, 0, dir, keep_modes(g.N[0]), keep_all(g.nf[0]), keep_all(g.nf[1]), st));
+    B200_TRY(strided_pass(p, fw, T, 0, dir, keep_modes(g.N[0]), keep_all(g.nf[0]), keep_all(g.nf[1]), st, mul));
   } else {
-    B200_TRY(strided_pass(p, fw, T, 0, dir, keep_modes(g.N[0]), keep_all(g.nf[0]), Keep{1, 0}, st));
+    B200_TRY(strided_pass(p, fw, T, 0, dir, keep_modes(g.N[0]), keep_all(g.nf[0]), Keep{1, 0}, st, mul));
   }
   return B200_OK;
 }
@@ -563,9 +569,9 @@ int fftp_type1(b200_plan* p, float2* fw, const float2* smaps, float2* img, int T
   R.img_out = img;
   R.smaps = smaps;
   R.fw = fw;
-  R.d_slow0 = p->d_deapod[0];
-  R.d_slow1 = g.dim == 3 ? p->d_deapod[1] : nullptr;
-  R.d_fast = p->d_deapod[g.dim - 1];
+  R.d_slow0 = p->dvec(0);
+  R.d_slow1 = g.dim == 3 ? p->dvec(1) : nullptr;
+  R.d_fast = p->dvec(g.dim - 1);
   R.T = T;
   R.conj_smaps = conj_smaps;
   R.accumulate = accumulate;

@@ -160,11 +160,32 @@ k_r2c(long long M, const float* __restrict__ d, float2* __restrict__ out) {
   out[j] = make_float2(d[j], 0.f);
 }
 
+// fw[t][i] *= kern[i]: the Toeplitz spectrum multiply of the cuFFT path (the fused FFT passes apply
+// it in the store of their last pass instead)
+__global__ void __launch_bounds__(GO_THREADS)
+k_mul_real_kernel(long long n, int T, float2* __restrict__ fw, const float* __restrict__ kern) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float k = kern[i];
+  for (int t = 0; t < T; ++t) {
+    float2 v = fw[(long long)t * n + i];
+    v.x *= k;
+    v.y *= k;
+    fw[(long long)t * n + i] = v;
+  }
+}
+
+int k_mul_real(b200_plan* p, float2* fw, const float* kern, int T, cudaStream_t st) {
+  k_mul_real_kernel<<<ceil_div(p->g.nftot, GO_THREADS), GO_THREADS, 0, st>>>(p->g.nftot, T, fw, kern);
+  CHECK_LAUNCH();
+  return B200_OK;
+}
+
 int k4a_pad(b200_plan* p, const float2* img, const float2* smaps, float2* fw, int T,
             int conj_smaps, cudaStream_t st) {
   const long long npairs = p->g.nftot / 2;
   k_pad<<<ceil_div(npairs, GO_THREADS), GO_THREADS, 0, st>>>(
-      p->g, T, img, smaps, p->d_deapod[0], p->d_deapod[1], p->d_deapod[2], fw, conj_smaps);
+      p->g, T, img, smaps, p->dvec(0), p->dvec(1), p->dvec(2), fw, conj_smaps);
   CHECK_LAUNCH();
   return B200_OK;
 }
@@ -172,8 +193,7 @@ int k4a_pad(b200_plan* p, const float2* img, const float2* smaps, float2* fw, in
 int k4b_crop(b200_plan* p, const float2* fw, const float2* smaps, float2* img, int T,
              int accumulate, float scale, int conj_smaps, cudaStream_t st) {
   k_crop<<<ceil_div(p->g.Ntot, GO_THREADS), GO_THREADS, 0, st>>>(
-      p->g, T, fw, smaps, p->d_deapod[0], p->d_deapod[1], p->d_deapod[2], img, accumulate, scale,
-      conj_smaps);
+      p->g, T, fw, smaps, p->dvec(0), p->dvec(1), p->dvec(2), img, accumulate, scale, conj_smaps);
   CHECK_LAUNCH();
   return B200_OK;
 }

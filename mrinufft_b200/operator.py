@@ -31,6 +31,7 @@ from mrinufft.operators.base import FourierOperatorBase
 
 from . import _lib
 from ._arrays import describe, from_device, module_name, to_device
+from .toeplitz import assemble_toeplitz_kernel, modulated_weights
 
 log = logging.getLogger("mrinufft_b200")
 
@@ -299,6 +300,7 @@ class MRIB200NUFFT(FourierOperatorBase):
 
     @density.setter
     def density(self, new_density):
+        self._toeplitz_kernel = None
         if new_density is None:
             self._density = None
             self._density_d = None
@@ -345,6 +347,7 @@ class MRIB200NUFFT(FourierOperatorBase):
             self.raw_op._set_pts(self._samples)
         if self._density_method is not None:
             self.compute_density(self._density_method)
+        self._toeplitz_kernel = None
 
     # ------------------------------------------------------------------ toggles for the trajectory gradient
     def toggle_grad_traj(self):
@@ -584,6 +587,80 @@ class MRIB200NUFFT(FourierOperatorBase):
 
             return cg(self, kspace_data, **kwargs)
         return super().pinv_solver(kspace_data, optim=optim, **kwargs)
+
+    # ------------------------------------------------------------------ Toeplitz Gram operator
+    def compute_toeplitz_kernel(self, weights=None):
+        """Spectrum of the Toeplitz embedding of ``A^H W A`` on the ``2N`` grid, device resident.
+
+        Same construction as ``compute_toeplitz_kernel`` / ``_compute_toep_2d`` / ``_compute_toep_3d``
+        (src/mrinufft/operators/toeplitz.py:35-200): ``2^(d-1)`` raw adjoints of phase-modulated
+        weights give the outer lags, Hermitian symmetry the rest, and one real inverse FFT the (real)
+        circulant spectrum.  The adjoints run in ``libb200nufft.so``; the assembly is a handful of
+        torch slicing ops at plan time.  Returns (and caches) a float32 CUDA tensor of shape ``2N``.
+        """
+        if self.ndim not in (2, 3):
+            raise ValueError(f"Toeplitz kernel calculation not implemented for ndim={self.ndim}")
+        if any(s % 2 for s in self.shape):
+            raise ValueError(f"Toeplitz kernel computation only supports even grid sizes, got {self.shape}.")
+        if self._spread_only:
+            raise ValueError("Toeplitz kernel needs a full NUFFT plan")
+        dev, M = self.device, self.n_samples
+        if weights is None:
+            w = self._density_d if self._density_d is not None else torch.ones(M, dtype=torch.float32, device=dev)
+        else:
+            w = to_device(weights, dev)
+            w = (w.real if w.is_complex() else w).to(torch.float32).reshape(-1)
+        omega = to_device(self._samples, dev, torch.float32)  # (M, d) radians
+
+        def adj(signs):
+            ksp = modulated_weights(w, omega, signs, self.shape)
+            out = torch.empty((1, *self.shape), dtype=torch.complex64, device=dev)
+            self.raw_op.type1(ksp.reshape(1, M).contiguous(), None, None, out, accumulate=False, scale=1.0)
+            return out[0]
+
+        kern = assemble_toeplitz_kernel(adj, self.shape, 1.0 / float(self.norm_factor))
+        self._toeplitz_kernel = kern.to(torch.float32).contiguous()
+        return self._toeplitz_kernel
+
+    def _gram_device(self, img: torch.Tensor) -> torch.Tensor:
+        """Toeplitz ``A^H A x`` on device tensors: img (B, 1|C, *XYZ) -> same shape."""
+        B, C, XYZ = self.n_batchs, self.n_coils, self.shape
+        if getattr(self, "_toeplitz_kernel", None) is None or not torch.is_tensor(self._toeplitz_kernel):
+            self.compute_toeplitz_kernel()
+        kern = self._toeplitz_kernel
+        scale = 1.0 / float(np.prod([2 * s for s in XYZ]))
+        plan = self.raw_op.plan
+        if self.uses_sense:
+            img = img.reshape(B, *XYZ)
+            out = torch.empty((B, 1, *XYZ), dtype=torch.complex64, device=self.device)
+            for b in range(B):
+                for i, (c0, c1) in enumerate(self._chunks()):
+                    plan.toeplitz_apply(img[b].data_ptr(), self._smaps_d[c0:c1].data_ptr(), kern.data_ptr(),
+                                        out[b, 0].data_ptr(), c1 - c0, int(i > 0), scale, self.stream)
+        else:
+            img = img.reshape(B, C, *XYZ)
+            out = torch.empty((B, C, *XYZ), dtype=torch.complex64, device=self.device)
+            for b in range(B):
+                for c0, c1 in self._chunks():
+                    plan.toeplitz_apply(img[b, c0:c1].data_ptr(), 0, kern.data_ptr(),
+                                        out[b, c0:c1].data_ptr(), c1 - c0, 0, scale, self.stream)
+        return out
+
+    def gram_op(self, data, toeplitz=True):
+        """Gram operator ``A^H A`` (base.py:316-342).  ``toeplitz=True`` applies the Toeplitz embedding
+        with two zero-padding-aware FFTs per coil on the device (no spreading / interpolation)."""
+        self.check_shape(image=data)
+        if not toeplitz:
+            return self.adj_op(self.op(data))
+        if tuple(self.raw_op.plan.nf) != tuple(2 * s for s in self.shape) or self.ndim not in (2, 3):
+            # oversampled grid is not exactly 2N: reference construction on top of op / adj_op
+            from mrinufft.operators.toeplitz import compute_toeplitz_kernel as _ref_kernel
+
+            if not isinstance(getattr(self, "_toeplitz_kernel", None), np.ndarray):
+                self._toeplitz_kernel = _ref_kernel(self, self.density)
+            return super().gram_op(data, toeplitz=True)
+        img, kind, dev = self._in(data)
+        return self._out(self._safe_squeeze(self._gram_device(img)), kind, dev)
 
     # ------------------------------------------------------------------ autodiff
     def make_autograd(self, *, wrt_data=True, wrt_traj=False, paired_batch=False):

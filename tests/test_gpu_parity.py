@@ -580,3 +580,42 @@ def test_pruned_fft_matches_cufft_path_and_oracle(mods, shape, C, sense):
         x_o = cpu.adj_op(ksp[0], smaps)
         assert rel_l2(res[2][0][0], y_o) <= 2e-6
         assert rel_l2(res[2][1][0, 0] if sense else res[2][1][0], x_o) <= 2e-6
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape,C,sense,dens", [((64, 32), 3, True, True), ((48, 40), 2, False, False),
+                                                ((32, 16, 32), 3, True, False), ((24, 20, 16), 1, False, True),
+                                                ((22, 26), 2, True, False)])
+def test_toeplitz_gram_matches_adj_op_of_op(mods, shape, C, sense, dens):
+    """Reference: tests/operators/test_batch.py:275-293 (Toeplitz gram_op vs adj_op(op), rtol 2e-4).
+    Pruned-FFT path (2^k grids), cuFFT path (other 2N grids) and the reference construction
+    (oversampled grid != 2N)."""
+    mrinufft, _, _ = mods
+    rng = np.random.default_rng(7)
+    M = 4000
+    samples = rng.uniform(-np.pi, np.pi, (M, len(shape))).astype(np.float32)
+    smaps = None
+    if sense:
+        smaps = (rng.standard_normal((C, *shape)) + 1j * rng.standard_normal((C, *shape))).astype(np.complex64)
+        smaps /= np.linalg.norm(smaps, axis=0)
+    density = rng.uniform(0.5, 1.5, M).astype(np.float32) if dens else False
+    op = mrinufft.get_operator("b200")(samples, shape, n_coils=C, smaps=smaps, density=density,
+                                       squeeze_dims=False)
+    img_shape = (1, 1, *shape) if sense else (1, C, *shape)
+    x = (rng.standard_normal(img_shape) + 1j * rng.standard_normal(img_shape)).astype(np.complex64)
+    direct = op.adj_op(op.op(x))
+    gram = op.gram_op(x, toeplitz=True)
+    assert gram.shape == direct.shape
+    err = np.linalg.norm(gram - direct) / np.linalg.norm(direct)
+    assert err <= 2e-5, err  # tolerance: relative L2; the reference uses rtol 2e-4 element-wise
+    # the kernel is cached and re-used; a torch input gives a torch output
+    import torch
+
+    xt = torch.from_numpy(x).cuda()
+    gt = op.gram_op(xt)
+    assert gt.is_cuda and np.allclose(gt.cpu().numpy(), gram, rtol=1e-5, atol=1e-6)
+    # changing the density invalidates the cached kernel
+    op.density = None
+    g2 = op.gram_op(x)
+    d2 = op.adj_op(op.op(x))
+    assert np.linalg.norm(g2 - d2) / np.linalg.norm(d2) <= 2e-5
