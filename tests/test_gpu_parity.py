@@ -619,3 +619,26 @@ def test_toeplitz_gram_matches_adj_op_of_op(mods, shape, C, sense, dens):
     g2 = op.gram_op(x)
     d2 = op.adj_op(op.op(x))
     assert np.linalg.norm(g2 - d2) / np.linalg.norm(d2) <= 2e-5
+
+
+@pytest.mark.gpu
+def test_stacked_b200_matches_full_3d(mods):
+    """`get_operator("stacked-b200")` (generic fallback of base.py:151-158: 2-D b200 NUFFT per plane +
+    FFT along z, src/mrinufft/operators/stacked.py:36-357) against the full 3-D b200 operator on a
+    stack-of-spirals trajectory (reference: tests/operators/test_stacked.py)."""
+    mrinufft, _, _ = mods
+    from mrinufft.operators.stacked import stacked2traj3d
+
+    rng = np.random.default_rng(5)
+    shape, M2 = (32, 32, 16), 600
+    traj2d = rng.uniform(-0.5, 0.5, (M2, 2)).astype(np.float32)
+    z_index = np.arange(shape[-1])
+    op_st = mrinufft.get_operator("stacked-b200")(traj2d, shape, smaps=None, z_index=z_index, n_coils=2, squeeze_dims=False)
+    traj3d = stacked2traj3d(traj2d, z_index, shape[-1]).astype(np.float32)
+    op_3d = mrinufft.get_operator("b200")(traj3d, shape, n_coils=2, squeeze_dims=False)
+    img = (rng.standard_normal((1, 2, *shape)) + 1j * rng.standard_normal((1, 2, *shape))).astype(np.complex64)
+    y_st = np.asarray(op_st.op(img)).reshape(1, 2, -1)
+    y_3d = np.asarray(op_3d.op(img)).reshape(1, 2, -1)
+    # the two operators use different normalisations of the z transform: compare up to one scalar
+    s = np.vdot(y_st, y_3d) / np.vdot(y_st, y_st)
+    assert np.linalg.norm(s * y_st - y_3d) <= 1e-4 * np.linalg.norm(y_3d)
