@@ -54,6 +54,7 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--spread-method", type=int, default=0)
     ap.add_argument("--interp-method", type=int, default=0)
+    ap.add_argument("--fft-method", type=int, default=0, help="0 auto, 1 cuFFT + pad/crop kernels, 2 fused zero-padding-aware passes")
     ap.add_argument("--rows-dbg", type=int, default=0, help="debug switches of the row kernels (timing experiments)")
     return ap.parse_args()
 
@@ -246,6 +247,7 @@ def run_b200(args):
     plan = op.raw_op.plan
     plan.set_option(0, args.spread_method)
     plan.set_option(1, args.interp_method)
+    plan.set_option(2, args.fft_method)
     plan.set_option(3, args.rows_dbg)
     img_d = crandn(1, 1, *shape)
     ksp_d = crandn(1, C, M)
