@@ -662,6 +662,15 @@ class MRIB200NUFFT(FourierOperatorBase):
         img, kind, dev = self._in(data)
         return self._out(self._safe_squeeze(self._gram_device(img)), kind, dev)
 
+    # ------------------------------------------------------------------ off-resonance correction
+    def with_off_resonance_correction(self, readout_time, b0_map=None, r2star_map=None, mask=None,
+                                      interpolator="svd"):
+        """Operator with off-resonance correction (base.py:385-398); the L interpolators ride the coil
+        batch of the device transforms (``mrinufft_b200.off_resonance``)."""
+        from .off_resonance import MRIB200FourierCorrected
+
+        return MRIB200FourierCorrected(self, b0_map, readout_time, r2star_map, mask, interpolator)
+
     # ------------------------------------------------------------------ autodiff
     def make_autograd(self, *, wrt_data=True, wrt_traj=False, paired_batch=False):
         """Torch autograd wrapper (role of base.py:536-574).  The reference module hard-imports
