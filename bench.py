@@ -324,6 +324,26 @@ def run_b200(args):
     except Exception as exc:  # noqa: BLE001
         extras["toeplitz_gram_error"] = str(exc)[:200]
 
+    # secondary: cost of new sample locations (fold + sort + visit-stream rebuild), i.e. what
+    # `update_samples` adds to the first transform after it (trajectory-learning loops pay it per step)
+    try:
+        pts_d = op.raw_op._pts
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            op.raw_op._set_pts(pts_d)
+            op._op_device(img_d)
+        torch.cuda.synchronize()
+        t_with = (time.perf_counter() - t0) / 3
+        t0 = time.perf_counter()
+        for _ in range(3):
+            op._op_device(img_d)
+        torch.cuda.synchronize()
+        t_without = (time.perf_counter() - t0) / 3
+        extras["setpts_and_stream_rebuild_ms"] = (t_with - t_without) * 1e3
+    except Exception as exc:  # noqa: BLE001
+        extras["setpts_error"] = str(exc)[:200]
+
     # end-to-end through the public API with HOST buffers (pinned), copies inside the timed region
     e2e = None
     if not args.no_e2e:

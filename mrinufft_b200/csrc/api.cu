@@ -17,6 +17,7 @@ int interp_tiled(b200_plan* p, const float2* fw, float2* ksp, int T, float scale
                  const float2* obs, cudaStream_t st);
 bool tiled_supported(const b200_plan* p, int T);
 void tiled_free(b200_plan* p);
+void tiled_invalidate(b200_plan* p);
 
 namespace {
 
@@ -437,7 +438,7 @@ int b200_plan_setpts(b200_plan* p, int64_t M, const float* xyz, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   p->M = M;
   p->pts_set = false;
-  tiled_free(p);
+  tiled_invalidate(p);
   B200_TRY(k1_setpts(p, xyz, st));
   p->pts_set = true;
   return B200_OK;

@@ -97,6 +97,7 @@ struct RowsState {
   int* d_counters = nullptr;     // [0] work counter, [1] split-row counter, [2..3] total visits (u64)
   void* d_scan_tmp = nullptr;
   size_t scan_tmp_bytes = 0;
+  size_t ent_cap = 0, chunk_cap = 0, pts_cap = 0;  // capacities (entries, chunks, points): grow-only
   long long nrows = 0, nsplit = 0, nvis = 0;
   unsigned S = 0;                // stream length in entries
   int nchunks = 0;
@@ -637,7 +638,9 @@ k_rows(Geom g, int T, int nchunks, unsigned S, long long M, const uint4* __restr
               if (T == 32 || half * 16 + tl < T) {
                 const u64 val = pack2(tre[tl * TFS + cl], tim[tl * TFS + cl]);
                 u64* a = dst + (long long)(2 * i) * g.nftot;
-                if (MODE == 0) *a = val;
+                // streaming stores: the grid is written once and not read again by this kernel --
+                // keep L2 for the point data (coil rows, x weights) that neighbouring tiles re-read
+                if (MODE == 0) __stcs(a, val);
                 else red_add_f32x2(reinterpret_cast<float2*>(a), val, 1);
               }
             }
@@ -650,7 +653,7 @@ k_rows(Geom g, int T, int nchunks, unsigned S, long long M, const uint4* __restr
       if (cl < xlim) {
 #pragma unroll
         for (int r = 0; r < 2; ++r)
-          for (int t = hl; t < T; t += 2) fbase[(long long)r * nfx + (long long)(t - hl) * g.nftot] = 0ull;
+          for (int t = hl; t < T; t += 2) __stcs(fbase + (long long)r * nfx + (long long)(t - hl) * g.nftot, 0ull);
       }
     };
     // grid rows -> registers
@@ -860,21 +863,33 @@ int build_stream(b200_plan* p, RowsState* ts, cudaStream_t st) {
   CUDA_TRY(cudaMemcpyAsync(&S, ts->d_start + nrows, 4, cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaStreamSynchronize(st));
   const int nchunks = (int)((S + LCH - 1) / LCH);
-  fr(ts->d_ent);
-  fr(ts->d_chunk_row);
-  fr(ts->d_split_rows);
-  ts->d_ent = nullptr;
-  ts->d_chunk_row = nullptr;
-  ts->d_split_rows = nullptr;
-  // + 64 entries of all-ones padding: the kernel looks one entry past the last chunk
-  if (cudaMalloc(&ts->d_ent, ((size_t)S + 64) * 16) != cudaSuccess) {
-    cudaGetLastError();
+  // + 64 entries of all-ones padding: the kernel looks one entry past the last chunk.
+  // Buffers only ever grow: update_samples in a trajectory-learning loop must not pay cudaFree's
+  // device synchronisation and a multi-GB cudaMalloc per step.
+  if ((size_t)S + 64 > ts->ent_cap) {
+    fr(ts->d_ent);
     ts->d_ent = nullptr;
-    ts->unsupported = true;
-    return B200_OK;
+    ts->ent_cap = 0;
+    const size_t cap = (size_t)S + 64 + (size_t)S / 16;
+    if (cudaMalloc(&ts->d_ent, cap * 16) != cudaSuccess) {
+      cudaGetLastError();
+      ts->d_ent = nullptr;
+      ts->unsupported = true;
+      return B200_OK;
+    }
+    ts->ent_cap = cap;
   }
-  CUDA_TRY(cudaMalloc(&ts->d_chunk_row, (size_t)(nchunks + 1) * 4));
-  CUDA_TRY(cudaMalloc(&ts->d_split_rows, (size_t)(nchunks + 1) * 4));
+  if ((size_t)nchunks + 1 > ts->chunk_cap) {
+    fr(ts->d_chunk_row);
+    fr(ts->d_split_rows);
+    ts->d_chunk_row = nullptr;
+    ts->d_split_rows = nullptr;
+    ts->chunk_cap = 0;
+    const size_t cap = (size_t)nchunks + 1 + (size_t)nchunks / 16;
+    CUDA_TRY(cudaMalloc(&ts->d_chunk_row, cap * 4));
+    CUDA_TRY(cudaMalloc(&ts->d_split_rows, cap * 4));
+    ts->chunk_cap = cap;
+  }
   CUDA_TRY(cudaMemsetAsync(ts->d_ent, 0xff, ((size_t)S + 64) * 16, st));
   CUDA_TRY(cudaMemsetAsync(ts->d_chunk_row, 0, (size_t)(nchunks + 1) * 4, st));
   k_build_stream<DIM, W><<<ceil_div(nrows * 32, 256), 256, 0, st>>>(
@@ -895,15 +910,21 @@ template <int DIM, int W>
 int prepare(b200_plan* p, RowsState* ts, cudaStream_t st) {
   const long long M = p->M;
   if (!ts->d_counters) CUDA_TRY(cudaMalloc(&ts->d_counters, 64));
+  if ((size_t)M > ts->pts_cap || !ts->d_iperm) {
+    if (ts->d_iperm) cudaFree(ts->d_iperm);
+    if (ts->d_ptab) cudaFree(ts->d_ptab);
+    ts->d_iperm = nullptr;
+    ts->d_ptab = nullptr;
+    ts->pts_cap = 0;
+    const size_t cap = (size_t)(M > 0 ? M : 1);
+    CUDA_TRY(cudaMalloc(&ts->d_ptab, cap * 8 * sizeof(float)));
+    CUDA_TRY(cudaMalloc(&ts->d_iperm, cap * 4));
+    ts->pts_cap = cap;
+  }
+  // the records (112 B per point) only feed the stream builder: freed again below
   if (ts->d_rec) cudaFree(ts->d_rec);
-  if (ts->d_iperm) cudaFree(ts->d_iperm);
-  if (ts->d_ptab) cudaFree(ts->d_ptab);
   ts->d_rec = nullptr;
-  ts->d_iperm = nullptr;
-  ts->d_ptab = nullptr;
-  CUDA_TRY(cudaMalloc(&ts->d_ptab, (size_t)(M > 0 ? M : 1) * 8 * sizeof(float)));
   CUDA_TRY(cudaMalloc(&ts->d_rec, (size_t)(M > 0 ? M : 1) * REC * sizeof(float)));
-  CUDA_TRY(cudaMalloc(&ts->d_iperm, (size_t)(M > 0 ? M : 1) * 4));
   if (M > 0) {
     k_point_records<W><<<ceil_div(M, 256), 256, 0, st>>>(
         p->g, M, p->d_poly, p->d_org_s[0], p->d_org_s[1], p->d_org_s[2], p->d_x1_s[0],
@@ -984,6 +1005,11 @@ bool tiled_supported(const b200_plan* p, int T) {
   for (int a = 0; a < g.dim; ++a)
     if (g.nf[a] < 2 * g.w) return false;
   return true;
+}
+
+// new sample locations: keep the (grow-only) buffers, rebuild their contents on the next execute
+void tiled_invalidate(b200_plan* p) {
+  if (p->tiled) ((RowsState*)p->tiled)->valid = false;
 }
 
 void tiled_free(b200_plan* p) {
