@@ -30,6 +30,7 @@ except ModuleNotFoundError:  # pragma: no cover
 
 from . import _lib  # noqa: E402
 from .operator import MRIB200NUFFT, RawB200Plan  # noqa: E402
+from .stacked import MRIB200StackedNUFFT  # noqa: E402
 
-__all__ = ["MRIB200NUFFT", "RawB200Plan", "_lib"]
+__all__ = ["MRIB200NUFFT", "MRIB200StackedNUFFT", "RawB200Plan", "_lib"]
 __version__ = "0.1.0"

@@ -690,3 +690,38 @@ def test_off_resonance_batched_matches_reference_wrapper(mods, shape, C, sense):
     xt = torch.from_numpy(x).cuda()
     yt = orc.op(xt)
     assert yt.is_cuda and np.allclose(yt.cpu().numpy(), ax, rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("sense", [False, True])
+def test_native_stacked_matches_generic_stacked(mods, sense):
+    """`MRIB200StackedNUFFT` (device resident) against the reference's generic `MRIStackedNUFFT` driving the
+    same 2-D b200 operator through host arrays (stacked.py:36-357): op, adj_op, adjointness, partial
+    z_index, numpy and torch inputs."""
+    mrinufft, mb, torch = mods
+    from mrinufft.operators.stacked import MRIStackedNUFFT
+
+    rng = np.random.default_rng(9)
+    shape, M2, C = (32, 24, 12), 500, 3
+    traj2d = rng.uniform(-0.5, 0.5, (M2, 2)).astype(np.float32)
+    z_index = np.array([0, 2, 3, 6, 7, 8, 11])
+    smaps = None
+    if sense:
+        smaps = (rng.standard_normal((C, *shape)) + 1j * rng.standard_normal((C, *shape))).astype(np.complex64)
+        smaps /= np.linalg.norm(smaps, axis=0)
+    nat = mrinufft.get_operator("stacked-b200")(traj2d, shape, smaps=smaps, z_index=z_index, n_coils=C)
+    assert isinstance(nat, mb.MRIB200StackedNUFFT)
+    gen = MRIStackedNUFFT(traj2d, shape, "b200", smaps, z_index=z_index, n_coils=C)
+    img_shape = (1, 1 if sense else C, *shape)
+    x = (rng.standard_normal(img_shape) + 1j * rng.standard_normal(img_shape)).astype(np.complex64)
+    y = (rng.standard_normal((1, C, len(z_index) * M2)) + 1j * rng.standard_normal((1, C, len(z_index) * M2)))
+    y = y.astype(np.complex64)
+    ax, ahy = nat.op(x), nat.adj_op(y)
+    assert isinstance(ax, np.ndarray) and ax.shape == (1, C, len(z_index) * M2) and ahy.shape == img_shape
+    assert rel_l2(ax, gen.op(x)) <= 2e-6 and rel_l2(ahy, gen.adj_op(y)) <= 2e-6
+    lhs, rhs = np.vdot(ax.ravel(), y.ravel()), np.vdot(x.ravel(), ahy.ravel())
+    assert abs(lhs - rhs) <= 5e-5 * abs(lhs)
+    xt = torch.from_numpy(x).cuda()
+    assert nat.op(xt).is_cuda and rel_l2(nat.op(xt).cpu().numpy(), ax) <= 1e-6
+    dc = nat.data_consistency(x, y)
+    assert rel_l2(dc, nat.adj_op(nat.op(x) - y)) <= 1e-5
