@@ -78,28 +78,30 @@ def taps_interp(W, X):
     for c in range(ncase):
         jb = c - jb0
         L.append(f"C{X}{c}:")
-        for r in range(2):
-            for ri in range(2):
-                o = r * 2 + ri
-                first = True
-                for q in range(NP):
-                    j = jb + q
-                    if j < 0 or j >= NJ:
-                        continue
+        # the four partial sums are independent chains: interleave them so that no instruction
+        # waits on the one issued just before it
+        first = [True] * 4
+        for q in range(NP):
+            j = jb + q
+            if j < 0 or j >= NJ:
+                continue
+            for r in range(2):
+                for ri in range(2):
+                    o = r * 2 + ri
                     a = r * 16 + ri * 8 + j
-                    if first:
+                    if first[o]:
                         L.append(f"mul.rn.f32x2 S{o}, %{a}, P{X}{q};")
-                        first = False
+                        first[o] = False
                     else:
                         L.append(f"fma.rn.f32x2 S{o}, %{a}, P{X}{q}, S{o};")
         L.append(f"bra.uni J{X};")
+    # row scales applied on the packed pairs, then one horizontal add per component
     L += [f"J{X}:",
+          f"mov.b64 A0, {{s{X}0, s{X}0}};", f"mov.b64 A1, {{s{X}1, s{X}1}};",
+          "mul.rn.f32x2 S0, S0, A0;", "mul.rn.f32x2 S1, S1, A0;",
+          "fma.rn.f32x2 S0, S2, A1, S0;", "fma.rn.f32x2 S1, S3, A1, S1;",
           "mov.b64 {lo, hi}, S0;", "add.f32 t0, lo, hi;",
           "mov.b64 {lo, hi}, S1;", "add.f32 t1, lo, hi;",
-          "mov.b64 {lo, hi}, S2;", "add.f32 t2, lo, hi;",
-          "mov.b64 {lo, hi}, S3;", "add.f32 t3, lo, hi;",
-          f"mul.f32 t0, t0, s{X}0;", f"fma.rn.f32 t0, t2, s{X}1, t0;",
-          f"mul.f32 t1, t1, s{X}0;", f"fma.rn.f32 t1, t3, s{X}1, t1;",
           f"mad.wide.u32 addr, n{X}, 256, ktl;",
           "red.global.add.v2.f32 [addr], {t0, t1};"]
     return L
