@@ -194,7 +194,9 @@ int b200_launch_count(int64_t* kernels, int64_t* ffts, int reset);
  *   key 1: interp method   (0 auto, 1 point driven, 2 tiled)
  *   key 2: FFT method      (0 auto, 1 cuFFT + pad/crop kernels, 2 fused zero-padding-aware passes)
  *   key 3: timing experiments on the tiled spreader (bit 0: skip the tile flush, bit 1: skip the
- *          coil-value copies; results are then wrong -- never set outside a profiling session)
+ *          coil-value copies; results are then wrong -- never set outside a profiling session;
+ *          bit 3: pretend the visit stream does not fit 32-bit indices, which exercises the
+ *          hand-over to the point-driven kernels -- set before b200_plan_setpts)
  */
 int b200_plan_set_option(b200_plan* plan, int key, int64_t value);
 

@@ -823,7 +823,7 @@ int build_stream(b200_plan* p, RowsState* ts, cudaStream_t st) {
     if (q) cudaFree(q);
   };
   ts->unsupported = false;
-  if (nrows >= (1LL << 30) || p->M >= (1LL << 31) - 2) {
+  if (nrows >= (1LL << 30) || p->M >= (1LL << 31) - 2 || (p->rows_dbg & 8)) {  // bit 3: test hook
     ts->unsupported = true;
     return B200_OK;
   }

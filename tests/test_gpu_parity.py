@@ -725,3 +725,18 @@ def test_native_stacked_matches_generic_stacked(mods, sense):
     assert nat.op(xt).is_cuda and rel_l2(nat.op(xt).cpu().numpy(), ax) <= 1e-6
     dc = nat.data_consistency(x, y)
     assert rel_l2(dc, nat.adj_op(nat.op(x) - y)) <= 1e-5
+
+
+@pytest.mark.gpu
+def test_rows_fallback_when_stream_does_not_fit(mods):
+    """When the visit stream would overflow its 32-bit indices the tiled kernels hand over to the
+    point-driven ones (spread_rows.cu `unsupported`); forced here through option key 3, bit 3."""
+    mrinufft, _, _ = mods
+    g = load_golden("random3D_sense")
+    op = make_op(mrinufft, g)
+    ref_y, ref_x = op.op(g["img"]), op.adj_op(g["ksp"])
+    op2 = make_op(mrinufft, g)
+    op2.raw_op.plan.set_option(3, 8)
+    op2.raw_op._set_pts(op2.samples)
+    assert rel_l2(op2.op(g["img"]), ref_y) <= 2e-6 and rel_l2(op2.adj_op(g["ksp"]), ref_x) <= 2e-6
+    assert rel_l2(op2.op(g["img"]), g["op"]) <= 5e-6
