@@ -358,6 +358,48 @@ k_build_stream(Geom g, long long nrows, const int32_t* __restrict__ bin_start,
   }
   const int tot0 = __shfl_sync(0xffffffffu, inc0, 31);
   const int pre[2] = {inc0 - l[0], tot0 + inc1 - l[1]};
+  // Tiles made of short ranges only (all but the dense k-space centre): the visits are grouped by
+  // their tap-kernel case `idx` with a counting sort, so that the consume loop runs through
+  // straight-line code for whole runs of visits (tools/gen_taps.py).  Deterministic: inside a case
+  // the order is (lane, slot, position).
+  constexpr int NC = 8 + W / 2;  // number of cases
+  __shared__ int s_cnt[8][NC][32];
+  const int wib = threadIdx.x >> 5;
+  const bool any_long = __any_sync(0xffffffffu, l[0] > 64 || l[1] > 64);
+  if (!any_long) {
+#pragma unroll
+    for (int c = 0; c < NC; ++c) s_cnt[wib][c][lane] = 0;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int slot = lane + 32 * h;
+      const int dz = (slot >> 1) / 3, left = ((slot >> 1) % 3) == 2 ? 1 : 0;
+      for (int i = 0; i < l[h]; ++i) s_cnt[wib][entry(b[h] + i, dz, left).z][lane] += 1;
+    }
+    // offsets: case-major, lane-minor exclusive prefix
+    int base = 0;
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      const int mine = s_cnt[wib][c][lane];
+      int inc = mine;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const int u = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d) inc += u;
+      }
+      s_cnt[wib][c][lane] = base + inc - mine;
+      base += __shfl_sync(0xffffffffu, inc, 31);
+    }
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int slot = lane + 32 * h;
+      const int dz = (slot >> 1) / 3, left = ((slot >> 1) % 3) == 2 ? 1 : 0;
+      for (int i = 0; i < l[h]; ++i) {
+        const uint4 e = entry(b[h] + i, dz, left);
+        out[s_cnt[wib][e.z][lane]++] = e;
+      }
+    }
+    return;
+  }
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
     const int slot = lane + 32 * h;

@@ -23,7 +23,7 @@ spread:  acc[r][c][j] += P_q * (a, a),  a = (re | im of this lane's coil value) 
 interp:  kt[s][lane] += sum_r s_r * sum_{q, lanes of the pair} acc[r][c][j] * P_q   (red.global.add.v2.f32)
 
 The loop is software-pipelined by hand over two register sets (A, B): the packet (and value) of
-visit k + 1 is loaded before the taps of visit k execute.
+visit k + 1 is loaded before the taps of visit k execute.  See `gen_loop` for the run structure.
 """
 import sys
 
@@ -36,68 +36,63 @@ def cases(W):
 
 
 def load_set(X, off_pk, off_vb, pred, spread):
+    """Load visit packet (+ coil value) into register set X; under `pred` (no further visit) only mark it."""
+    L = []
+    if pred:
+        L.append(f"@{pred} mov.u32 i{X}, 0xffffffff;")
     p = f"@!{pred} " if pred else ""
-    L = [f"{p}ld.shared.v2.b64 {{P{X}0, P{X}1}}, [pk+{off_pk}];",
-         f"{p}ld.shared.v2.b64 {{P{X}2, P{X}3}}, [pk+{off_pk + 16}];",
-         f"{p}ld.shared.v4.b32 {{s{X}0, s{X}1, i{X}, n{X}}}, [pk+{off_pk + 32}];"]
+    L += [f"{p}ld.shared.v2.b64 {{P{X}0, P{X}1}}, [pk+{off_pk}];",
+          f"{p}ld.shared.v2.b64 {{P{X}2, P{X}3}}, [pk+{off_pk + 16}];",
+          f"{p}ld.shared.v4.b32 {{s{X}0, s{X}1, i{X}, n{X}}}, [pk+{off_pk + 32}];"]
     if spread:
         L.append(f"{p}ld.shared.b64 v{X}, [vb+{off_vb}];")
     return L
 
 
-def taps_spread(W, X):
-    jb0, ncase = cases(W)
+def taps_spread(W, X, c):
+    """acc += P (x) A for tap-kernel case c, visit in register set X (straight-line code)."""
+    jb0, _ = cases(W)
     NP = W // 2 + 1
+    jb = c - jb0
     L = [f"mov.b64 {{vx, vy}}, v{X};",
          f"mul.f32 t0, vx, s{X}0;", f"mul.f32 t1, vy, s{X}0;",
          f"mul.f32 t2, vx, s{X}1;", f"mul.f32 t3, vy, s{X}1;",
-         "mov.b64 A0, {t0, t0};", "mov.b64 A1, {t1, t1};", "mov.b64 A2, {t2, t2};", "mov.b64 A3, {t3, t3};",
-         f"tbl{X}: .branchtargets " + ", ".join(f"C{X}{i}" for i in range(ncase)) + ";",
-         f"brx.idx.uni i{X}, tbl{X};"]
-    for c in range(ncase):
-        jb = c - jb0
-        L.append(f"C{X}{c}:")
-        for q in range(NP):
-            j = jb + q
-            if j < 0 or j >= NJ:
-                continue
-            for r in range(2):
-                for ri in range(2):
-                    a = r * 16 + ri * 8 + j
-                    L.append(f"fma.rn.f32x2 %{a}, P{X}{q}, A{r * 2 + ri}, %{a};")
-        L.append(f"bra.uni J{X};")
-    L.append(f"J{X}:")
+         "mov.b64 A0, {t0, t0};", "mov.b64 A1, {t1, t1};", "mov.b64 A2, {t2, t2};", "mov.b64 A3, {t3, t3};"]
+    for q in range(NP):
+        j = jb + q
+        if j < 0 or j >= NJ:
+            continue
+        for r in range(2):
+            for ri in range(2):
+                a = r * 16 + ri * 8 + j
+                L.append(f"fma.rn.f32x2 %{a}, P{X}{q}, A{r * 2 + ri}, %{a};")
     return L
 
 
-def taps_interp(W, X):
-    jb0, ncase = cases(W)
+def taps_interp(W, X, c):
+    """kt[s] += sum of the taps of case c read from the tile registers, visit in register set X."""
+    jb0, _ = cases(W)
     NP = W // 2 + 1
-    L = [f"tbl{X}: .branchtargets " + ", ".join(f"C{X}{i}" for i in range(ncase)) + ";",
-         f"brx.idx.uni i{X}, tbl{X};"]
-    for c in range(ncase):
-        jb = c - jb0
-        L.append(f"C{X}{c}:")
-        # the four partial sums are independent chains: interleave them so that no instruction
-        # waits on the one issued just before it
-        first = [True] * 4
-        for q in range(NP):
-            j = jb + q
-            if j < 0 or j >= NJ:
-                continue
-            for r in range(2):
-                for ri in range(2):
-                    o = r * 2 + ri
-                    a = r * 16 + ri * 8 + j
-                    if first[o]:
-                        L.append(f"mul.rn.f32x2 S{o}, %{a}, P{X}{q};")
-                        first[o] = False
-                    else:
-                        L.append(f"fma.rn.f32x2 S{o}, %{a}, P{X}{q}, S{o};")
-        L.append(f"bra.uni J{X};")
+    jb = c - jb0
+    L = []
+    # the four partial sums are independent chains: interleave them so that no instruction waits
+    # on the one issued just before it
+    first = [True] * 4
+    for q in range(NP):
+        j = jb + q
+        if j < 0 or j >= NJ:
+            continue
+        for r in range(2):
+            for ri in range(2):
+                o = r * 2 + ri
+                a = r * 16 + ri * 8 + j
+                if first[o]:
+                    L.append(f"mul.rn.f32x2 S{o}, %{a}, P{X}{q};")
+                    first[o] = False
+                else:
+                    L.append(f"fma.rn.f32x2 S{o}, %{a}, P{X}{q}, S{o};")
     # row scales applied on the packed pairs, then one horizontal add per component
-    L += [f"J{X}:",
-          f"mov.b64 A0, {{s{X}0, s{X}0}};", f"mov.b64 A1, {{s{X}1, s{X}1}};",
+    L += [f"mov.b64 A0, {{s{X}0, s{X}0}};", f"mov.b64 A1, {{s{X}1, s{X}1}};",
           "mul.rn.f32x2 S0, S0, A0;", "mul.rn.f32x2 S1, S1, A0;",
           "fma.rn.f32x2 S0, S2, A1, S0;", "fma.rn.f32x2 S1, S3, A1, S1;",
           "mov.b64 {lo, hi}, S0;", "add.f32 t0, lo, hi;",
@@ -108,25 +103,43 @@ def taps_interp(W, X):
 
 
 def gen_loop(W, spread):
+    """One asm block that consumes a run of `n` staged visits.
+
+    The stream builder groups the visits of a tile by tap-kernel case, so consecutive visits mostly
+    share their case: after one indexed branch (`brx.idx`) the visits of a run execute a two-visit
+    loop of straight-line code -- one taken branch per two visits -- and only a change of case goes
+    back through the dispatcher.  Two register sets (A, B) alternate: the packet of the next visit
+    is loaded before the taps of the current one execute.
+    """
     name = f"rows_loop_{'spread' if spread else 'interp'}_w{W}"
     taps = taps_spread if spread else taps_interp
+    _, ncase = cases(W)
+    step = ["add.u32 pk, pk, 48;"] + (["add.u32 vb, vb, 256;"] if spread else []) + ["add.s32 n, n, -1;"]
+    step2 = ["add.u32 pk, pk, 96;"] + (["add.u32 vb, vb, 512;"] if spread else []) + ["add.s32 n, n, -2;"]
     body = ["{",
             ".reg .b64 PA<4>, PB<4>, vA, vB, A<4>, S<4>, addr, ktl;",
             ".reg .b32 sA<2>, sB<2>, iA, iB, nA, nB, vx, vy, lo, hi, t<4>, pk, vb, n;",
-            ".reg .pred p1, p2, p3;",
+            ".reg .pred p1, p2, p3, p4, p5;",
             "mov.u32 pk, %32;", "mov.u32 n, %33;"]
     body.append("mov.u32 vb, %34;" if spread else "mov.u64 ktl, %34;")
     body += load_set("A", 0, 0, None, spread)
-    body += ["LOOP:", "setp.lt.s32 p1, n, 2;"]
-    body += load_set("B", 48, 256, "p1", spread)
-    body += taps(W, "A")
-    body += ["@p1 bra.uni DONE;", "setp.lt.s32 p2, n, 3;"]
-    body += load_set("A", 96, 512, "p2", spread)
-    body += taps(W, "B")
-    body += ["add.u32 pk, pk, 96;"]
-    if spread:
-        body.append("add.u32 vb, vb, 512;")
-    body += ["add.s32 n, n, -2;", "setp.gt.s32 p3, n, 0;", "@p3 bra.uni LOOP;", "DONE:", "}"]
+    for X, Y in (("A", "B"), ("B", "A")):
+        body += [f"D{X}:", "setp.lt.s32 p5, n, 1;", "@p5 bra.uni DONE;",
+                 f"tbl{X}: .branchtargets " + ", ".join(f"R{X}{i}" for i in range(ncase)) + ";",
+                 f"brx.idx.uni i{X}, tbl{X};"]
+        for c in range(ncase):
+            body += [f"R{X}{c}:", "setp.lt.s32 p1, n, 2;"]
+            body += load_set(Y, 48, 256, "p1", spread)
+            body += taps(W, X, c)
+            body += [f"setp.ne.u32 p2, i{Y}, {c};", f"@p2 bra.uni X{X}{c};", "setp.lt.s32 p3, n, 3;"]
+            body += load_set(X, 96, 512, "p3", spread)
+            body += taps(W, Y, c)
+            body += step2
+            body += [f"setp.eq.u32 p4, i{X}, {c};", f"@p4 bra.uni R{X}{c};", f"bra.uni D{X};",
+                     f"X{X}{c}:"]
+            body += step
+            body += [f"bra.uni D{Y};"]
+    body += ["DONE:", "}"]
     L = [f"__device__ __forceinline__ void {name}(",
          "    unsigned long long (&acc)[32], unsigned pk, int n, "
          + ("unsigned vb) {" if spread else "const void* ktl) {"),
