@@ -160,8 +160,11 @@ __device__ __forceinline__ RowInfo row_info(const RowArgs& A, int r) {
 }
 
 // type 2 x-pass: image row -> grid row.  grid (ceil(nrows / TX), 1, T)
-template <int L, int DIR>
-__global__ void __launch_bounds__(FT)
+// HALF: Nx == L / 2 (sigma = 2, Nx even): the non-zero inputs of a thread are its first and last
+// R1 / 4 points, at offsets known at compile time -- no per-element index arithmetic or predicates
+// (the generic path spends 70 % of its instructions there, ncu).
+template <int L, int DIR, bool HALF>
+__global__ void __launch_bounds__(FT, (HALF && L <= 512) ? 3 : 1)
 k_fft_rows_t2(RowArgs A, int nrows, const float2* __restrict__ tw) {
   constexpr int R1 = Split<L>::R1, R2 = Split<L>::R2, RS = R1 * (R2 + 1);
   extern __shared__ float2 S[];  // [TX][R1][R2 + 1]
@@ -173,7 +176,51 @@ k_fft_rows_t2(RowArgs A, int nrows, const float2* __restrict__ tw) {
     const int row = item / R2, n2 = item % R2;
     const int r = blockIdx.x * TX + row;
     float2 a[R1];
-    if (r < nrows) {
+    if (HALF && r < nrows) {
+      const RowInfo ri = row_info(A, r);
+      constexpr int Q = R1 / 4;  // non-zero points per end
+      // fine index n = n1 R2 + n2: modes n >= 0 (n1 < Q) sit at image index n + Nx/2, modes
+      // n - L < 0 (n1 >= 3Q) at image index n - L + Nx/2 = (n1 - 3Q) R2 + n2
+      const float2* ip = img + ri.img_off + n2;
+      const float* dp = A.d_fast + n2;
+      constexpr int hi_off = L / 4;  // Nx / 2
+      float2 v[2 * Q];
+      float dw[2 * Q];
+      sfor<0, Q>([&](auto I) {
+        constexpr int q = decltype(I)::value;
+        v[q] = __ldg(ip + hi_off + q * R2);
+        v[Q + q] = __ldg(ip + q * R2);
+      });
+      sfor<0, Q>([&](auto I) {
+        constexpr int q = decltype(I)::value;
+        dw[q] = __ldg(dp + hi_off + q * R2);
+        dw[Q + q] = __ldg(dp + q * R2);
+      });
+      if (sm) {
+        const float2* sp = sm + ri.img_off + n2;
+        float2 sv[2 * Q];
+        sfor<0, Q>([&](auto I) {
+          constexpr int q = decltype(I)::value;
+          sv[q] = __ldg(sp + hi_off + q * R2);
+          sv[Q + q] = __ldg(sp + q * R2);
+        });
+        sfor<0, 2 * Q>([&](auto I) {
+          constexpr int q = decltype(I)::value;
+          const float2 x = cscale(v[q], ri.dsl * dw[q]);
+          v[q] = A.conj_smaps ? cmul_conj(x, sv[q]) : cmul(x, sv[q]);
+        });
+      } else {
+        sfor<0, 2 * Q>([&](auto I) {
+          constexpr int q = decltype(I)::value;
+          v[q] = cscale(v[q], ri.dsl * dw[q]);
+        });
+      }
+      sfor<0, R1>([&](auto I) {
+        constexpr int n1 = decltype(I)::value;
+        a[n1] = n1 < Q ? v[n1 < Q ? n1 : 0]
+                       : (n1 >= 3 * Q ? v[n1 >= 3 * Q ? Q + (n1 - 3 * Q) : 0] : make_float2(0.f, 0.f));
+      });
+    } else if (r < nrows) {
       const RowInfo ri = row_info(A, r);
       // predicated loads, issued in two batches of R1/2 taps so that all real loads of a batch
       // (image, deapodisation factor, sensitivity map) are in flight together
@@ -447,9 +494,9 @@ int launch_strided(const StridedArgs& A, int ntx, int nouter, int T, const float
   return launch_strided_m<L, DIR, false>(A, ntx, nouter, T, tw, st);
 }
 
-template <int L, int DIR>
-int launch_rows_t2(const RowArgs& A, int nrows, const float2* tw, cudaStream_t st) {
-  auto kern = k_fft_rows_t2<L, DIR>;
+template <int L, int DIR, bool HALF>
+int launch_rows_t2_h(const RowArgs& A, int nrows, const float2* tw, cudaStream_t st) {
+  auto kern = k_fft_rows_t2<L, DIR, HALF>;
   const size_t smem = (size_t)TX * Split<L>::R1 * (Split<L>::R2 + 1) * sizeof(float2);
   static bool done = false;
   if (!done) {
@@ -459,6 +506,13 @@ int launch_rows_t2(const RowArgs& A, int nrows, const float2* tw, cudaStream_t s
   kern<<<dim3(ceil_div(nrows, TX), 1, A.T), FT, smem, st>>>(A, nrows, tw);
   CHECK_LAUNCH();
   return B200_OK;
+}
+
+template <int L, int DIR>
+int launch_rows_t2(const RowArgs& A, int nrows, const float2* tw, cudaStream_t st) {
+  const int Nx = A.g.N[A.g.dim - 1];
+  if (2 * Nx == L && Nx % 2 == 0) return launch_rows_t2_h<L, DIR, true>(A, nrows, tw, st);
+  return launch_rows_t2_h<L, DIR, false>(A, nrows, tw, st);
 }
 
 template <int L, int DIR, bool HALF>
