@@ -955,18 +955,19 @@ int prepare(b200_plan* p, RowsState* ts, cudaStream_t st) {
   if ((size_t)M > ts->pts_cap || !ts->d_iperm) {
     if (ts->d_iperm) cudaFree(ts->d_iperm);
     if (ts->d_ptab) cudaFree(ts->d_ptab);
+    if (ts->d_rec) cudaFree(ts->d_rec);
     ts->d_iperm = nullptr;
     ts->d_ptab = nullptr;
+    ts->d_rec = nullptr;
     ts->pts_cap = 0;
     const size_t cap = (size_t)(M > 0 ? M : 1);
     CUDA_TRY(cudaMalloc(&ts->d_ptab, cap * 8 * sizeof(float)));
     CUDA_TRY(cudaMalloc(&ts->d_iperm, cap * 4));
+    // the records (112 B per point) only feed the stream builder, but stay allocated: a
+    // cudaMalloc / cudaFree pair of that size per update_samples costs up to tens of ms
+    CUDA_TRY(cudaMalloc(&ts->d_rec, cap * REC * sizeof(float)));
     ts->pts_cap = cap;
   }
-  // the records (112 B per point) only feed the stream builder: freed again below
-  if (ts->d_rec) cudaFree(ts->d_rec);
-  ts->d_rec = nullptr;
-  CUDA_TRY(cudaMalloc(&ts->d_rec, (size_t)(M > 0 ? M : 1) * REC * sizeof(float)));
   if (M > 0) {
     k_point_records<W><<<ceil_div(M, 256), 256, 0, st>>>(
         p->g, M, p->d_poly, p->d_org_s[0], p->d_org_s[1], p->d_org_s[2], p->d_x1_s[0],
@@ -976,10 +977,6 @@ int prepare(b200_plan* p, RowsState* ts, cudaStream_t st) {
     CHECK_LAUNCH();
   }
   B200_TRY((build_stream<DIM, W>(p, ts, st)));
-  // the records only feed the stream builder
-  CUDA_TRY(cudaStreamSynchronize(st));
-  cudaFree(ts->d_rec);
-  ts->d_rec = nullptr;
   ts->M = M;
   ts->valid = true;
   return B200_OK;
