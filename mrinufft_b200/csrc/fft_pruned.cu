@@ -114,7 +114,7 @@ k_fft_strided(StridedArgs A, const float2* __restrict__ tw) {
       if (kept(k, L, A.out)) {
         float2 v = b[brev(k2, R2)];
         if (MUL) v = cscale(v, __ldg(A.mul + goff + (long long)k * A.stride_n + tx));
-        g[(long long)k * A.stride_n + tx] = v;
+        __stcs(g + (long long)k * A.stride_n + tx, v);
       }
     });
   }
@@ -285,7 +285,7 @@ k_fft_rows_t2(RowArgs A, int nrows, const float2* __restrict__ tw) {
     float2* out = A.fw + (long long)t * A.g.nftot + row_info(A, r).fw_off;
     sfor<0, R2>([&](auto I) {
       constexpr int k2 = decltype(I)::value;
-      out[k1 + R1 * k2] = b[brev(k2, R2)];
+      __stcs(out + k1 + R1 * k2, b[brev(k2, R2)]);
     });
   }
 }
