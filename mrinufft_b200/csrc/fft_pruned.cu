@@ -75,8 +75,11 @@ k_fft_strided(StridedArgs A, const float2* __restrict__ tw) {
   constexpr int R1 = Split<L>::R1, R2 = Split<L>::R2;
   extern __shared__ float2 S[];  // [L][TX]
   const int lo = kept_index(blockIdx.y, A.outer_L, A.outer_keep);
-  const long long goff = (long long)lo * A.outer_stride + (long long)blockIdx.x * TX;
-  float2* g = A.base + (long long)blockIdx.z * A.coil_stride + goff;
+  // with the Toeplitz multiply the coil index varies fastest over the grid of CTAs: the 32 CTAs that
+  // need the same tile of the (coil-independent) factor run together and share it through L2
+  const int bt = MUL ? blockIdx.x : blockIdx.z, bx = MUL ? blockIdx.z : blockIdx.x;
+  const long long goff = (long long)lo * A.outer_stride + (long long)bx * TX;
+  float2* g = A.base + (long long)bt * A.coil_stride + goff;
   // step A: R1-point FFTs over n1 (n = n1 R2 + n2), twiddle W_L^(n2 k1)
   for (int item = threadIdx.x; item < R2 * TX; item += FT) {
     const int n2 = item / TX, tx = item % TX;
@@ -107,13 +110,23 @@ k_fft_strided(StridedArgs A, const float2* __restrict__ tw) {
       constexpr int n2 = decltype(I)::value;
       b[n2] = S[(k1 * R2 + n2) * TX + tx];
     });
+    // Toeplitz factor of this thread's outputs: requested before the FFT so that the loads are in
+    // flight while it runs
+    float mf[MUL ? R2 : 1];
+    if (MUL) {
+      sfor<0, R2>([&](auto I) {
+        constexpr int k2 = decltype(I)::value;
+        const int k = k1 + R1 * k2;
+        mf[MUL ? k2 : 0] = kept(k, L, A.out) ? __ldg(A.mul + goff + (long long)k * A.stride_n + tx) : 0.f;
+      });
+    }
     fftreg::fft<R2, DIR>(b);
     sfor<0, R2>([&](auto I) {
       constexpr int k2 = decltype(I)::value;
       const int k = k1 + R1 * k2;
       if (kept(k, L, A.out)) {
         float2 v = b[brev(k2, R2)];
-        if (MUL) v = cscale(v, __ldg(A.mul + goff + (long long)k * A.stride_n + tx));
+        if (MUL) v = cscale(v, mf[MUL ? k2 : 0]);
         __stcs(g + (long long)k * A.stride_n + tx, v);
       }
     });
@@ -481,7 +494,7 @@ int launch_strided_m(const StridedArgs& A, int ntx, int nouter, int T, const flo
     B200_TRY(set_smem(kern, smem));
     done = true;
   }
-  kern<<<dim3(ntx, nouter, T), FT, smem, st>>>(A, tw);
+  kern<<<MUL ? dim3(T, nouter, ntx) : dim3(ntx, nouter, T), FT, smem, st>>>(A, tw);
   CHECK_LAUNCH();
   return B200_OK;
 }
