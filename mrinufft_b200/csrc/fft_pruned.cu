@@ -440,6 +440,114 @@ k_fft_rows_t1(RowArgs A, int nrows, const float2* __restrict__ tw) {
   });
 }
 
+// type 1 x-pass for L = 512, sigma = 2: three radix-8 steps (512 = 8 x 8 x 8) instead of 32 x 16.
+// An 8-point register FFT needs 16 registers instead of 64, so the kernel runs at 64 registers and four
+// CTAs (32 warps) per SM, all 64 threads of a row work in every step, and the inputs are read
+// straight from global memory (8 coalesced loads per thread, 64 KB in flight per SM) -- the 32 x 16
+// version was latency bound at 128 registers and 2.65 TB/s.
+//   n = 64 n1 + 8 n2 + n3,  k = k1 + 8 k2 + 64 k3
+//   step 1 (n2, n3): FFT over n1, twiddle W^(8 n2 k1)          -> S1[k1][8 n2 + n3]
+//   step 2 (k1, n3): FFT over n2, twiddle W^(n3 (k1 + 8 k2))    -> S2[k2][9 k1 + n3]
+//   step 3 (k1, k2): FFT over n3; kept outputs k3 in {6, 7, 0, 1} are image columns j, 64+j, 128+j,
+//                    192+j with j = k1 + 8 k2 = the thread's index in its row: coalesced map reads
+//                    and image writes.
+template <int DIR>
+__global__ void __launch_bounds__(256, 4)
+k_fft_rows_t1_512(RowArgs A, int nrows, const float2* __restrict__ tw) {
+  constexpr int L = 512, ROWS = 4, PS = 72;  // PS: padded slab stride (conflict-free exchanges)
+  __shared__ float2 S1[ROWS][8 * PS];
+  __shared__ float2 S2[ROWS][8 * PS];
+  __shared__ float2 stw[L];
+  for (int i = threadIdx.x; i < L; i += 256) {
+    float2 w = __ldg(tw + i);
+    if (DIR < 0) w.y = -w.y;
+    stw[i] = w;
+  }
+  const int row = threadIdx.x >> 6, j = threadIdx.x & 63;
+  const int hi = j >> 3, lo = j & 7;
+  const int r = blockIdx.x * ROWS + row;
+  const bool live = r < nrows;
+  RowInfo ri{};
+  if (live) ri = row_info(A, r);
+  const bool sense = A.smaps != nullptr;
+  const int t_begin = sense ? 0 : blockIdx.z;
+  const int t_end = sense ? A.T : blockIdx.z + 1;
+  float2 acc[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) acc[q] = make_float2(0.f, 0.f);
+  __syncthreads();
+  for (int t = t_begin; t < t_end; ++t) {
+    float2 a[8];
+    {
+      const float2* in = A.fw + (long long)t * A.g.nftot + ri.fw_off + j;
+      sfor<0, 8>([&](auto I) {
+        constexpr int n1 = decltype(I)::value;
+        a[n1] = live ? __ldg(in + n1 * 64) : make_float2(0.f, 0.f);
+      });
+    }
+    float2 sv[4];
+    if (sense && live) {
+      const float2* sm = A.smaps + (long long)t * A.g.Ntot + ri.img_off + j;
+      sfor<0, 4>([&](auto I) { sv[decltype(I)::value] = __ldg(sm + 64 * decltype(I)::value); });
+    }
+    // step 1: thread (n2 = hi, n3 = lo)
+    fftreg::fft<8, DIR>(a);
+    sfor<0, 8>([&](auto I) {
+      constexpr int k1 = decltype(I)::value;
+      float2 v = a[brev(k1, 8)];
+      if (k1 > 0) v = fftreg::cmul(v, stw[8 * hi * k1]);
+      S1[row][k1 * PS + j] = v;
+    });
+    __syncthreads();
+    // step 2: thread (k1 = hi, n3 = lo)
+    sfor<0, 8>([&](auto I) {
+      constexpr int n2 = decltype(I)::value;
+      a[n2] = S1[row][hi * PS + n2 * 8 + lo];
+    });
+    fftreg::fft<8, DIR>(a);
+    sfor<0, 8>([&](auto I) {
+      constexpr int k2 = decltype(I)::value;
+      float2 v = a[brev(k2, 8)];
+      v = fftreg::cmul(v, stw[lo * (hi + 8 * k2)]);
+      S2[row][k2 * PS + hi * 9 + lo] = v;
+    });
+    __syncthreads();
+    // step 3: thread (k1 = lo, k2 = hi)
+    sfor<0, 8>([&](auto I) {
+      constexpr int n3 = decltype(I)::value;
+      a[n3] = S2[row][hi * PS + lo * 9 + n3];
+    });
+    fftreg::fft<8, DIR>(a);
+    sfor<0, 4>([&](auto I) {
+      constexpr int q = decltype(I)::value;
+      constexpr int k3 = (q + 6) & 7;  // q = 0..3 -> k3 = 6, 7, 0, 1 -> image column 64 q + j
+      const float2 v = a[brev(k3, 8)];
+      if (sense) {
+        const float2 pr = A.conj_smaps ? cmul(v, sv[q]) : cmul_conj(v, sv[q]);
+        acc[q].x += pr.x;
+        acc[q].y += pr.y;
+      } else {
+        acc[q] = v;
+      }
+    });
+    // the barriers of the next iteration order these reads of S2 (and the step-2 reads of S1) before
+    // their buffers are written again
+  }
+  if (!live) return;
+  float2* outimg = (sense ? A.img_out : A.img_out + (long long)blockIdx.z * A.g.Ntot) + ri.img_off + j;
+  sfor<0, 4>([&](auto I) {
+    constexpr int q = decltype(I)::value;
+    float2 v = cscale(acc[q], ri.dsl * __ldg(A.d_fast + 64 * q + j) * A.scale);
+    float2* o = outimg + 64 * q;
+    if (A.accumulate) {
+      const float2 old = *o;
+      v.x += old.x;
+      v.y += old.y;
+    }
+    *o = v;
+  });
+}
+
 // ------------------------------------------------------------------------------ host side
 int ensure_twiddles(b200_plan* p) {
   for (int a = 0; a < p->g.dim; ++a) {
@@ -545,6 +653,11 @@ int launch_rows_t1_h(const RowArgs& A, int nrows, const float2* tw, cudaStream_t
 template <int L, int DIR>
 int launch_rows_t1(const RowArgs& A, int nrows, const float2* tw, cudaStream_t st) {
   const int Nx = A.g.N[A.g.dim - 1];
+  if (L == 512 && Nx == 256) {
+    k_fft_rows_t1_512<DIR><<<dim3(ceil_div(nrows, 4), 1, A.smaps ? 1 : A.T), 256, 0, st>>>(A, nrows, tw);
+    CHECK_LAUNCH();
+    return B200_OK;
+  }
   if (2 * Nx == L && Nx % 2 == 0) return launch_rows_t1_h<L, DIR, true>(A, nrows, tw, st);
   return launch_rows_t1_h<L, DIR, false>(A, nrows, tw, st);
 }
