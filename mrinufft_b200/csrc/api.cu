@@ -78,6 +78,7 @@ int do_spread(b200_plan* p, const float2* ksp, const float* density, float2* fw,
               cudaStream_t st) {
   Timed tm(p, EV_SPREAD, st);
   int method = p->spread_method;
+  p->spread_empty = nullptr;
   if (method == 0) method = tiled_supported(p, T) ? 2 : 1;
   if (method == 2 && !tiled_supported(p, T)) method = 1;
   if (method == 2) {
@@ -124,7 +125,7 @@ int grid_to_image(b200_plan* p, const float2* smaps, float2* img, int T, int acc
                   float scale, int conj_smaps, cudaStream_t st) {
   if (use_fftp(p)) {
     Timed tm(p, EV_FFT, st);
-    return fftp_type1(p, p->d_fw, smaps, img, T, accumulate, isign, scale, conj_smaps, st);
+    return fftp_type1(p, p->d_fw, smaps, img, T, accumulate, isign, scale, conj_smaps, st, p->spread_empty);
   }
   B200_TRY(exec_fft(p, p->d_fw, T, isign, st));
   Timed tm(p, EV_GRID, st);
@@ -489,7 +490,10 @@ int b200_type1(b200_plan* p, const void* ksp, const float* density, const void* 
   }
   DeviceGuard guard(p->device);
   cudaStream_t st = (cudaStream_t)stream;
-  B200_TRY(do_spread(p, (const float2*)ksp, density, p->d_fw, T, st));
+  p->spread_may_skip_empty = use_fftp(p);
+  const int rc = do_spread(p, (const float2*)ksp, density, p->d_fw, T, st);
+  p->spread_may_skip_empty = false;
+  B200_TRY(rc);
   return grid_to_image(p, (const float2*)smaps, (float2*)img, T, accumulate, isign, scale, conj_smaps,
                        st);
 }
@@ -511,7 +515,10 @@ int b200_data_consistency(b200_plan* p, const void* img, const void* smaps, cons
   B200_TRY(image_to_grid(p, (const float2*)img, (const float2*)smaps, T, -1, 0, st));
   // K5: residual fused into the interpolation epilogue
   B200_TRY(do_interp(p, p->d_fw, p->d_ksp_tmp, T, scale, (const float2*)obs, st));
-  B200_TRY(do_spread(p, p->d_ksp_tmp, density, p->d_fw, T, st));
+  p->spread_may_skip_empty = use_fftp(p);
+  const int rc = do_spread(p, p->d_ksp_tmp, density, p->d_fw, T, st);
+  p->spread_may_skip_empty = false;
+  B200_TRY(rc);
   return grid_to_image(p, (const float2*)smaps, (float2*)grad, T, accumulate, +1, scale, 0, st);
 }
 

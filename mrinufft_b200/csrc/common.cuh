@@ -118,6 +118,11 @@ struct b200_plan {
 
   // state of the tiled spread/interp kernels (spread_tiled.cu)
   void* tiled = nullptr;
+  // spreading into a grid that the fused FFT passes consume next: tiles without visitors are neither
+  // zero-filled by the spreader nor read by the first FFT pass (flag byte per tile, see spread_rows.cu)
+  bool spread_may_skip_empty = false;       // set by the caller of do_spread
+  const uint32_t* spread_empty = nullptr;   // set by the spreader: valid for the grid it just wrote
+  int empty_nyh = 0, empty_nbx = 0;
 
   // options
   int spread_method = 0, interp_method = 0, fft_method = 0;
@@ -160,6 +165,6 @@ int fftp_type2(b200_plan* p, const float2* img, const float2* smaps, float2* fw,
                int conj_smaps, cudaStream_t st, const float* mul = nullptr);
 int k_mul_real(b200_plan* p, float2* fw, const float* kern, int T, cudaStream_t st);
 int fftp_type1(b200_plan* p, float2* fw, const float2* smaps, float2* img, int T, int accumulate,
-               int isign, float scale, int conj_smaps, cudaStream_t st);
+               int isign, float scale, int conj_smaps, cudaStream_t st, const uint32_t* empty = nullptr);
 
 static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }

@@ -67,9 +67,14 @@ struct StridedArgs {
   Keep outer_keep;         // which outer indices are processed (blockIdx.y enumerates them)
   Keep in, out;            // non-zero inputs / wanted outputs along the transformed axis
   const float* mul;        // nullable: real factor per grid point applied to the outputs (Toeplitz)
+  // nullable: bit strings of the spreader's empty tiles (spread_rows.cu, k_mark_empty) -- tiles it
+  // left unwritten because no point visits them; read as zeros.  Only for passes along axis 0.
+  const uint32_t* empty;
+  int empty_3d;            // 1: transformed axis = z, outer index = y; 0 (2-D): transformed axis = y
+  int nyh, nbx;
 };
 
-template <int L, int DIR, bool MUL>
+template <int L, int DIR, bool MUL, bool EMPTY>
 __global__ void __launch_bounds__(FT)
 k_fft_strided(StridedArgs A, const float2* __restrict__ tw) {
   constexpr int R1 = Split<L>::R1, R2 = Split<L>::R2;
@@ -80,6 +85,24 @@ k_fft_strided(StridedArgs A, const float2* __restrict__ tw) {
   const int bt = MUL ? blockIdx.x : blockIdx.z, bx = MUL ? blockIdx.z : blockIdx.x;
   const long long goff = (long long)lo * A.outer_stride + (long long)bx * TX;
   float2* g = A.base + (long long)bt * A.coil_stride + goff;
+  // the bit string of this CTA's column of spreader tiles (16 columns = one tile width)
+  __shared__ uint32_t ebits[EMPTY ? L / 32 : 1];
+  if (EMPTY) {
+    const int wpc = A.empty_3d ? L / 32 : (L / 2 + 31) / 32;
+    const long long col = A.empty_3d ? (long long)(lo >> 1) * A.nbx + bx : bx;
+    if (threadIdx.x < wpc) ebits[threadIdx.x] = __ldg(A.empty + col * wpc + threadIdx.x);
+    __syncthreads();
+    // a column without any visited tile (outside the trajectory's support): the transform of zeros
+    bool all_empty = true;
+    for (int w = 0; w < wpc; ++w) all_empty = all_empty && ebits[w] == 0xffffffffu;
+    if (all_empty) {
+      for (int item = threadIdx.x; item < L * TX; item += FT) {
+        const int k = item / TX, tx = item % TX;
+        if (kept(k, L, A.out)) __stcs(g + (long long)k * A.stride_n + tx, make_float2(0.f, 0.f));
+      }
+      return;
+    }
+  }
   // step A: R1-point FFTs over n1 (n = n1 R2 + n2), twiddle W_L^(n2 k1)
   for (int item = threadIdx.x; item < R2 * TX; item += FT) {
     const int n2 = item / TX, tx = item % TX;
@@ -87,7 +110,12 @@ k_fft_strided(StridedArgs A, const float2* __restrict__ tw) {
     sfor<0, R1>([&](auto I) {
       constexpr int n1 = decltype(I)::value;
       const int n = n1 * R2 + n2;
-      a[n1] = kept(n, L, A.in) ? g[(long long)n * A.stride_n + tx] : make_float2(0.f, 0.f);
+      bool live = kept(n, L, A.in);
+      if (EMPTY) {
+        const int pos = A.empty_3d ? n : (n >> 1);
+        live = live && !((ebits[pos >> 5] >> (pos & 31)) & 1u);
+      }
+      a[n1] = live ? g[(long long)n * A.stride_n + tx] : make_float2(0.f, 0.f);
     });
     fftreg::fft<R1, DIR>(a);
     sfor<0, R1>([&](auto I) {
@@ -593,9 +621,9 @@ int set_smem(K kern, size_t bytes) {
     }                                                                \
   } while (0)
 
-template <int L, int DIR, bool MUL>
+template <int L, int DIR, bool MUL, bool EMPTY>
 int launch_strided_m(const StridedArgs& A, int ntx, int nouter, int T, const float2* tw, cudaStream_t st) {
-  auto kern = k_fft_strided<L, DIR, MUL>;
+  auto kern = k_fft_strided<L, DIR, MUL, EMPTY>;
   const size_t smem = (size_t)L * TX * sizeof(float2);
   static bool done = false;
   if (!done) {
@@ -611,8 +639,9 @@ int launch_strided_m(const StridedArgs& A, int ntx, int nouter, int T, const flo
 // cfg-C: 50.0 ms for the six passes against 42.4 ms with 16-column tiles; not kept.)
 template <int L, int DIR>
 int launch_strided(const StridedArgs& A, int ntx, int nouter, int T, const float2* tw, cudaStream_t st) {
-  if (A.mul) return launch_strided_m<L, DIR, true>(A, ntx, nouter, T, tw, st);
-  return launch_strided_m<L, DIR, false>(A, ntx, nouter, T, tw, st);
+  if (A.mul) return launch_strided_m<L, DIR, true, false>(A, ntx, nouter, T, tw, st);
+  if (A.empty) return launch_strided_m<L, DIR, false, true>(A, ntx, nouter, T, tw, st);
+  return launch_strided_m<L, DIR, false, false>(A, ntx, nouter, T, tw, st);
 }
 
 template <int L, int DIR, bool HALF>
@@ -664,11 +693,15 @@ int launch_rows_t1(const RowArgs& A, int nrows, const float2* tw, cudaStream_t s
 
 // pass along axis `a` (not the fastest one) of the [nf0][nf1][nf2] (or [nf0][nf1]) grid
 int strided_pass(b200_plan* p, float2* fw, int T, int a, int dir, Keep in, Keep out, Keep outer_keep,
-                 cudaStream_t st, const float* mul = nullptr) {
+                 cudaStream_t st, const float* mul = nullptr, const uint32_t* empty = nullptr) {
   const Geom& g = p->g;
   StridedArgs A;
   A.base = fw;
   A.mul = mul;
+  A.empty = (a == 0 && TX == 16) ? empty : nullptr;
+  A.empty_3d = g.dim == 3 ? 1 : 0;
+  A.nyh = p->empty_nyh;
+  A.nbx = p->empty_nbx;
   A.coil_stride = g.nftot;
   A.in = in;
   A.out = out;
@@ -742,15 +775,16 @@ int fftp_type2(b200_plan* p, const float2* img, const float2* smaps, float2* fw,
 
 // FFT + K4b:  oversampled grid -> image(s)
 int fftp_type1(b200_plan* p, float2* fw, const float2* smaps, float2* img, int T, int accumulate,
-               int isign, float scale, int conj_smaps, cudaStream_t st) {
+               int isign, float scale, int conj_smaps, cudaStream_t st, const uint32_t* empty) {
   B200_TRY(ensure_twiddles(p));
   const Geom& g = p->g;
   const int dir = isign < 0 ? -1 : 1;
   if (g.dim == 3) {
-    B200_TRY(strided_pass(p, fw, T, 0, dir, keep_all(g.nf[0]), keep_modes(g.N[0]), keep_all(g.nf[1]), st));
+    B200_TRY(strided_pass(p, fw, T, 0, dir, keep_all(g.nf[0]), keep_modes(g.N[0]), keep_all(g.nf[1]), st, nullptr,
+                          empty));
     B200_TRY(strided_pass(p, fw, T, 1, dir, keep_all(g.nf[1]), keep_modes(g.N[1]), keep_modes(g.N[0]), st));
   } else {
-    B200_TRY(strided_pass(p, fw, T, 0, dir, keep_all(g.nf[0]), keep_modes(g.N[0]), Keep{1, 0}, st));
+    B200_TRY(strided_pass(p, fw, T, 0, dir, keep_all(g.nf[0]), keep_modes(g.N[0]), Keep{1, 0}, st, nullptr, empty));
   }
   RowArgs R{};
   R.g = g;

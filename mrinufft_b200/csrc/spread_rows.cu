@@ -92,6 +92,8 @@ struct RowsState {
   uint32_t* d_start = nullptr;   // [nrows + 1] stream position of a tile's header word
   uint4* d_ent = nullptr;        // [S + slack] the visit stream
   float* d_ptab = nullptr;       // [M][8] pair-packed x weights per sorted point
+  uint32_t* d_empty = nullptr;   // empty-tile bit strings (k_mark_empty)
+  size_t empty_cap = 0;
   int32_t* d_chunk_row = nullptr;  // [nchunks] tile owning the first word of a chunk
   int32_t* d_split_rows = nullptr; // tiles cut by a chunk boundary (accumulated with red.add)
   int* d_counters = nullptr;     // [0] work counter, [1] split-row counter, [2..3] total visits (u64)
@@ -299,6 +301,26 @@ k_scan_inputs(long long n, const int32_t* __restrict__ tot, uint32_t* __restrict
   if (i >= n) return;
   const int t = tot[i];
   words[i] = t < 0 ? 0u : (uint32_t)t + 1u;
+}
+
+// One flag bit per tile, 1 = no visitors, laid out as a bit string per grid column of tiles along the
+// slowest axis: 3-D word [(y / 2) nbx + bx][z / 32], bit z % 32; 2-D word [bx][(y / 2) / 32], bit
+// (y / 2) % 32.  Lets the spreader skip the zero-fill of such tiles when the next consumer is the fused
+// FFT, whose first pass (along that axis) then substitutes zeros instead of reading them (half the grid
+// for a radial trajectory); a CTA of that pass needs one contiguous bit string.
+template <int DIM>
+__global__ void __launch_bounds__(256)
+k_mark_empty(Geom g, long long nrows, const int32_t* __restrict__ tot, uint32_t* __restrict__ bits,
+             int words_per_col) {
+  const long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= nrows) return;
+  RowCoord rc;
+  if (!decode_row<DIM>(g, row, &rc) || tot[row] != 0) return;
+  const int nyh = g.nf[DIM - 2] / 2, nbx = num_xtiles<DIM>(g);
+  const long long col = DIM == 3 ? (long long)(rc.y >> 1) * nbx + rc.bx : rc.bx;
+  const int pos = DIM == 3 ? rc.z : (rc.y >> 1);
+  (void)nyh;
+  atomicOr(bits + col * words_per_col + (pos >> 5), 1u << (pos & 31));
 }
 
 // The visit stream, written once per trajectory: 16-byte entries {s0, s1, idx, s}, tile after tile.
@@ -588,7 +610,7 @@ template <int DIM, int W, bool SPREAD>
 __global__ void __launch_bounds__(THREADS, 4)
 k_rows(Geom g, int T, int nchunks, unsigned S, long long M, const uint4* __restrict__ ent,
        const int32_t* __restrict__ chunk_row, const float* __restrict__ ptab,
-       float2* __restrict__ kt, float2* __restrict__ fw, int* __restrict__ counter, int dbg) {
+       float2* __restrict__ kt, float2* __restrict__ fw, int* __restrict__ counter, int dbg, int skip_empty) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   constexpr int SMW = smem_per_warp(SPREAD);
   constexpr unsigned FULL = 0xffffffffu;
@@ -692,7 +714,7 @@ k_rows(Geom g, int T, int nchunks, unsigned S, long long M, const uint4* __restr
     };
     // a tile without visits: plain zero stores
     auto store_zero = [&]() {
-      if (cl < xlim) {
+      if (cl < xlim && !skip_empty) {
 #pragma unroll
         for (int r = 0; r < 2; ++r)
           for (int t = hl; t < T; t += 2) __stcs(fbase + (long long)r * nfx + (long long)(t - hl) * g.nftot, 0ull);
@@ -934,6 +956,21 @@ int build_stream(b200_plan* p, RowsState* ts, cudaStream_t st) {
   }
   CUDA_TRY(cudaMemsetAsync(ts->d_ent, 0xff, ((size_t)S + 64) * 16, st));
   CUDA_TRY(cudaMemsetAsync(ts->d_chunk_row, 0, (size_t)(nchunks + 1) * 4, st));
+  {
+    const int nyh = p->g.nf[DIM - 2] / 2, nbx = num_xtiles<DIM>(p->g);
+    const int npos = DIM == 3 ? p->g.nf[0] : nyh;          // tiles per column
+    const int wpc = (npos + 31) / 32;
+    const size_t nwords = (size_t)(DIM == 3 ? (size_t)nyh * nbx : nbx) * wpc;
+    if (nwords > ts->empty_cap) {
+      fr(ts->d_empty);
+      ts->d_empty = nullptr;
+      CUDA_TRY(cudaMalloc(&ts->d_empty, nwords * 4));
+      ts->empty_cap = nwords;
+    }
+    CUDA_TRY(cudaMemsetAsync(ts->d_empty, 0, nwords * 4, st));
+    k_mark_empty<DIM><<<ceil_div(nrows, 256), 256, 0, st>>>(p->g, nrows, ts->d_tot, ts->d_empty, wpc);
+    CHECK_LAUNCH();
+  }
   k_build_stream<DIM, W><<<ceil_div(nrows * 32, 256), 256, 0, st>>>(
       p->g, nrows, p->d_bin_start, ts->d_tot, ts->d_start, ts->d_rec, ts->d_ent, ts->d_chunk_row,
       ts->d_split_rows, ts->d_counters + 1);
@@ -1007,7 +1044,13 @@ int launch_rows(b200_plan* p, RowsState* ts, float2* fw, int T, cudaStream_t st)
   const bool timed = p->timing && p->ev_ok;
   if (timed) cudaEventRecord(p->ev[8], st);
   kern<<<grid, THREADS, smem, st>>>(p->g, T, ts->nchunks, ts->S, p->M, ts->d_ent, ts->d_chunk_row,
-                                    ts->d_ptab, ts->d_kt, fw, ts->d_counters, p->rows_dbg);
+                                    ts->d_ptab, ts->d_kt, fw, ts->d_counters, p->rows_dbg,
+                                    (SPREAD && p->spread_may_skip_empty) ? 1 : 0);
+  if (SPREAD) {
+    p->spread_empty = p->spread_may_skip_empty ? ts->d_empty : nullptr;
+    p->empty_nyh = p->g.nf[DIM - 2] / 2;
+    p->empty_nbx = num_xtiles<DIM>(p->g);
+  }
   if (timed) {
     cudaEventRecord(p->ev[9], st);
     p->ev_used[4] = 1;
