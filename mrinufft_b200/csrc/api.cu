@@ -18,6 +18,7 @@ int interp_tiled(b200_plan* p, const float2* fw, float2* ksp, int T, float scale
 bool tiled_supported(const b200_plan* p, int T);
 void tiled_free(b200_plan* p);
 void tiled_invalidate(b200_plan* p);
+const uint32_t* tiled_empty_bits(b200_plan* p, cudaStream_t st);
 
 namespace {
 
@@ -107,11 +108,19 @@ bool use_fftp(const b200_plan* p) {
 }
 
 // image(s) -> transformed oversampled grid (K4a + FFT)
+// `for_tiled_interp`: the grid is consumed by the row interpolator next, which only reads tiles that
+// some point visits -- the last FFT pass may leave the others unwritten
 int image_to_grid(b200_plan* p, const float2* img, const float2* smaps, int T, int isign,
-                  int conj_smaps, cudaStream_t st) {
+                  int conj_smaps, cudaStream_t st, bool for_interp = false) {
   if (use_fftp(p)) {
+    const uint32_t* unread = nullptr;
+    if (for_interp && p->pts_set && p->M > 0) {
+      int method = p->interp_method;
+      if (method == 0) method = tiled_supported(p, T) ? 2 : 1;
+      if (method == 2 && tiled_supported(p, T)) unread = tiled_empty_bits(p, st);
+    }
     Timed tm(p, EV_FFT, st);
-    return fftp_type2(p, img, smaps, p->d_fw, T, isign, conj_smaps, st);
+    return fftp_type2(p, img, smaps, p->d_fw, T, isign, conj_smaps, st, nullptr, unread);
   }
   {
     Timed tm(p, EV_GRID, st);
@@ -477,7 +486,7 @@ int b200_type2(b200_plan* p, const void* img, const void* smaps, void* ksp, int 
   }
   DeviceGuard guard(p->device);
   cudaStream_t st = (cudaStream_t)stream;
-  B200_TRY(image_to_grid(p, (const float2*)img, (const float2*)smaps, T, isign, conj_smaps, st));
+  B200_TRY(image_to_grid(p, (const float2*)img, (const float2*)smaps, T, isign, conj_smaps, st, true));
   return do_interp(p, p->d_fw, (float2*)ksp, T, scale, nullptr, st);
 }
 
@@ -512,7 +521,7 @@ int b200_data_consistency(b200_plan* p, const void* img, const void* smaps, cons
     CUDA_TRY(cudaMalloc(&p->d_ksp_tmp,
                         (size_t)p->ntrans_max * (size_t)(p->M > 0 ? p->M : 1) * sizeof(float2)));
   }
-  B200_TRY(image_to_grid(p, (const float2*)img, (const float2*)smaps, T, -1, 0, st));
+  B200_TRY(image_to_grid(p, (const float2*)img, (const float2*)smaps, T, -1, 0, st, true));
   // K5: residual fused into the interpolation epilogue
   B200_TRY(do_interp(p, p->d_fw, p->d_ksp_tmp, T, scale, (const float2*)obs, st));
   p->spread_may_skip_empty = use_fftp(p);

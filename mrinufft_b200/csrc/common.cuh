@@ -162,7 +162,8 @@ int k_real_to_cpx(b200_plan* p, const float* d, float2* out, cudaStream_t st);
 // fused pad/crop + zero-padding-aware FFT passes (fft_pruned.cu)
 bool fftp_supported(const b200_plan* p);
 int fftp_type2(b200_plan* p, const float2* img, const float2* smaps, float2* fw, int T, int isign,
-               int conj_smaps, cudaStream_t st, const float* mul = nullptr);
+               int conj_smaps, cudaStream_t st, const float* mul = nullptr,
+               const uint32_t* unread = nullptr);
 int k_mul_real(b200_plan* p, float2* fw, const float* kern, int T, cudaStream_t st);
 int fftp_type1(b200_plan* p, float2* fw, const float2* smaps, float2* img, int T, int accumulate,
                int isign, float scale, int conj_smaps, cudaStream_t st, const uint32_t* empty = nullptr);

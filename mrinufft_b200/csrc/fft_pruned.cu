@@ -71,12 +71,16 @@ struct StridedArgs {
   // left unwritten because no point visits them; read as zeros.  Only for passes along axis 0.
   const uint32_t* empty;
   int empty_3d;            // 1: transformed axis = z, outer index = y; 0 (2-D): transformed axis = y
+  int empty_out;           // 0: applies to the inputs (type 1), 1: to the outputs (type 2)
   int nyh, nbx;
 };
 
-template <int L, int DIR, bool MUL, bool EMPTY>
+// EMODE 0: plain; 1: the spreader's empty tiles are not read (type 1, first pass); 2: tiles that no
+// point visits are not written (type 2, last pass: the row interpolator never reads them)
+template <int L, int DIR, bool MUL, int EMODE>
 __global__ void __launch_bounds__(FT)
 k_fft_strided(StridedArgs A, const float2* __restrict__ tw) {
+  constexpr bool EMPTY = EMODE != 0;
   constexpr int R1 = Split<L>::R1, R2 = Split<L>::R2;
   extern __shared__ float2 S[];  // [L][TX]
   const int lo = kept_index(blockIdx.y, A.outer_L, A.outer_keep);
@@ -95,6 +99,7 @@ k_fft_strided(StridedArgs A, const float2* __restrict__ tw) {
     // a column without any visited tile (outside the trajectory's support): the transform of zeros
     bool all_empty = true;
     for (int w = 0; w < wpc; ++w) all_empty = all_empty && ebits[w] == 0xffffffffu;
+    if (all_empty && EMODE == 2) return;  // nobody will read this column
     if (all_empty) {
       for (int item = threadIdx.x; item < L * TX; item += FT) {
         const int k = item / TX, tx = item % TX;
@@ -111,7 +116,7 @@ k_fft_strided(StridedArgs A, const float2* __restrict__ tw) {
       constexpr int n1 = decltype(I)::value;
       const int n = n1 * R2 + n2;
       bool live = kept(n, L, A.in);
-      if (EMPTY) {
+      if (EMODE == 1) {
         const int pos = A.empty_3d ? n : (n >> 1);
         live = live && !((ebits[pos >> 5] >> (pos & 31)) & 1u);
       }
@@ -152,7 +157,12 @@ k_fft_strided(StridedArgs A, const float2* __restrict__ tw) {
     sfor<0, R2>([&](auto I) {
       constexpr int k2 = decltype(I)::value;
       const int k = k1 + R1 * k2;
-      if (kept(k, L, A.out)) {
+      bool wanted = kept(k, L, A.out);
+      if (EMODE == 2) {
+        const int pos = A.empty_3d ? k : (k >> 1);
+        wanted = wanted && !((ebits[pos >> 5] >> (pos & 31)) & 1u);
+      }
+      if (wanted) {
         float2 v = b[brev(k2, R2)];
         if (MUL) v = cscale(v, mf[MUL ? k2 : 0]);
         __stcs(g + (long long)k * A.stride_n + tx, v);
@@ -621,9 +631,9 @@ int set_smem(K kern, size_t bytes) {
     }                                                                \
   } while (0)
 
-template <int L, int DIR, bool MUL, bool EMPTY>
+template <int L, int DIR, bool MUL, int EMODE>
 int launch_strided_m(const StridedArgs& A, int ntx, int nouter, int T, const float2* tw, cudaStream_t st) {
-  auto kern = k_fft_strided<L, DIR, MUL, EMPTY>;
+  auto kern = k_fft_strided<L, DIR, MUL, EMODE>;
   const size_t smem = (size_t)L * TX * sizeof(float2);
   static bool done = false;
   if (!done) {
@@ -639,9 +649,10 @@ int launch_strided_m(const StridedArgs& A, int ntx, int nouter, int T, const flo
 // cfg-C: 50.0 ms for the six passes against 42.4 ms with 16-column tiles; not kept.)
 template <int L, int DIR>
 int launch_strided(const StridedArgs& A, int ntx, int nouter, int T, const float2* tw, cudaStream_t st) {
-  if (A.mul) return launch_strided_m<L, DIR, true, false>(A, ntx, nouter, T, tw, st);
-  if (A.empty) return launch_strided_m<L, DIR, false, true>(A, ntx, nouter, T, tw, st);
-  return launch_strided_m<L, DIR, false, false>(A, ntx, nouter, T, tw, st);
+  if (A.mul) return launch_strided_m<L, DIR, true, 0>(A, ntx, nouter, T, tw, st);
+  if (A.empty && A.empty_out) return launch_strided_m<L, DIR, false, 2>(A, ntx, nouter, T, tw, st);
+  if (A.empty) return launch_strided_m<L, DIR, false, 1>(A, ntx, nouter, T, tw, st);
+  return launch_strided_m<L, DIR, false, 0>(A, ntx, nouter, T, tw, st);
 }
 
 template <int L, int DIR, bool HALF>
@@ -693,12 +704,14 @@ int launch_rows_t1(const RowArgs& A, int nrows, const float2* tw, cudaStream_t s
 
 // pass along axis `a` (not the fastest one) of the [nf0][nf1][nf2] (or [nf0][nf1]) grid
 int strided_pass(b200_plan* p, float2* fw, int T, int a, int dir, Keep in, Keep out, Keep outer_keep,
-                 cudaStream_t st, const float* mul = nullptr, const uint32_t* empty = nullptr) {
+                 cudaStream_t st, const float* mul = nullptr, const uint32_t* empty = nullptr,
+                 int empty_out = 0) {
   const Geom& g = p->g;
   StridedArgs A;
   A.base = fw;
   A.mul = mul;
   A.empty = (a == 0 && TX == 16) ? empty : nullptr;
+  A.empty_out = empty_out;
   A.empty_3d = g.dim == 3 ? 1 : 0;
   A.nyh = p->empty_nyh;
   A.nbx = p->empty_nbx;
@@ -746,7 +759,7 @@ bool fftp_supported(const b200_plan* p) {
 
 // K4a + FFT:  image(s) -> oversampled grid, all T coils
 int fftp_type2(b200_plan* p, const float2* img, const float2* smaps, float2* fw, int T, int isign,
-               int conj_smaps, cudaStream_t st, const float* mul) {
+               int conj_smaps, cudaStream_t st, const float* mul, const uint32_t* unread) {
   B200_TRY(ensure_twiddles(p));
   const Geom& g = p->g;
   const int dir = isign < 0 ? -1 : 1;
@@ -766,9 +779,11 @@ int fftp_type2(b200_plan* p, const float2* img, const float2* smaps, float2* fw,
   if (g.dim == 3) {
     // y-pass on the N0 non-zero planes, then z-pass everywhere
     B200_TRY(strided_pass(p, fw, T, 1, dir, keep_modes(g.N[1]), keep_all(g.nf[1]), keep_modes(g.N[0]), st));
-    B200_TRY(strided_pass(p, fw, T, 0, dir, keep_modes(g.N[0]), keep_all(g.nf[0]), keep_all(g.nf[1]), st, mul));
+    B200_TRY(strided_pass(p, fw, T, 0, dir, keep_modes(g.N[0]), keep_all(g.nf[0]), keep_all(g.nf[1]), st, mul,
+                          mul ? nullptr : unread, 1));
   } else {
-    B200_TRY(strided_pass(p, fw, T, 0, dir, keep_modes(g.N[0]), keep_all(g.nf[0]), Keep{1, 0}, st, mul));
+    B200_TRY(strided_pass(p, fw, T, 0, dir, keep_modes(g.N[0]), keep_all(g.nf[0]), Keep{1, 0}, st, mul,
+                          mul ? nullptr : unread, 1));
   }
   return B200_OK;
 }

@@ -1152,6 +1152,18 @@ static int ensure_state(b200_plan* p, cudaStream_t st) {
   DISPATCH_DW(prepare, p, ts, st);
 }
 
+// Bit strings of the tiles that no point visits (nullptr if the row kernels do not serve this
+// trajectory): the type-2 FFT may leave those tiles unwritten, the row interpolator never reads them.
+const uint32_t* tiled_empty_bits(b200_plan* p, cudaStream_t st) {
+  if (ensure_state(p, st) != B200_OK) return nullptr;
+  RowsState* ts = state(p);
+  if (ts->unsupported || !ts->d_empty) return nullptr;
+  const int d = p->g.dim;
+  p->empty_nyh = p->g.nf[d - 2] / 2;
+  p->empty_nbx = (p->g.nf[d - 1] + CX - 1) / CX;
+  return ts->d_empty;
+}
+
 // Both entry points return 1 (not an error) when the row kernels cannot serve this trajectory
 // (more than 2^31 visits or 2^27 points): the caller then uses the point-driven kernels.
 int spread_tiled(b200_plan* p, const float2* ksp, const float* density, float2* fw, int T,
