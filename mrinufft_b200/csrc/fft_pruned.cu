@@ -77,7 +77,10 @@ struct StridedArgs {
 
 // EMODE 0: plain; 1: the spreader's empty tiles are not read (type 1, first pass); 2: tiles that no
 // point visits are not written (type 2, last pass: the row interpolator never reads them)
-template <int L, int DIR, bool MUL, int EMODE>
+// KIN / KOUT = 1: the non-zero inputs / wanted outputs are the modes of an N = L / 2 image (sigma = 2), a
+// pattern known at compile time: inputs n1 < R1/4 or n1 >= 3 R1/4, outputs k2 < R2/4 or k2 >= 3 R2/4 --
+// no per-element predicates.  0: generic (run-time `Keep`, all-kept included).
+template <int L, int DIR, bool MUL, int EMODE, int KIN, int KOUT>
 __global__ void __launch_bounds__(FT)
 k_fft_strided(StridedArgs A, const float2* __restrict__ tw) {
   constexpr bool EMPTY = EMODE != 0;
@@ -112,15 +115,22 @@ k_fft_strided(StridedArgs A, const float2* __restrict__ tw) {
   for (int item = threadIdx.x; item < R2 * TX; item += FT) {
     const int n2 = item / TX, tx = item % TX;
     float2 a[R1];
+    const float2* gin = g + (long long)n2 * A.stride_n + tx;
+    const long long sR2 = A.stride_n * R2;
     sfor<0, R1>([&](auto I) {
       constexpr int n1 = decltype(I)::value;
-      const int n = n1 * R2 + n2;
-      bool live = kept(n, L, A.in);
-      if (EMODE == 1) {
-        const int pos = A.empty_3d ? n : (n >> 1);
-        live = live && !((ebits[pos >> 5] >> (pos & 31)) & 1u);
+      constexpr bool static_zero = KIN == 1 && n1 >= R1 / 4 && n1 < 3 * R1 / 4;
+      if constexpr (static_zero) {
+        a[n1] = make_float2(0.f, 0.f);
+      } else {
+        const int n = n1 * R2 + n2;
+        bool live = KIN == 1 ? true : kept(n, L, A.in);
+        if (EMODE == 1) {
+          const int pos = A.empty_3d ? n : (n >> 1);
+          live = live && !((ebits[pos >> 5] >> (pos & 31)) & 1u);
+        }
+        a[n1] = live ? gin[n1 * sR2] : make_float2(0.f, 0.f);
       }
-      a[n1] = live ? g[(long long)n * A.stride_n + tx] : make_float2(0.f, 0.f);
     });
     fftreg::fft<R1, DIR>(a);
     sfor<0, R1>([&](auto I) {
@@ -146,6 +156,8 @@ k_fft_strided(StridedArgs A, const float2* __restrict__ tw) {
     // Toeplitz factor of this thread's outputs: requested before the FFT so that the loads are in
     // flight while it runs
     float mf[MUL ? R2 : 1];
+    float2* gout = g + (long long)k1 * A.stride_n + tx;
+    const long long sR1 = A.stride_n * R1;
     if (MUL) {
       sfor<0, R2>([&](auto I) {
         constexpr int k2 = decltype(I)::value;
@@ -156,16 +168,19 @@ k_fft_strided(StridedArgs A, const float2* __restrict__ tw) {
     fftreg::fft<R2, DIR>(b);
     sfor<0, R2>([&](auto I) {
       constexpr int k2 = decltype(I)::value;
-      const int k = k1 + R1 * k2;
-      bool wanted = kept(k, L, A.out);
-      if (EMODE == 2) {
-        const int pos = A.empty_3d ? k : (k >> 1);
-        wanted = wanted && !((ebits[pos >> 5] >> (pos & 31)) & 1u);
-      }
-      if (wanted) {
-        float2 v = b[brev(k2, R2)];
-        if (MUL) v = cscale(v, mf[MUL ? k2 : 0]);
-        __stcs(g + (long long)k * A.stride_n + tx, v);
+      constexpr bool static_drop = KOUT == 1 && k2 >= R2 / 4 && k2 < 3 * R2 / 4;
+      if constexpr (!static_drop) {
+        const int k = k1 + R1 * k2;
+        bool wanted = KOUT == 1 ? true : kept(k, L, A.out);
+        if (EMODE == 2) {
+          const int pos = A.empty_3d ? k : (k >> 1);
+          wanted = wanted && !((ebits[pos >> 5] >> (pos & 31)) & 1u);
+        }
+        if (wanted) {
+          float2 v = b[brev(k2, R2)];
+          if (MUL) v = cscale(v, mf[MUL ? k2 : 0]);
+          __stcs(gout + k2 * sR1, v);
+        }
       }
     });
   }
@@ -631,9 +646,9 @@ int set_smem(K kern, size_t bytes) {
     }                                                                \
   } while (0)
 
-template <int L, int DIR, bool MUL, int EMODE>
+template <int L, int DIR, bool MUL, int EMODE, int KIN, int KOUT>
 int launch_strided_m(const StridedArgs& A, int ntx, int nouter, int T, const float2* tw, cudaStream_t st) {
-  auto kern = k_fft_strided<L, DIR, MUL, EMODE>;
+  auto kern = k_fft_strided<L, DIR, MUL, EMODE, KIN, KOUT>;
   const size_t smem = (size_t)L * TX * sizeof(float2);
   static bool done = false;
   if (!done) {
@@ -649,10 +664,21 @@ int launch_strided_m(const StridedArgs& A, int ntx, int nouter, int T, const flo
 // cfg-C: 50.0 ms for the six passes against 42.4 ms with 16-column tiles; not kept.)
 template <int L, int DIR>
 int launch_strided(const StridedArgs& A, int ntx, int nouter, int T, const float2* tw, cudaStream_t st) {
-  if (A.mul) return launch_strided_m<L, DIR, true, 0>(A, ntx, nouter, T, tw, st);
-  if (A.empty && A.empty_out) return launch_strided_m<L, DIR, false, 2>(A, ntx, nouter, T, tw, st);
-  if (A.empty) return launch_strided_m<L, DIR, false, 1>(A, ntx, nouter, T, tw, st);
-  return launch_strided_m<L, DIR, false, 0>(A, ntx, nouter, T, tw, st);
+  // sigma = 2 patterns: modes of an N = L / 2 image <-> Keep{L / 4, L / 4}; everything <-> Keep{L, 0}
+  const bool in_half = A.in.np == L / 4 && A.in.nm == L / 4, in_all = A.in.np == L && A.in.nm == 0;
+  const bool out_half = A.out.np == L / 4 && A.out.nm == L / 4, out_all = A.out.np == L && A.out.nm == 0;
+  if (A.mul) return launch_strided_m<L, DIR, true, 0, 0, 0>(A, ntx, nouter, T, tw, st);
+  if (in_half && out_all) {  // type 2
+    if (A.empty && A.empty_out) return launch_strided_m<L, DIR, false, 2, 1, 0>(A, ntx, nouter, T, tw, st);
+    if (!A.empty) return launch_strided_m<L, DIR, false, 0, 1, 0>(A, ntx, nouter, T, tw, st);
+  }
+  if (in_all && out_half) {  // type 1
+    if (A.empty && !A.empty_out) return launch_strided_m<L, DIR, false, 1, 0, 1>(A, ntx, nouter, T, tw, st);
+    if (!A.empty) return launch_strided_m<L, DIR, false, 0, 0, 1>(A, ntx, nouter, T, tw, st);
+  }
+  if (A.empty && A.empty_out) return launch_strided_m<L, DIR, false, 2, 0, 0>(A, ntx, nouter, T, tw, st);
+  if (A.empty) return launch_strided_m<L, DIR, false, 1, 0, 0>(A, ntx, nouter, T, tw, st);
+  return launch_strided_m<L, DIR, false, 0, 0, 0>(A, ntx, nouter, T, tw, st);
 }
 
 template <int L, int DIR, bool HALF>
