@@ -114,7 +114,7 @@ int image_to_grid(b200_plan* p, const float2* img, const float2* smaps, int T, i
                   int conj_smaps, cudaStream_t st, bool for_interp = false) {
   if (use_fftp(p)) {
     const uint32_t* unread = nullptr;
-    if (for_interp && p->pts_set && p->M > 0) {
+    if (for_interp && p->pts_set && p->M > 0 && p->g.dim == 3) {
       int method = p->interp_method;
       if (method == 0) method = tiled_supported(p, T) ? 2 : 1;
       if (method == 2 && tiled_supported(p, T)) unread = tiled_empty_bits(p, st);
@@ -499,7 +499,7 @@ int b200_type1(b200_plan* p, const void* ksp, const float* density, const void* 
   }
   DeviceGuard guard(p->device);
   cudaStream_t st = (cudaStream_t)stream;
-  p->spread_may_skip_empty = use_fftp(p);
+  p->spread_may_skip_empty = use_fftp(p) && p->g.dim == 3;
   const int rc = do_spread(p, (const float2*)ksp, density, p->d_fw, T, st);
   p->spread_may_skip_empty = false;
   B200_TRY(rc);
@@ -524,7 +524,7 @@ int b200_data_consistency(b200_plan* p, const void* img, const void* smaps, cons
   B200_TRY(image_to_grid(p, (const float2*)img, (const float2*)smaps, T, -1, 0, st, true));
   // K5: residual fused into the interpolation epilogue
   B200_TRY(do_interp(p, p->d_fw, p->d_ksp_tmp, T, scale, (const float2*)obs, st));
-  p->spread_may_skip_empty = use_fftp(p);
+  p->spread_may_skip_empty = use_fftp(p) && p->g.dim == 3;
   const int rc = do_spread(p, p->d_ksp_tmp, density, p->d_fw, T, st);
   p->spread_may_skip_empty = false;
   B200_TRY(rc);

@@ -95,8 +95,8 @@ k_fft_strided(StridedArgs A, const float2* __restrict__ tw) {
   // the bit string of this CTA's column of spreader tiles (16 columns = one tile width)
   __shared__ uint32_t ebits[EMPTY ? L / 32 : 1];
   if (EMPTY) {
-    const int wpc = A.empty_3d ? L / 32 : (L / 2 + 31) / 32;
-    const long long col = A.empty_3d ? (long long)(lo >> 1) * A.nbx + bx : bx;
+    constexpr int wpc = L / 32;  // 3-D only: one bit per grid plane
+    const long long col = (long long)(lo >> 1) * A.nbx + bx;
     if (threadIdx.x < wpc) ebits[threadIdx.x] = __ldg(A.empty + col * wpc + threadIdx.x);
     __syncthreads();
     // a column without any visited tile (outside the trajectory's support): the transform of zeros
@@ -126,8 +126,9 @@ k_fft_strided(StridedArgs A, const float2* __restrict__ tw) {
         const int n = n1 * R2 + n2;
         bool live = KIN == 1 ? true : kept(n, L, A.in);
         if (EMODE == 1) {
-          const int pos = A.empty_3d ? n : (n >> 1);
-          live = live && !((ebits[pos >> 5] >> (pos & 31)) & 1u);
+          // tile of grid plane n (3-D only): word n >> 5, bit n & 31 -- static word index when R2 = 16
+          if constexpr (R2 == 16) live = live && !((ebits[n1 >> 1] >> ((n1 & 1) * 16 + n2)) & 1u);
+          else live = live && !((ebits[n >> 5] >> (n & 31)) & 1u);
         }
         a[n1] = live ? gin[n1 * sR2] : make_float2(0.f, 0.f);
       }
@@ -173,8 +174,8 @@ k_fft_strided(StridedArgs A, const float2* __restrict__ tw) {
         const int k = k1 + R1 * k2;
         bool wanted = KOUT == 1 ? true : kept(k, L, A.out);
         if (EMODE == 2) {
-          const int pos = A.empty_3d ? k : (k >> 1);
-          wanted = wanted && !((ebits[pos >> 5] >> (pos & 31)) & 1u);
+          if constexpr (R1 == 32) wanted = wanted && !((ebits[k2] >> k1) & 1u);
+          else wanted = wanted && !((ebits[k >> 5] >> (k & 31)) & 1u);
         }
         if (wanted) {
           float2 v = b[brev(k2, R2)];
@@ -736,7 +737,7 @@ int strided_pass(b200_plan* p, float2* fw, int T, int a, int dir, Keep in, Keep 
   StridedArgs A;
   A.base = fw;
   A.mul = mul;
-  A.empty = (a == 0 && TX == 16) ? empty : nullptr;
+  A.empty = (a == 0 && TX == 16 && g.dim == 3) ? empty : nullptr;  // (2-D grids are small: not worth it)
   A.empty_out = empty_out;
   A.empty_3d = g.dim == 3 ? 1 : 0;
   A.nyh = p->empty_nyh;
