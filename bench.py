@@ -34,7 +34,7 @@ for _p in (ROOT, ROOT / "baseline" / "_ref"):
 METRIC = "3D 32-coil NUFFT op+adj_op throughput"
 # DRAM bytes (read + write) of one launch of the row kernels at cfg-C, `ncu --set full`:
 # profiles/r01_k_rows_stream_full.txt
-NCU_TRAFFIC_GB = {"spread": 56.8, "interp": 42.1}
+NCU_TRAFFIC_GB = {"spread": 39.7, "interp": 42.5}
 UNIT = "k-samples/s"
 
 
@@ -409,7 +409,7 @@ def run_b200(args):
         "step_algorithmic_bytes": ab["pair_all_coils"],
         "step_frac": ab["pair_all_coils"] / (ms_max * 1e-3) / 1e9 / peak,
         "note": "the row kernels are bound by instruction issue and the L1/shared data pipe, not by HBM "
-                "(ncu: issue 52-57 %, l1tex 55-67 %, dram 25-30 %); frac is quoted against the HBM floor as the "
+                "(ncu: issue 54-56 %, dram 26-31 %); frac is quoted against the HBM floor as the "
                 "contract asks",
     }
 
