@@ -47,6 +47,10 @@ typedef struct b200_plan b200_plan;
 
 /* plan flags */
 #define B200_SPREAD_ONLY 1   /* finufft `spreadinterponly=1` (finufft.py:225-232) */
+#define B200_DOUBLE      2   /* float64 / complex128 plan: `dtype = samples.dtype` (base.py:934), finufft's
+                                double instantiation.  Every data pointer of the plan's calls is then
+                                complex128 / float64 (sample coordinates and density included).
+                                Correctness-first kernels; no spread-only mode, sort read-back or Toeplitz. */
 
 /* Version of this ABI (bumped on any signature change). */
 int b200_abi_version(void);

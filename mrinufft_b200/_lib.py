@@ -16,6 +16,7 @@ _HERE = Path(__file__).resolve().parent
 LIB_PATH = _HERE / "csrc" / "libb200nufft.so"
 
 B200_SPREAD_ONLY = 1
+B200_DOUBLE = 2
 
 # every symbol declared in include/b200nufft.h (tests check the export list against the header)
 _SIGNATURES = {
@@ -109,7 +110,8 @@ def launch_count(reset: bool = False):
 class Plan:
     """Thin RAII wrapper of ``b200_plan`` (one device, one trajectory, both transform types)."""
 
-    def __init__(self, shape, n_trans_max=1, eps=1e-6, upsampfac=2.0, spread_only=False, device=0):
+    def __init__(self, shape, n_trans_max=1, eps=1e-6, upsampfac=2.0, spread_only=False, device=0,
+                 double=False):
         self._lib = load()
         self._h = C.c_void_p(None)
         self.shape = tuple(int(s) for s in shape)
@@ -120,7 +122,7 @@ class Plan:
         check(
             self._lib.b200_plan_create(
                 C.byref(self._h), self.dim, n_modes, self.n_trans_max, float(eps), float(upsampfac),
-                B200_SPREAD_ONLY if spread_only else 0, self.device,
+                (B200_SPREAD_ONLY if spread_only else 0) | (B200_DOUBLE if double else 0), self.device,
             ),
             "b200_plan_create",
         )

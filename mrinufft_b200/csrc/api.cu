@@ -257,6 +257,22 @@ int b200_plan_create(b200_plan** out, int dim, const int64_t* n_modes, int n_tra
     return B200_EINVAL;
   }
 
+  if (flags & B200_DOUBLE) {
+    // complex128 path (double_path.cu): own workspace and kernels, same entry points
+    if (flags & B200_SPREAD_ONLY) {
+      b200_set_error("B200_DOUBLE plans do not support B200_SPREAD_ONLY");
+      delete p;
+      return B200_EINVAL;
+    }
+    const int rc = dbl_init(p);
+    if (rc != B200_OK) {
+      b200_plan_destroy(p);
+      return rc;
+    }
+    *out = p;
+    return B200_OK;
+  }
+
   KernelTables kt;
   es_fit_polynomial(w, beta, eps, &kt);
   g.deg = kt.deg;
@@ -338,6 +354,7 @@ int b200_plan_destroy(b200_plan* p) {
     if (q) cudaFree(q);
   };
   tiled_free(p);
+  dbl_free(p);
   fr(p->d_poly);
   for (int a = 0; a < 3; ++a) {
     fr(p->d_deapod[a]);
@@ -448,6 +465,11 @@ int b200_plan_setpts(b200_plan* p, int64_t M, const float* xyz, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   p->M = M;
   p->pts_set = false;
+  if (p->dbl) {
+    B200_TRY(dbl_setpts(p, (const double*)xyz, st));
+    p->pts_set = true;
+    return B200_OK;
+  }
   tiled_invalidate(p);
   B200_TRY(k1_setpts(p, xyz, st));
   p->pts_set = true;
@@ -458,6 +480,10 @@ int b200_plan_get_sort(b200_plan* p, int32_t* origin, float* x1, int32_t* key, i
                        void* stream) {
   if (!p || !p->pts_set) {
     b200_set_error("b200_plan_get_sort: setpts has not been called");
+    return B200_ESTATE;
+  }
+  if (p->dbl) {
+    b200_set_error("b200_plan_get_sort: B200_DOUBLE plans do not sort their points");
     return B200_ESTATE;
   }
   DeviceGuard guard(p->device);
@@ -486,6 +512,7 @@ int b200_type2(b200_plan* p, const void* img, const void* smaps, void* ksp, int 
   }
   DeviceGuard guard(p->device);
   cudaStream_t st = (cudaStream_t)stream;
+  if (p->dbl) return dbl_type2(p, img, smaps, ksp, T, isign, (double)scale, conj_smaps, st);
   B200_TRY(image_to_grid(p, (const float2*)img, (const float2*)smaps, T, isign, conj_smaps, st, true));
   return do_interp(p, p->d_fw, (float2*)ksp, T, scale, nullptr, st);
 }
@@ -499,6 +526,8 @@ int b200_type1(b200_plan* p, const void* ksp, const float* density, const void* 
   }
   DeviceGuard guard(p->device);
   cudaStream_t st = (cudaStream_t)stream;
+  if (p->dbl)
+    return dbl_type1(p, ksp, density, smaps, img, T, accumulate, isign, (double)scale, conj_smaps, st);
   p->spread_may_skip_empty = use_fftp(p) && p->g.dim == 3;
   const int rc = do_spread(p, (const float2*)ksp, density, p->d_fw, T, st);
   p->spread_may_skip_empty = false;
@@ -517,6 +546,8 @@ int b200_data_consistency(b200_plan* p, const void* img, const void* smaps, cons
   }
   DeviceGuard guard(p->device);
   cudaStream_t st = (cudaStream_t)stream;
+  if (p->dbl)
+    return dbl_data_consistency(p, img, smaps, obs, density, grad, T, accumulate, (double)scale, st);
   if (!p->d_ksp_tmp) {
     CUDA_TRY(cudaMalloc(&p->d_ksp_tmp,
                         (size_t)p->ntrans_max * (size_t)(p->M > 0 ? p->M : 1) * sizeof(float2)));
@@ -541,8 +572,8 @@ int b200_toeplitz_apply(b200_plan* p, const void* img, const void* smaps, const 
     b200_set_error("T=%d outside [1, n_trans_max=%d]", T, p->ntrans_max);
     return B200_EINVAL;
   }
-  if (p->flags & B200_SPREAD_ONLY) {
-    b200_set_error("b200_toeplitz_apply needs a full (not B200_SPREAD_ONLY) plan");
+  if ((p->flags & B200_SPREAD_ONLY) || p->dbl) {
+    b200_set_error("b200_toeplitz_apply needs a full single-precision plan");
     return B200_ESTATE;
   }
   for (int a = 0; a < p->g.dim; ++a)

@@ -118,6 +118,8 @@ struct b200_plan {
 
   // state of the tiled spread/interp kernels (spread_tiled.cu)
   void* tiled = nullptr;
+  // complex128 path (double_path.cu): non-null for plans created with B200_DOUBLE
+  void* dbl = nullptr;
   // spreading into a grid that the fused FFT passes consume next: tiles without visitors are neither
   // zero-filled by the spreader nor read by the first FFT pass (flag byte per tile, see spread_rows.cu)
   bool spread_may_skip_empty = false;       // set by the caller of do_spread
@@ -167,5 +169,17 @@ int fftp_type2(b200_plan* p, const float2* img, const float2* smaps, float2* fw,
 int k_mul_real(b200_plan* p, float2* fw, const float* kern, int T, cudaStream_t st);
 int fftp_type1(b200_plan* p, float2* fw, const float2* smaps, float2* img, int T, int accumulate,
                int isign, float scale, int conj_smaps, cudaStream_t st, const uint32_t* empty = nullptr);
+
+// complex128 path (double_path.cu)
+int dbl_init(b200_plan* p);
+void dbl_free(b200_plan* p);
+int dbl_setpts(b200_plan* p, const double* xyz, cudaStream_t st);
+int dbl_type2(b200_plan* p, const void* img, const void* smaps, void* ksp, int T, int isign, double scale,
+              int conj_smaps, cudaStream_t st);
+int dbl_type1(b200_plan* p, const void* ksp, const void* density, const void* smaps, void* img, int T,
+              int accumulate, int isign, double scale, int conj_smaps, cudaStream_t st);
+int dbl_data_consistency(b200_plan* p, const void* img, const void* smaps, const void* obs,
+                         const void* density, void* grad, int T, int accumulate, double scale,
+                         cudaStream_t st);
 
 static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }

@@ -51,6 +51,7 @@ class MRIB200FourierCorrected(MRIFourierCorrected):
 
         fo = self._fourier_op
         ok = isinstance(fo, MRIB200NUFFT) and not fo._spread_only and (fo.uses_sense or fo.n_coils == 1)
+        ok = ok and not fo._double  # the batched path is single precision
         # samples are kept in radians; a trajectory that small would be re-scaled on re-entry
         ok = ok and float(np.abs(fo.samples).max()) - 1e-4 >= 0.5
         if ok:

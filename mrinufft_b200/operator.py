@@ -55,7 +55,7 @@ class RawB200Plan:
     ``finufft.py:23-80``, and ``RawCufinufftPlan``, ``cufinufft.py:51-137``)."""
 
     def __init__(self, samples, shape, n_trans=1, eps=1e-6, upsampfac=2.0, spread_only=False,
-                 device=None):
+                 device=None, double=False):
         self.device = torch.device("cuda", torch.cuda.current_device() if device is None else device)
         self.shape = tuple(int(s) for s in shape)
         self.ndim = len(self.shape)
@@ -63,8 +63,9 @@ class RawB200Plan:
         self.n_trans = int(n_trans)
         self.spread_only = bool(spread_only)
         self.isign_flip = False  # toggle_grad_traj: e^{-i} <-> e^{+i}
+        self.double = bool(double)
         self.plan = _lib.Plan(self.shape, n_trans_max=self.n_trans, eps=eps, upsampfac=upsampfac,
-                              spread_only=spread_only, device=self.device.index)
+                              spread_only=spread_only, device=self.device.index, double=self.double)
         self.n_samples = 0
         self._pts = None
         self._set_pts(samples)
@@ -75,7 +76,7 @@ class RawB200Plan:
 
     def _set_pts(self, samples):
         """``Plan.setpts`` (finufft.py:55-62): fold + bin-sort on the device."""
-        pts = to_device(samples, self.device, torch.float32)
+        pts = to_device(samples, self.device, torch.float64 if self.double else torch.float32)
         if pts.ndim != 2 or pts.shape[1] != self.ndim:
             raise ValueError(f"samples should have shape (M, {self.ndim}), got {tuple(pts.shape)}")
         self._pts = pts
@@ -159,6 +160,7 @@ class MRIB200NUFFT(FourierOperatorBase):
         coil_chunk=None,
         spreadinterponly=0,
         isign=None,
+        precision="single",
         **kwargs,
     ):
         if not _lib.library_built():
@@ -179,9 +181,18 @@ class MRIB200NUFFT(FourierOperatorBase):
         dev_index = torch.cuda.current_device() if gpu_device_id is None else int(gpu_device_id)
         self.device = torch.device("cuda", dev_index)
 
+        if precision not in ("single", "double"):
+            raise ValueError("precision should be 'single' or 'double'")
+        # single precision is the native, tuned path (cufinufft precedent: float64 samples are cast,
+        # cufinufft.py:338-340); precision="double" opts into the complex128 kernels
+        self._double = precision == "double"
+        if self._double and spreadinterponly:
+            raise ValueError("precision='double' does not support spreadinterponly plans")
+        self._rdt = torch.float64 if self._double else torch.float32
+        self._cdt = torch.complex128 if self._double else torch.complex64
         samples = self._normalize_samples(samples)
         self._samples = samples
-        self.dtype = np.float32
+        self.dtype = np.float64 if self._double else np.float32
         if n_coils < 1:
             raise ValueError("n_coils should be ≥ 1")
         self.n_coils = n_coils
@@ -199,7 +210,7 @@ class MRIB200NUFFT(FourierOperatorBase):
 
         self.raw_op = RawB200Plan(
             samples, self.shape, n_trans=self._pick_chunk(), eps=self.eps, upsampfac=self.upsampfac,
-            spread_only=self._spread_only, device=dev_index,
+            spread_only=self._spread_only, device=dev_index, double=self._double,
         )
         if self._user_isign_flip:
             self.raw_op.toggle_grad_traj()
@@ -216,10 +227,12 @@ class MRIB200NUFFT(FourierOperatorBase):
                 samples = samples.get()
             samples = np.asarray(samples)
         samples = proper_trajectory(samples, normalize="pi")
-        if samples.dtype != np.float32:
+        want = np.float64 if getattr(self, "_double", False) else np.float32
+        if samples.dtype != want:
             if samples.dtype == np.float64:
-                self.log.info("b200 backend computes in float32/complex64: casting float64 samples.")
-            samples = samples.astype(np.float32)
+                self.log.info("b200 backend computes in float32/complex64 unless precision='double': "
+                              "casting float64 samples.")
+            samples = samples.astype(want)
         return np.ascontiguousarray(samples.reshape(-1, len(self.shape)))
 
     def _pick_chunk(self) -> int:
@@ -232,7 +245,8 @@ class MRIB200NUFFT(FourierOperatorBase):
         if self._spread_only:
             return min(self.n_coils, 8)
         sigma = self.upsampfac
-        grid_bytes = 8 * float(np.prod([max(2 * 8, int(np.ceil(sigma * s))) for s in self.shape]))
+        grid_bytes = (16 if self._double else 8) * float(
+            np.prod([max(2 * 8, int(np.ceil(sigma * s))) for s in self.shape]))
         free, _ = torch.cuda.mem_get_info(self.device)
         # grids + cuFFT work area (same order) may take at most ~45% of the free memory
         cap = int(0.45 * free / (2.0 * grid_bytes))
@@ -249,9 +263,9 @@ class MRIB200NUFFT(FourierOperatorBase):
     def stream(self):
         return torch.cuda.current_stream(self.device).cuda_stream
 
-    def _in(self, arr, dtype=torch.complex64):
+    def _in(self, arr, dtype=None):
         kind, dev = describe(arr)
-        t = to_device(arr, self.device, dtype)
+        t = to_device(arr, self.device, self._cdt if dtype is None else dtype)
         return t, kind, dev
 
     def _out(self, t, kind, dev):
@@ -280,7 +294,7 @@ class MRIB200NUFFT(FourierOperatorBase):
             self.log.warning("updating number of coils via Smaps.")
         self._smaps = new_smaps
         # a contiguous complex64 CUDA tensor on this device is used zero-copy (never written to)
-        self._smaps_d = to_device(new_smaps, self.device, torch.complex64)
+        self._smaps_d = to_device(new_smaps, self.device, self._cdt)
 
     def compute_smaps(self, method=None):
         """Same grammar as ``FourierOperatorBase.compute_smaps`` (base.py:407-448) + device arrays."""
@@ -310,7 +324,7 @@ class MRIB200NUFFT(FourierOperatorBase):
         d = to_device(new_density, self.device)
         if d.is_complex():
             d = d.real
-        d = d.to(torch.float32).contiguous().reshape(-1)
+        d = d.to(self._rdt).contiguous().reshape(-1)
         self._density_d = d
         self._density = new_density if isinstance(new_density, np.ndarray) else d.cpu().numpy()
 
@@ -377,9 +391,10 @@ class MRIB200NUFFT(FourierOperatorBase):
     def _op_device(self, img: torch.Tensor, ksp: torch.Tensor | None = None) -> torch.Tensor:
         """img (B, 1|C, *XYZ) complex64 on device -> ksp (B, C, K)."""
         B, C, K, XYZ = self.n_batchs, self.n_coils, self.n_samples, self.shape
-        inv_norm = float(self.inv_norm_factor)
+        # the C ABI carries the scale as a float: double plans get 1 and are scaled here in float64
+        inv_norm = 1.0 if self._double else float(self.inv_norm_factor)
         if ksp is None:
-            ksp = torch.empty((B, C, K), dtype=torch.complex64, device=self.device)
+            ksp = torch.empty((B, C, K), dtype=self._cdt, device=self.device)
         ksp = ksp.view(B, C, K)
         raw = self.raw_op
         if self._spread_only:
@@ -400,18 +415,20 @@ class MRIB200NUFFT(FourierOperatorBase):
             for b in range(B):
                 for c0, c1 in self._chunks():
                     raw.type2(img[b, c0:c1], None, ksp[b, c0:c1], inv_norm)
+        if self._double:
+            ksp *= float(self.inv_norm_factor)
         return ksp
 
     def _adj_device(self, ksp: torch.Tensor, img: torch.Tensor | None = None) -> torch.Tensor:
         """ksp (B, C, K) complex64 on device -> img (B, 1|C, *XYZ)."""
         B, C, K, XYZ = self.n_batchs, self.n_coils, self.n_samples, self.shape
-        inv_norm = float(self.inv_norm_factor)
+        inv_norm = 1.0 if self._double else float(self.inv_norm_factor)
         ksp = ksp.reshape(B, C, K)
         raw = self.raw_op
         dens = self._density_d
         if self._spread_only:
             if img is None:
-                img = torch.empty((B, C, *XYZ), dtype=torch.complex64, device=self.device)
+                img = torch.empty((B, C, *XYZ), dtype=self._cdt, device=self.device)
             img = img.view(B, C, *XYZ)
             for b in range(B):
                 for c0, c1 in self._chunks():
@@ -423,7 +440,7 @@ class MRIB200NUFFT(FourierOperatorBase):
             return img
         if self.uses_sense:
             if img is None:
-                img = torch.empty((B, 1, *XYZ), dtype=torch.complex64, device=self.device)
+                img = torch.empty((B, 1, *XYZ), dtype=self._cdt, device=self.device)
             img = img.view(B, 1, *XYZ)
             for b in range(B):
                 for i, (c0, c1) in enumerate(self._chunks()):
@@ -431,12 +448,14 @@ class MRIB200NUFFT(FourierOperatorBase):
                               scale=inv_norm, conj_smaps=self._conj_smaps)
         else:
             if img is None:
-                img = torch.empty((B, C, *XYZ), dtype=torch.complex64, device=self.device)
+                img = torch.empty((B, C, *XYZ), dtype=self._cdt, device=self.device)
             img = img.view(B, C, *XYZ)
             for b in range(B):
                 for c0, c1 in self._chunks():
                     raw.type1(ksp[b, c0:c1], dens, None, img[b, c0:c1], accumulate=False,
                               scale=inv_norm)
+        if self._double:
+            img *= float(self.inv_norm_factor)
         return img
 
     def _dc_device(self, img: torch.Tensor, obs: torch.Tensor) -> torch.Tensor:
@@ -447,11 +466,11 @@ class MRIB200NUFFT(FourierOperatorBase):
         raw = self.raw_op
         dens = self._density_d
         dptr = 0 if dens is None else dens.data_ptr()
-        if self._spread_only or raw.isign_flip or self._conj_smaps:
+        if self._spread_only or raw.isign_flip or self._conj_smaps or self._double:
             return self._adj_device(self._op_device(img) - obs)
         if self.uses_sense:
             img = img.reshape(B, *XYZ)
-            grad = torch.empty((B, 1, *XYZ), dtype=torch.complex64, device=self.device)
+            grad = torch.empty((B, 1, *XYZ), dtype=self._cdt, device=self.device)
             for b in range(B):
                 for i, (c0, c1) in enumerate(self._chunks()):
                     raw.plan.data_consistency(
@@ -459,7 +478,7 @@ class MRIB200NUFFT(FourierOperatorBase):
                         dptr, grad[b, 0].data_ptr(), c1 - c0, int(i > 0), inv_norm, self.stream)
         else:
             img = img.reshape(B, C, *XYZ)
-            grad = torch.empty((B, C, *XYZ), dtype=torch.complex64, device=self.device)
+            grad = torch.empty((B, C, *XYZ), dtype=self._cdt, device=self.device)
             for b in range(B):
                 for c0, c1 in self._chunks():
                     raw.plan.data_consistency(
@@ -477,7 +496,7 @@ class MRIB200NUFFT(FourierOperatorBase):
         img, kind, dev = self._in(data)
         out = None
         if ksp is not None and module_name(ksp) == "torch" and ksp.is_cuda and ksp.is_contiguous() \
-                and ksp.dtype == torch.complex64 and ksp.device == self.device:
+                and ksp.dtype == self._cdt and ksp.device == self.device:
             out = ksp
         res = self._op_device(img, out)
         res = self._safe_squeeze(res)
@@ -492,7 +511,7 @@ class MRIB200NUFFT(FourierOperatorBase):
         ksp, kind, dev = self._in(coeffs)
         out = None
         if img is not None and module_name(img) == "torch" and img.is_cuda and img.is_contiguous() \
-                and img.dtype == torch.complex64 and img.device == self.device:
+                and img.dtype == self._cdt and img.device == self.device:
             out = img
         res = self._adj_device(ksp, out)
         res = self._safe_squeeze(res)
@@ -513,7 +532,7 @@ class MRIB200NUFFT(FourierOperatorBase):
         img, _, _ = self._in(image)
         T = int(np.prod(img.shape[: img.ndim - len(self.shape)])) if img.ndim > len(self.shape) else 1
         img = img.reshape(T, *self.shape)
-        out = torch.empty((T, self.n_samples), dtype=torch.complex64, device=self.device)
+        out = torch.empty((T, self.n_samples), dtype=self._cdt, device=self.device)
         step = self.raw_op.n_trans
         for t0 in range(0, T, step):
             if self._spread_only:
@@ -530,7 +549,7 @@ class MRIB200NUFFT(FourierOperatorBase):
         ksp, _, _ = self._in(coeffs)
         ksp = ksp.reshape(-1, self.n_samples)
         T = ksp.shape[0]
-        out = torch.empty((T, *self.shape), dtype=torch.complex64, device=self.device)
+        out = torch.empty((T, *self.shape), dtype=self._cdt, device=self.device)
         step = self.raw_op.n_trans
         for t0 in range(0, T, step):
             k = ksp[t0:t0 + step]
@@ -559,7 +578,7 @@ class MRIB200NUFFT(FourierOperatorBase):
         self._n_batchs = 1
         try:
             x = np.random.random(self.shape).astype(np.complex64)
-            x = to_device(x, self.device, torch.complex64)
+            x = to_device(x, self.device, self._cdt)
             x_norm = torch.linalg.norm(x)
             x = x / x_norm
             x_new_norm = x_norm
@@ -574,7 +593,7 @@ class MRIB200NUFFT(FourierOperatorBase):
                 x = x_new
             if i == max_iter - 1:
                 warnings.warn("Lipschitz constant did not converge")
-            return np.float32(x_new_norm.item())
+            return (np.float64 if self._double else np.float32)(x_new_norm.item())
         finally:
             self._n_coils, self._n_batchs, self._smaps, self._smaps_d, self.squeeze_dims = saved
 
@@ -600,6 +619,9 @@ class MRIB200NUFFT(FourierOperatorBase):
         """
         if self.ndim not in (2, 3):
             raise ValueError(f"Toeplitz kernel calculation not implemented for ndim={self.ndim}")
+        if self._double:
+            raise ValueError("the device Toeplitz path is single precision (gram_op falls back to the "
+                             "reference construction for precision='double')")
         if any(s % 2 for s in self.shape):
             raise ValueError(f"Toeplitz kernel computation only supports even grid sizes, got {self.shape}.")
         if self._spread_only:
@@ -632,14 +654,14 @@ class MRIB200NUFFT(FourierOperatorBase):
         plan = self.raw_op.plan
         if self.uses_sense:
             img = img.reshape(B, *XYZ)
-            out = torch.empty((B, 1, *XYZ), dtype=torch.complex64, device=self.device)
+            out = torch.empty((B, 1, *XYZ), dtype=self._cdt, device=self.device)
             for b in range(B):
                 for i, (c0, c1) in enumerate(self._chunks()):
                     plan.toeplitz_apply(img[b].data_ptr(), self._smaps_d[c0:c1].data_ptr(), kern.data_ptr(),
                                         out[b, 0].data_ptr(), c1 - c0, int(i > 0), scale, self.stream)
         else:
             img = img.reshape(B, C, *XYZ)
-            out = torch.empty((B, C, *XYZ), dtype=torch.complex64, device=self.device)
+            out = torch.empty((B, C, *XYZ), dtype=self._cdt, device=self.device)
             for b in range(B):
                 for c0, c1 in self._chunks():
                     plan.toeplitz_apply(img[b, c0:c1].data_ptr(), 0, kern.data_ptr(),
@@ -652,7 +674,8 @@ class MRIB200NUFFT(FourierOperatorBase):
         self.check_shape(image=data)
         if not toeplitz:
             return self.adj_op(self.op(data))
-        if tuple(self.raw_op.plan.nf) != tuple(2 * s for s in self.shape) or self.ndim not in (2, 3):
+        if tuple(self.raw_op.plan.nf) != tuple(2 * s for s in self.shape) or self.ndim not in (2, 3) \
+                or self._double:
             # oversampled grid is not exactly 2N: reference construction on top of op / adj_op
             from mrinufft.operators.toeplitz import compute_toeplitz_kernel as _ref_kernel
 

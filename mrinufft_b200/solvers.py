@@ -41,7 +41,8 @@ def cg(
     """Fixed-step Polak-Ribiere conjugate gradient on ``data_consistency`` (optim.py:801-902)."""
     dev = operator.device
     kind, kdev = describe(kspace_data)
-    y = to_device(kspace_data, dev, torch.complex64)
+    cdt = getattr(operator, "_cdt", torch.complex64)
+    y = to_device(kspace_data, dev, cdt)
     lipschitz_cst = float(operator.get_lipschitz_cst())
 
     def _scaled_dcp():  # optim.py:151-165
@@ -53,7 +54,7 @@ def cg(
         return reduce_fn(v) if reduce_fn is not None else v
 
     old_density = None
-    xi = None if x_init is None else to_device(x_init, dev, torch.complex64)
+    xi = None if x_init is None else to_device(x_init, dev, cdt)
     if operator.uses_density:
         if xi is None:
             xi = _scaled_dcp()
@@ -62,8 +63,8 @@ def cg(
         operator.density = None
     try:
         full = operator.img_full_shape
-        image = torch.zeros(full, dtype=torch.complex64, device=dev) if xi is None else xi.reshape(full).clone()
-        x0_d = None if x0 is None else to_device(x0, dev, torch.complex64).reshape(full)
+        image = torch.zeros(full, dtype=cdt, device=dev) if xi is None else xi.reshape(full).clone()
+        x0_d = None if x0 is None else to_device(x0, dev, cdt).reshape(full)
         velocity = torch.zeros_like(image)
 
         def _grad(img):

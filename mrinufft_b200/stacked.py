@@ -43,7 +43,7 @@ class MRIB200StackedNUFFT(MRIStackedNUFFT):
         if self.smaps is None:
             return None
         if self._smaps_dev is None or self._smaps_dev[0] is not self.smaps:
-            self._smaps_dev = (self.smaps, to_device(self.smaps, self._dev, torch.complex64)
+            self._smaps_dev = (self.smaps, to_device(self.smaps, self._dev, self.operator._cdt)
                                .reshape(self.n_coils, *self.shape))
         return self._smaps_dev[1]
 
@@ -66,7 +66,7 @@ class MRIB200StackedNUFFT(MRIStackedNUFFT):
         B, C, XYZ = self.n_batchs, self.n_coils, self.shape
         NS, NZ = len(self._samples2d), len(self.z_index)
         zsel = self._zsel()
-        ksp = torch.empty((B, C * NZ, NS), dtype=torch.complex64, device=self._dev)
+        ksp = torch.empty((B, C * NZ, NS), dtype=self.operator._cdt, device=self._dev)
         sm = self._smaps_d()
         img = img.reshape(B, 1 if sm is not None else C, *XYZ)
         for b in range(B):
@@ -83,10 +83,10 @@ class MRIB200StackedNUFFT(MRIStackedNUFFT):
         zsel = self._zsel()
         sm = self._smaps_d()
         ksp = ksp.reshape(B, C * NZ, NS)
-        out = torch.empty((B, 1 if sm is not None else C, *XYZ), dtype=torch.complex64, device=self._dev)
+        out = torch.empty((B, 1 if sm is not None else C, *XYZ), dtype=self.operator._cdt, device=self._dev)
         for b in range(B):
             planes = self.operator._adj_device(ksp[b:b + 1].contiguous())  # (1, C*NZ, X, Y)
-            imgz = torch.zeros((C, *XYZ), dtype=torch.complex64, device=self._dev)
+            imgz = torch.zeros((C, *XYZ), dtype=self.operator._cdt, device=self._dev)
             imgz.index_copy_(-1, zsel, planes.reshape(C, NZ, *XYZ[:2]).permute(0, 2, 3, 1))
             imgc = self._ifftz_d(imgz)
             out[b] = torch.sum(imgc * torch.conj(sm), dim=0, keepdim=True) if sm is not None else imgc

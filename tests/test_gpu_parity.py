@@ -741,3 +741,34 @@ def test_rows_fallback_when_stream_does_not_fit(mods):
     op2.raw_op._set_pts(op2.samples)
     assert rel_l2(op2.op(g["img"]), ref_y) <= 2e-6 and rel_l2(op2.adj_op(g["ksp"]), ref_x) <= 2e-6
     assert rel_l2(op2.op(g["img"]), g["op"]) <= 5e-6
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case,eps,tol", [("random2D_sense", 1e-6, 5e-6), ("random3D", 1e-6, 5e-6),
+                                          ("random2D", 1e-11, 2e-10), ("cones3D", 1e-10, 2e-9)])
+def test_double_precision_path_matches_reference_ndft(mods, case, eps, tol):
+    """`precision="double"` (complex128 kernels, B200_DOUBLE plans) against the reference's NDFT goldens:
+    the same bar as single precision at eps = 1e-6, and the accuracy only double can reach at small eps
+    (rel-L2 within ~20 eps of the exact transform).  Outputs are complex128, inputs are not mutated."""
+    mrinufft, _, torch = mods
+    g = load_golden(case)
+    op = mrinufft.get_operator("b200")(
+        g["samples"].astype(np.float64), g["shape"], n_coils=g["n_coils"], smaps=g.get("smaps"),
+        squeeze_dims=False, eps=eps, precision="double")
+    assert op.cpx_dtype == np.complex128 and op.samples.dtype == np.float64
+    # exact transforms of the float64 samples (the goldens were made with float32 sample values, which
+    # convert exactly): evaluate the NDFT with the reference's numpy backend in double
+    ref = mrinufft.get_operator("numpy")(g["samples"].astype(np.float64), g["shape"], n_coils=g["n_coils"],
+                                         smaps=g.get("smaps"))
+    ref.squeeze_dims = False
+    img = g["img"].astype(np.complex128)
+    ksp = g["ksp"].astype(np.complex128)
+    y, x = op.op(img), op.adj_op(ksp)
+    assert y.dtype == np.complex128 and x.dtype == np.complex128
+    assert rel_l2(y, ref.op(img)) <= tol and rel_l2(x, ref.adj_op(ksp)) <= tol
+    dc = op.data_consistency(img, ksp)
+    assert rel_l2(dc, ref.adj_op(ref.op(img) - ksp)) <= 2 * tol
+    lhs, rhs = np.vdot(y.ravel(), ksp.ravel()), np.vdot(img.ravel(), x.ravel())
+    assert abs(lhs - rhs) <= 1e-12 * abs(lhs)
+    yt = op.op(torch.from_numpy(img).cuda())
+    assert yt.is_cuda and yt.dtype == torch.complex128
