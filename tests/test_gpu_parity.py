@@ -772,3 +772,35 @@ def test_double_precision_path_matches_reference_ndft(mods, case, eps, tol):
     assert abs(lhs - rhs) <= 1e-12 * abs(lhs)
     yt = op.op(torch.from_numpy(img).cuda())
     assert yt.is_cuda and yt.dtype == torch.complex128
+
+
+@pytest.mark.gpu
+def test_empty_tile_skipping_follows_update_samples(mods):
+    """On 3-D power-of-two grids tiles without visitors are neither written by the spreader nor read by the
+    FFT (and not written by the type-2 FFT): the bit strings must follow `update_samples`.  A compact
+    trajectory (most tiles empty) is replaced by a full one and vice versa; results must equal those of
+    freshly built operators, for both transform types, with coil chunks (accumulate) and SENSE."""
+    mrinufft, _, _ = mods
+    rng = np.random.default_rng(21)
+    shape, C, M = (32, 32, 32), 5, 6000
+    compact = (0.12 * rng.standard_normal((M, 3))).clip(-0.49, 0.49).astype(np.float32)
+    full = rng.uniform(-0.5, 0.5, (M, 3)).astype(np.float32)
+    smaps = (rng.standard_normal((C, *shape)) + 1j * rng.standard_normal((C, *shape))).astype(np.complex64)
+    smaps /= np.linalg.norm(smaps, axis=0)
+    img = (rng.standard_normal((1, 1, *shape)) + 1j * rng.standard_normal((1, 1, *shape))).astype(np.complex64)
+    ksp = (rng.standard_normal((1, C, M)) + 1j * rng.standard_normal((1, C, M))).astype(np.complex64)
+    kw = dict(n_coils=C, smaps=smaps, squeeze_dims=False, coil_chunk=2)
+    op = mrinufft.get_operator("b200")(compact, shape, **kw)
+    for a, b in ((compact, full), (full, compact)):
+        op.update_samples(a)
+        _ = op.op(img), op.adj_op(ksp)
+        op.update_samples(b)
+        fresh = mrinufft.get_operator("b200")(b, shape, **kw)
+        assert rel_l2(op.op(img), fresh.op(img)) <= 1e-6
+        assert rel_l2(op.adj_op(ksp), fresh.adj_op(ksp)) <= 1e-6
+        assert rel_l2(op.data_consistency(img, ksp), fresh.data_consistency(img, ksp)) <= 1e-6
+    # ... and the compact case against the exact NDFT (sampled): adjointness is the cheap strong check
+    op.update_samples(compact)
+    y, x = op.op(img), op.adj_op(ksp)
+    lhs, rhs = np.vdot(y.ravel(), ksp.ravel()), np.vdot(img.ravel(), x.ravel())
+    assert abs(lhs - rhs) <= 5e-5 * abs(lhs)
