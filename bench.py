@@ -226,6 +226,9 @@ def run_b200(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        # NCCL prints its version banner (and any NCCL_DEBUG output) to stdout by default: keep stdout
+        # for the one JSON line of the contract
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     if not mrinufft_b200.MRIB200NUFFT.available:
         raise RuntimeError("b200 backend unavailable (libb200nufft.so missing or no GPU): no fallback")
