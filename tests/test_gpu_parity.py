@@ -544,7 +544,8 @@ def test_odd_grid_sizes_wrap(mods, shape):
 # ------------------------------------------------------------------ fused zero-padding-aware FFT passes
 @pytest.mark.parametrize("shape,C,sense", [((32, 64), 3, True), ((16, 128), 1, False), ((16, 32, 64), 3, True),
                                            ((64, 16, 32), 2, False), ((128, 128, 128), 2, True),
-                                           ((16, 256), 3, True), ((16, 16, 256), 2, False)])
+                                           ((16, 256), 3, True), ((16, 16, 256), 2, False),
+                                           ((256, 16), 2, True), ((256, 16, 16), 3, True), ((16, 256, 32), 2, False)])
 def test_pruned_fft_matches_cufft_path_and_oracle(mods, shape, C, sense):
     """Power-of-two grids take the fused pad/crop + pruned FFT passes (option key 2 = 2); they must
     agree with the cuFFT + k_pad/k_crop path (key 2 = 1) and with the CPU oracle, both signs, SENSE
