@@ -643,7 +643,10 @@ k_rows(Geom g, int T, int nchunks, unsigned S, long long M, const uint4* __restr
     const unsigned base = (unsigned)c * LCH;
     const uint4* v = ent + base;
     const int nw = (int)min((unsigned)LCH, S - base);
-    const int nsub = (nw + VBLK - 1) / VBLK;
+    // consume blocks: 16 entries for the spreader (the granularity of its value copies), a whole packet
+    // block of 32 for the interpolator (half the per-block bookkeeping)
+    constexpr int SB = SPREAD ? VBLK : MBLK, SPB = MBLK / SB;
+    const int nsub = (nw + SB - 1) / SB;
     // is the entry behind the chunk a header (or the end of the stream)?  Then the last tile ends here.
     const bool tail_whole = __ldg(reinterpret_cast<const unsigned*>(v + nw) + 2) == IDX_HDR;
 
@@ -811,9 +814,9 @@ k_rows(Geom g, int T, int nchunks, unsigned S, long long M, const uint4* __restr
 #pragma unroll 1
     for (int j = 0; j < nsub; ++j) {
       const bool more = j + 1 < nsub;
-      const bool new_block = more && ((j + 1) & 1) == 0;
+      const bool new_block = more && ((j + 1) % SPB) == 0;
       if (new_block) {
-        const int nb = (j + 1) >> 1;
+        const int nb = (j + 1) / SPB;
         is_val = is_nxt;
         is_nxt = load_is(nb + 1);
         prefetch_stream(nb + 3);
@@ -826,12 +829,12 @@ k_rows(Geom g, int T, int nchunks, unsigned S, long long M, const uint4* __restr
       if (more) cp_async_wait<1>();
       else cp_async_wait<0>();
       __syncwarp();
-      const int n = min(VBLK, nw - j * VBLK);
-      const unsigned pk_a = meta_a + (unsigned)((((j >> 1) & 1) * MBLK + (j & 1) * VBLK) * 48);
+      const int n = min(SB, nw - j * SB);
+      const unsigned pk_a = meta_a + (unsigned)((((j / SPB) & 1) * MBLK + (j % SPB) * SB) * 48);
       const unsigned vb_a = vbuf_a + (unsigned)((j & 1) * VBLK * 32 + lane) * 8u;
 
       // the sub-block is a sequence of visit runs separated by header entries
-      unsigned hm = (hb_cur >> ((j & 1) * VBLK)) & 0xffffu;
+      unsigned hm = SPB == 1 ? hb_cur : ((hb_cur >> ((j % SPB) * SB)) & 0xffffu);
       int k0 = 0;
       for (;;) {
         const int k1 = hm ? (__ffs(hm) - 1) : n;
