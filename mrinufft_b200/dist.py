@@ -7,7 +7,9 @@ the sensitivity maps and of the k-space data.  Collectives (NCCL over NVLink on 
 the CPU tests) are needed only where the path has a real exchange step:
 
 * SENSE ``adj_op`` / ``data_consistency``: one all-reduce(sum) of the coil-combined image;
-* ``cg`` on calibrationless (coil-sharded) iterates: scalar all-reduces of the inner products;
+* ``pinv_solver`` (``cg`` / ``lsqr`` / ``lsmr``, ``mrinufft_b200.solvers``): scalar all-reduces of the
+  k-space norms, and of the image-domain inner products when the iterate is coil-sharded
+  (calibrationless); the Lipschitz constant of ``cg`` is broadcast from rank 0;
 * ``op`` and calibrationless ``adj_op``: no communication (results stay sharded by coil).
 
 ``local_factory`` builds the rank-local operator; the default is ``MRIB200NUFFT``.  The CPU tests
@@ -80,12 +82,8 @@ class CoilShardedOperator:
             dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
 
     def reduce_scalar(self, v: torch.Tensor) -> torch.Tensor:
-        """Sum a 0-d tensor over ranks (CG inner products on coil-sharded iterates)."""
-        if self.uses_sense:
-            return v  # the iterate is replicated: local dots are already global
-        v = v.clone()
-        self._allreduce_tensor(v.reshape(1))
-        return v
+        """Sum an image-domain scalar over ranks (inner products on coil-sharded iterates)."""
+        return self.reduce_img(v)
 
     # -- operator surface ---------------------------------------------------------------------
     def op(self, image):
@@ -104,6 +102,71 @@ class CoilShardedOperator:
         if self.uses_sense and self.world > 1:
             g = self._allreduce(g)
         return g
+
+    # -- device-level surface and reductions used by mrinufft_b200.solvers -------------------------
+    @property
+    def density(self):
+        return self.local.density
+
+    @density.setter
+    def density(self, value):
+        self.local.density = value
+
+    def _op_device(self, img):
+        return self.local._op_device(img)
+
+    def _adj_device(self, ksp):
+        img = self.local._adj_device(ksp)
+        if self.uses_sense and self.world > 1:
+            self._allreduce_tensor(img)
+        return img
+
+    def _dc_device(self, img, obs):
+        g = self.local._dc_device(img, obs)
+        if self.uses_sense and self.world > 1:
+            self._allreduce_tensor(g)
+        return g
+
+    def reduce_ksp(self, v: torch.Tensor) -> torch.Tensor:
+        """Sum k-space-domain scalars over ranks (k-space is always sharded by coil)."""
+        if self.world == 1:
+            return v
+        v = v.clone()
+        self._allreduce_tensor(v.reshape(-1))
+        return v
+
+    def reduce_img(self, v: torch.Tensor) -> torch.Tensor:
+        """Sum image-domain scalars over ranks: a no-op for the replicated SENSE image."""
+        if self.uses_sense or self.world == 1:
+            return v
+        v = v.clone()
+        self._allreduce_tensor(v.reshape(-1))
+        return v
+
+    def get_lipschitz_cst(self, max_iter=10):
+        """Rank 0's power-method estimate, broadcast: the single-coil operator is the same on every
+        rank but the power method starts from an unseeded random image (base.py:1194), and the CG
+        step size must be identical everywhere or the replicated iterates drift apart."""
+        lip = float(self.local.get_lipschitz_cst(max_iter))
+        if self.world > 1:
+            t = torch.tensor([lip], dtype=torch.float64, device=getattr(self.local, "device", "cpu"))
+            src = 0 if self.group is None else dist.get_global_rank(self.group, 0)
+            dist.broadcast(t, src=src, group=self.group)
+            lip = float(t.item())
+        return lip
+
+    def pinv_solver(self, ksp_local, optim="lsqr", **kwargs):
+        """``pinv_solver`` on this rank's k-space slice (base.py:667-690): device-resident solvers with
+        the inner products all-reduced.  SENSE: the image is identical on every rank; calibrationless:
+        every rank gets the images of its own coils."""
+        from .solvers import SOLVERS
+
+        if optim not in SOLVERS:
+            raise ValueError(f"coil-sharded pinv_solver supports {sorted(SOLVERS)}, got {optim!r}")
+        if optim == "cg":
+            kwargs.setdefault("lipschitz_cst", self.get_lipschitz_cst())
+            return SOLVERS[optim](self, ksp_local, reduce_fn=self.reduce_img, reduce_ksp=self.reduce_ksp, **kwargs)
+        return SOLVERS[optim](self, ksp_local, reduce_ksp=self.reduce_ksp, reduce_img=self.reduce_img, **kwargs)
 
     def gather_kspace(self, ksp_local):
         """All-gather the coil-sharded k-space (only if the caller wants it on every rank)."""

@@ -598,13 +598,13 @@ class MRIB200NUFFT(FourierOperatorBase):
             self._n_coils, self._n_batchs, self._smaps, self._smaps_d, self.squeeze_dims = saved
 
     def pinv_solver(self, kspace_data, optim="lsqr", **kwargs):
-        """Solve ``A x = y`` (base.py:667-690).  ``optim="cg"`` runs device resident
-        (``solvers.cg``); other optimisers use the reference implementations on top of this
-        operator's ``op`` / ``adj_op``."""
-        if optim == "cg":
-            from .solvers import cg
+        """Solve ``A x = y`` (base.py:667-690).  ``cg``, ``lsqr`` and ``lsmr`` run device resident
+        (``mrinufft_b200.solvers``, iterate-level mirrors of ``extras/optim.py``); any other
+        registered optimiser uses the reference implementation on top of ``op`` / ``adj_op``."""
+        from .solvers import SOLVERS
 
-            return cg(self, kspace_data, **kwargs)
+        if isinstance(optim, str) and optim in SOLVERS:
+            return SOLVERS[optim](self, kspace_data, **kwargs)
         return super().pinv_solver(kspace_data, optim=optim, **kwargs)
 
     # ------------------------------------------------------------------ Toeplitz Gram operator

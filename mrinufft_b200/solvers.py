@@ -1,17 +1,33 @@
-"""Device-resident conjugate gradient for ``MRIB200NUFFT.pinv_solver(optim="cg")``.
+"""Device-resident iterative solvers behind ``MRIB200NUFFT.pinv_solver`` (``cg``, ``lsqr``, ``lsmr``).
 
-Mirrors ``mrinufft.extras.optim.cg`` (``src/mrinufft/extras/optim.py:801-902``) statement by
-statement, including its quirks: the Polak-Ribiere ``beta`` is built from the
-UN-conjugated dot product (``xp.dot``), ``max(0, beta)`` follows numpy's lexicographic ordering of
-complex numbers, the first step is ``velocity = tol*velocity + grad/L``, and the stop test is on the
-un-normalised ``||grad_new|| <= tol``.  The reference runs it through ``with_numpy_cupy`` (host
-round trips per iteration without cupy); here the iterate, the k-space data and all reductions stay
-on the device, the gradient is the fused ``b200_data_consistency`` call.
+The reference's solvers (``src/mrinufft/extras/optim.py``: ``lsqr`` 249-495, ``lsmr`` 498-798, ``cg``
+801-902) run through ``with_numpy_cupy``: without cupy every ``op`` / ``adj_op`` of every iteration is
+a host round trip of the whole k-space batch.  Here the iterates, the k-space data and all vector
+updates stay on the device; only the per-batch scalars (a handful of floats per iteration) come to
+the host, where the Givens-rotation recurrences run in numpy exactly as in the reference.
 
-With coil-sharded operators (``mrinufft_b200.dist``) the reductions go through ``reduce_fn``.
+Iterate-level parity is the contract (tests/test_solvers_cpu.py compares iterate by iterate against
+the reference on its exact-NDFT backend), so the reference's quirks are kept:
+
+* ``cg``: the Polak-Ribiere ``beta`` is built from the UN-conjugated dot product (``xp.dot``),
+  ``max(0, beta)`` follows numpy's lexicographic ordering of complex numbers, the first step is
+  ``velocity = tol*velocity + grad/L``, the stop test is on the un-normalised ``||grad_new|| <= tol``,
+  and the step size comes from the density-weighted operator while the iteration runs un-weighted.
+* ``lsqr`` / ``lsmr``: the plane rotations are decided for the whole batch at once (``any`` over the
+  batch), ``lsmr`` never advances its iteration counter (so ``minrbar`` keeps its initial 1e100 and
+  the condition estimate is ``mean(max(maxrbar, rhotemp) / rhotemp)``), and with a density the start
+  is the scaled density-compensated adjoint while the iteration itself is un-weighted.
+  NOT mirrored: the reference forgets to restore ``operator.density`` when a callback is supplied
+  (early ``return`` before the restore, optim.py:491-495, 794-798).
+
+With coil-sharded operators (``mrinufft_b200.dist``) squared norms / dot products of k-space vectors
+go through ``reduce_ksp`` and those of coil-sharded (calibrationless) images through ``reduce_img``:
+one small all-reduce each.
 """
 
 from __future__ import annotations
+
+import contextlib
 
 import numpy as np
 import torch
@@ -19,6 +35,7 @@ import torch
 from ._arrays import describe, from_device, to_device
 
 
+# ---------------------------------------------------------------------------------------- helpers
 def _lex_max0(beta: complex) -> complex:
     """``max(0, beta)`` with numpy's complex ordering: keep beta iff Re>0 or (Re==0 and Im>0)."""
     if beta.real > 0 or (beta.real == 0 and beta.imag > 0):
@@ -26,6 +43,406 @@ def _lex_max0(beta: complex) -> complex:
     return 0.0
 
 
+def _ident(v):
+    return v
+
+
+class _Ctx:
+    """What the solvers need from an operator: device, dtypes, shapes, the device-level transforms."""
+
+    def __init__(self, operator, kspace_data, reduce_ksp=None, reduce_img=None):
+        self.op = operator
+        self.dev = operator.device
+        self.cdt = getattr(operator, "_cdt", torch.complex64)
+        self.rnp = np.float64 if self.cdt == torch.complex128 else np.float32
+        self.kind, self.kdev = describe(kspace_data)
+        self.full_img = tuple(operator.img_full_shape)
+        self.full_ksp = tuple(operator.ksp_full_shape)
+        self.reduce_ksp = reduce_ksp or _ident
+        self.reduce_img = reduce_img or _ident
+        self.y = to_device(kspace_data, self.dev, self.cdt).reshape(self.full_ksp)
+
+    def A(self, x):
+        return self.op._op_device(x.reshape(self.full_img)).reshape(self.full_ksp)
+
+    def AH(self, y):
+        return self.op._adj_device(y.reshape(self.full_ksp)).reshape(self.full_img)
+
+    def image(self, arr):
+        return to_device(arr, self.dev, self.cdt).reshape(self.full_img)
+
+    def out(self, x):
+        return from_device(x, self.kind, self.kdev)
+
+    # per-batch 2-norms (optim.py:57-58) as a host (B,) array of the operator's real precision
+    def _norm(self, t, reduce):
+        sq = torch.sum(t.real.reshape(t.shape[0], -1) ** 2 + t.imag.reshape(t.shape[0], -1) ** 2, dim=1)
+        return np.sqrt(reduce(sq).cpu().numpy().astype(self.rnp))
+
+    def knorm(self, t):
+        return self._norm(t, self.reduce_ksp)
+
+    def inorm(self, t):
+        return self._norm(t, self.reduce_img)
+
+    # host (B,) scalars -> device tensor that broadcasts from the left (``_bc_left``, optim.py:68-86)
+    def bc(self, s, like):
+        s = np.array(np.broadcast_to(np.asarray(s, dtype=self.rnp), (like.shape[0],)))
+        t = torch.from_numpy(s).to(like.device)
+        return t.reshape(-1, *([1] * (like.ndim - 1)))
+
+    def scaled_dcp(self):
+        """Scaled density-compensated adjoint (``_scaled_dcp``, optim.py:151-165)."""
+        xi = self.AH(self.y)
+        yy = self.A(xi)
+        num = torch.sqrt(self.reduce_ksp(torch.sum(self.y.real ** 2 + self.y.imag ** 2)))
+        den = torch.sqrt(self.reduce_ksp(torch.sum(yy.real ** 2 + yy.imag ** 2)))
+        return xi * (num / den)
+
+
+@contextlib.contextmanager
+def _density_off(operator):
+    """The solvers iterate on the un-weighted operator (optim.py:838-842) -- always restored."""
+    saved = operator.density if operator.uses_density else None
+    if saved is not None:
+        operator.density = None
+    try:
+        yield
+    finally:
+        if saved is not None:
+            operator.density = saved
+
+
+def _givens(a, b):
+    """Plane rotation ``(c, s, r)`` with ``c a + s b = r`` in the overflow-safe form of Choi's
+    SymOrtho, evaluated like ``_sym_ortho`` (optim.py:213-246): which of the four formulas is used
+    is decided for the whole batch (``any`` over its entries)."""
+    a = np.asarray(a)
+    b = np.asarray(b)
+    if np.any(b == 0):
+        return np.sign(a), 0, np.abs(a)
+    if np.any(a == 0):
+        return 0, np.sign(b), np.abs(b)
+    if np.any(np.abs(b) > np.abs(a)):
+        t = a / b
+        s = np.sign(b) / np.sqrt(1 + t * t)
+        return s * t, s, b / s
+    t = b / a
+    c = np.sign(a) / np.sqrt(1 + t * t)
+    return c, c * t, a / c
+
+
+class _Bidiag:
+    """Golub-Kahan bidiagonalisation shared by ``lsqr`` and ``lsmr``: ``u`` (k-space) and ``v`` (image)
+    live on the device, ``alpha`` / ``beta`` per batch on the host.
+
+    ``start`` is the common prologue (optim.py:354-385 and 600-625), ``step`` the first lines of both
+    loops (optim.py:402-414 and 669-680).
+    """
+
+    def __init__(self, ctx: _Ctx, x0_d):
+        self.c = ctx
+        self.u = ctx.y.clone()
+        self.bnorm = ctx.knorm(self.u)
+        self.beta = self.bnorm.copy()
+        if x0_d is not None:
+            self.u -= ctx.A(x0_d)
+            self.beta = ctx.knorm(self.u)
+        self.v = None
+        self.alpha = None
+
+    def start(self, x):
+        c = self.c
+        if np.all(self.beta) > 0:
+            self.u /= c.bc(self.beta, self.u)
+            self.v = c.AH(self.u)
+            self.alpha = c.inorm(self.v)
+        else:
+            self.v = x.clone()
+            self.alpha = np.zeros(self.v.shape[0], dtype=c.rnp)
+        if np.any((self.alpha * self.beta) == 0):
+            return False
+        if np.all(self.alpha) > 0:
+            self.v /= c.bc(self.alpha, self.v)
+        return True
+
+    def step(self):
+        """Next pair of Lanczos vectors.  Returns True when the ``beta > 0`` branch ran."""
+        c = self.c
+        self.u *= -c.bc(self.alpha, self.u)
+        self.u += c.A(self.v)
+        self.beta = c.knorm(self.u)
+        if not (np.all(self.beta) > 0):
+            return False
+        self.u /= c.bc(self.beta, self.u)
+        return True
+
+    def step_v(self):
+        c = self.c
+        self.v *= -c.bc(self.beta, self.v)
+        self.v += c.AH(self.u)
+        self.alpha = c.inorm(self.v)
+        if np.all(self.alpha) > 0:
+            self.v /= c.bc(self.alpha, self.v)
+
+
+def _initial_iterate(ctx: _Ctx, x0, x_init):
+    """(x, x0_d): the starting image (a fresh device tensor) and the regularisation centre."""
+    x0_d = None if x0 is None else ctx.image(x0)
+    if x_init is not None:
+        x = ctx.image(x_init).clone()
+    elif x0_d is not None:
+        x = x0_d.clone()
+    else:
+        x = torch.zeros(ctx.full_img, dtype=ctx.cdt, device=ctx.dev)
+    return x, x0_d
+
+
+def _stop_code(test1, test2, test3, t1, rtol, atol, ctol):
+    """The six stopping rules shared by lsqr / lsmr (optim.py:466-479, 769-782)."""
+    if np.all(1 + test3 <= 1):
+        return 6
+    if np.all(1 + test2 <= 1):
+        return 5
+    if np.all(1 + t1 <= 1):
+        return 4
+    if np.all(test3 <= ctol):
+        return 3
+    if np.all(test2 <= atol):
+        return 2
+    if np.all(test1 <= rtol):
+        return 1
+    return 0
+
+
+def _finish(ctx: _Ctx, x, callback_returns):
+    if ctx.op.squeeze_dims:
+        x = ctx.op._safe_squeeze(x)
+    out = ctx.out(x)
+    if callback_returns:
+        return out, callback_returns
+    return out
+
+
+# ------------------------------------------------------------------------------------------- LSQR
+def lsqr(
+    operator,
+    kspace_data,
+    damp: float = 0.0,
+    atol: float = 1e-6,
+    btol: float = 1e-6,
+    conlim: float = 1e8,
+    max_iter: int = 100,
+    x0=None,
+    x_init=None,
+    callback=None,
+    progressbar=False,
+    reduce_ksp=None,
+    reduce_img=None,
+):
+    """LSQR (Paige & Saunders 1982) on ``argmin ||A x - y||^2 + damp^2 ||x - x0||^2`` (optim.py:249-495)."""
+    ctx = _Ctx(operator, kspace_data, reduce_ksp, reduce_img)
+    np_eps = np.finfo(ctx.rnp).eps
+    ctol = 1 / conlim if conlim > 0 else 0
+    with contextlib.ExitStack() as stack:
+        if operator.uses_density:
+            if x_init is None:
+                x_init = ctx.scaled_dcp()
+            stack.enter_context(_density_off(operator))
+        x, x0_d = _initial_iterate(ctx, x0, x_init)
+        gk = _Bidiag(ctx, x0_d)
+        bnorm = gk.bnorm
+        if not gk.start(x):
+            return ctx.out(x)
+        w = gk.v.clone()
+
+        alpha, beta = gk.alpha, gk.beta
+        rhobar = alpha
+        phibar = beta
+        ddnorm = res2 = xnorm = xxnorm = z = anorm = 0.0
+        dampsq = damp ** 2
+        cs2, sn2 = -1, 0.0
+        callback_returns = []
+        for _ in range(max_iter):
+            if gk.step():
+                beta = gk.beta
+                anorm = np.sqrt(anorm ** 2 + alpha ** 2 + beta ** 2 + dampsq)
+                gk.step_v()
+                alpha = gk.alpha
+            else:
+                beta = gk.beta
+            if damp:
+                rhobar1 = np.sqrt(rhobar ** 2 + dampsq)
+                cs1 = rhobar / rhobar1
+                sn1 = damp / rhobar1
+                psi = sn1 * phibar
+                phibar = cs1 * phibar
+            else:
+                rhobar1 = rhobar
+                psi = 0.0
+            # rotation that removes beta from the lower-bidiagonal matrix
+            cs, sn, rho = _givens(rhobar1, beta)
+            theta = sn * alpha
+            rhobar = -cs * alpha
+            phi = cs * phibar
+            phibar = sn * phibar
+            tau = sn * phi
+            t1 = phi / rho
+            t2 = -theta / rho
+
+            # x += (phi / rho) w ;  ||w / rho||^2 feeds the condition estimate ;  w = v - (theta / rho) w
+            ddnorm = ddnorm + (ctx.inorm(w) / np.abs(rho)) ** 2
+            x += ctx.bc(t1, w) * w
+            w *= ctx.bc(t2, w)
+            w += gk.v
+
+            # rotation on the right: estimate of ||x||
+            delta = sn2 * rho
+            gambar = -cs2 * rho
+            rhs = phi - delta * z
+            zbar = rhs / gambar
+            xnorm = np.sqrt(xxnorm + zbar ** 2)
+            gamma = np.sqrt(gambar ** 2 + theta ** 2)
+            cs2 = gambar / gamma
+            sn2 = theta / gamma
+            z = rhs / gamma
+            xxnorm = xxnorm + z ** 2
+
+            acond = anorm * np.sqrt(ddnorm)
+            res2 = res2 + psi ** 2
+            rnorm = np.sqrt(phibar ** 2 + res2)
+            arnorm = alpha * np.abs(tau)
+
+            test1 = rnorm / bnorm
+            test2 = arnorm / (anorm * rnorm + np_eps)
+            test3 = 1 / (acond + np_eps)
+            t1 = test1 / (1 + anorm * xnorm / bnorm)
+            rtol = btol + atol * anorm * xnorm / bnorm
+
+            if callback:
+                callback_returns.append(callback(ctx.out(x), operator, kspace_data, damp=damp, x0=x0))
+            if _stop_code(test1, test2, test3, t1, rtol, atol, ctol):
+                break
+    return _finish(ctx, x, callback_returns)
+
+
+# ------------------------------------------------------------------------------------------- LSMR
+def lsmr(
+    operator,
+    kspace_data,
+    damp: float = 0.0,
+    atol: float = 1e-6,
+    btol: float = 1e-6,
+    conlim: float = 1e8,
+    max_iter: int = 100,
+    x0=None,
+    x_init=None,
+    callback=None,
+    progressbar=False,
+    reduce_ksp=None,
+    reduce_img=None,
+):
+    """LSMR (Fong & Saunders 2011) on the same problem as :func:`lsqr` (optim.py:498-798)."""
+    ctx = _Ctx(operator, kspace_data, reduce_ksp, reduce_img)
+    ctol = 1 / conlim if conlim > 0 else 0
+    with contextlib.ExitStack() as stack:
+        if operator.uses_density:
+            if x_init is None:
+                x_init = ctx.scaled_dcp()
+            stack.enter_context(_density_off(operator))
+        x, x0_d = _initial_iterate(ctx, x0, x_init)
+        # the reference's lsmr subtracts A(x) of the STARTING iterate when x0 is given (optim.py:610-612)
+        gk = _Bidiag(ctx, x if x0 is not None else None)
+        normb = gk.bnorm
+        if not gk.start(x):
+            return ctx.out(x)
+        alpha, beta = gk.alpha, gk.beta
+        damp_b = np.full(x.shape[0], damp, np.float32)
+
+        zetabar = alpha * beta
+        alphabar = alpha
+        rho = rhobar = cbar = 1
+        sbar = 0
+        h = gk.v.clone()
+        hbar = torch.zeros_like(h)
+
+        # estimate of ||r||
+        betadd = beta
+        betad = 0
+        rhodold = 1
+        tautildeold = thetatilde = zeta = d = 0
+        # estimates of ||A|| and cond(A)
+        normA2 = alpha * alpha
+        maxrbar = 0
+        callback_returns = []
+        for _ in range(max_iter):
+            if gk.step():
+                gk.step_v()
+            alpha, beta = gk.alpha, gk.beta
+
+            chat, shat, alphahat = _givens(alphabar, damp_b)
+            rhoold = rho
+            c, s, rho = _givens(alphahat, beta)
+            thetanew = s * alpha
+            alphabar = c * alpha
+
+            # rotation Qbar_i: R_i^T -> R_i^bar
+            rhobarold = rhobar
+            zetaold = zeta
+            thetabar = sbar * rho
+            rhotemp = cbar * rho
+            cbar, sbar, rhobar = _givens(cbar * rho, thetanew)
+            zeta = cbar * zetabar
+            zetabar = -sbar * zetabar
+
+            # hbar = h - (thetabar rho / (rhoold rhobarold)) hbar ;  x += (zeta / (rho rhobar)) hbar ;
+            # h = v - (thetanew / rho) h
+            hbar *= ctx.bc(-(thetabar * rho / (rhoold * rhobarold)), hbar)
+            hbar += h
+            x += ctx.bc(zeta / (rho * rhobar), hbar) * hbar
+            h *= ctx.bc(-(thetanew / rho), h)
+            h += gk.v
+
+            # estimate of ||r||: rotations Qhat_{k,2k+1}, Q_{k,k+1}, Qtilde_{k-1}
+            betaacute = chat * betadd
+            betacheck = -shat * betadd
+            betahat = c * betaacute
+            betadd = -s * betaacute
+            thetatildeold = thetatilde
+            ctildeold, stildeold, rhotildeold = _givens(rhodold, thetabar)
+            thetatilde = stildeold * rhobar
+            rhodold = ctildeold * rhobar
+            betad = -stildeold * betad + ctildeold * betahat
+            tautildeold = (zetaold - thetatildeold * tautildeold) / rhotildeold
+            taud = (zeta - thetatilde * tautildeold) / rhodold
+            d = d + betacheck * betacheck
+            normr = np.sqrt(d + (betad - taud) ** 2 + betadd * betadd)
+
+            normA2 = normA2 + beta * beta
+            normA = np.sqrt(normA2)
+            normA2 = normA2 + alpha * alpha
+
+            # the reference's iteration counter stays at 0, so its minrbar keeps the initial 1e100
+            # (inf once cast to float32): min(minrbar, rhotemp) is rhotemp
+            maxrbar = np.max(np.maximum(maxrbar, rhobarold))
+            condA = np.mean(np.maximum(maxrbar, rhotemp) / rhotemp)
+
+            normar = np.abs(zetabar)
+            normx = ctx.inorm(x)
+            test1 = normr / normb
+            test2 = normar / (normA * normr) if np.all((normA * normr) != 0) else np.inf
+            test3 = 1 / condA
+            t1 = test1 / (1 + normA * normx / normb)
+            rtol = btol + atol * normA * normx / normb
+
+            if callback:
+                callback_returns.append(callback(ctx.out(x), operator, kspace_data, damp=damp_b, x0=x0))
+            if _stop_code(test1, test2, test3, t1, rtol, atol, ctol):
+                break
+    return _finish(ctx, x, callback_returns)
+
+
+# --------------------------------------------------------------------------------------------- CG
 def cg(
     operator,
     kspace_data,
@@ -37,34 +454,29 @@ def cg(
     progressbar=False,
     callback=None,
     reduce_fn=None,
+    lipschitz_cst=None,
+    reduce_ksp=None,
 ):
-    """Fixed-step Polak-Ribiere conjugate gradient on ``data_consistency`` (optim.py:801-902)."""
-    dev = operator.device
-    kind, kdev = describe(kspace_data)
-    cdt = getattr(operator, "_cdt", torch.complex64)
-    y = to_device(kspace_data, dev, cdt)
-    lipschitz_cst = float(operator.get_lipschitz_cst())
+    """Fixed-step Polak-Ribiere conjugate gradient on ``data_consistency`` (optim.py:801-902).
 
-    def _scaled_dcp():  # optim.py:151-165
-        xi = operator._adj_device(y)
-        yy = operator._op_device(xi)
-        return xi * torch.linalg.norm(y) / torch.linalg.norm(yy)
+    ``reduce_fn`` sums image-domain scalars over the ranks of a coil-sharded (calibrationless)
+    iterate; ``lipschitz_cst`` lets a sharded caller hand in the constant agreed between ranks.
+    """
+    ctx = _Ctx(operator, kspace_data, reduce_ksp, reduce_fn)
+    y, cdt, dev = ctx.y, ctx.cdt, ctx.dev
+    if lipschitz_cst is None:
+        lipschitz_cst = float(operator.get_lipschitz_cst())
+    _sum = ctx.reduce_img
 
-    def _sum(v):
-        return reduce_fn(v) if reduce_fn is not None else v
-
-    old_density = None
-    xi = None if x_init is None else to_device(x_init, dev, cdt)
-    if operator.uses_density:
-        if xi is None:
-            xi = _scaled_dcp()
-        old_density = operator.density
-        old_density_d = operator._density_d
-        operator.density = None
-    try:
-        full = operator.img_full_shape
+    xi = None if x_init is None else ctx.image(x_init)
+    with contextlib.ExitStack() as stack:
+        if operator.uses_density:
+            if xi is None:
+                xi = ctx.scaled_dcp()
+            stack.enter_context(_density_off(operator))
+        full = ctx.full_img
         image = torch.zeros(full, dtype=cdt, device=dev) if xi is None else xi.reshape(full).clone()
-        x0_d = None if x0 is None else to_device(x0, dev, cdt).reshape(full)
+        x0_d = None if x0 is None else ctx.image(x0)
         velocity = torch.zeros_like(image)
 
         def _grad(img):
@@ -90,18 +502,8 @@ def cg(
             image = image - velocity / lipschitz_cst
             grad = grad_new
             if callback:
-                img_cb = from_device(image, kind, kdev)
-                callbacks_results.append(callback(img_cb, operator, kspace_data, damp=damp, x0=x0))
-        if operator.squeeze_dims:
-            image = operator._safe_squeeze(image)
-    finally:
-        if old_density is not None:
-            operator._density = old_density
-            operator._density_d = old_density_d
-    out = from_device(image, kind, kdev)
-    if callbacks_results:
-        return out, callbacks_results
-    return out
+                callbacks_results.append(callback(ctx.out(image), operator, kspace_data, damp=damp, x0=x0))
+    return _finish(ctx, image, callbacks_results)
 
 
-_ = np
+SOLVERS = {"cg": cg, "lsqr": lsqr, "lsmr": lsmr}

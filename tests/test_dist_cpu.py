@@ -40,6 +40,38 @@ class _NumpyLocalOp:
     def data_consistency(self, image, obs):
         return self.adj_op(self.op(image) - obs.reshape(1, self.n_coils, -1))
 
+    # device-level surface used by mrinufft_b200.solvers (CPU tensors here)
+    device = torch.device("cpu")
+    _cdt = torch.complex128
+    squeeze_dims = False
+    uses_density = False
+    density = None
+    n_batchs = 1
+
+    @property
+    def img_full_shape(self):
+        return (1, 1 if self.smaps is not None else self.n_coils, *self.shape)
+
+    @property
+    def ksp_full_shape(self):
+        return (1, self.n_coils, self.A.shape[0])
+
+    def _op_device(self, img):
+        return torch.from_numpy(self.op(img.numpy()))
+
+    def _adj_device(self, ksp):
+        return torch.from_numpy(np.ascontiguousarray(self.adj_op(ksp.numpy())))
+
+    def _dc_device(self, img, obs):
+        return torch.from_numpy(np.ascontiguousarray(self.data_consistency(img.numpy(), obs.numpy())))
+
+    def get_lipschitz_cst(self, max_iter=10):
+        # the largest eigenvalue of A^H A plus a rank-dependent error, like a power method started
+        # from unseeded random numbers would give: the sharded operator must agree on rank 0's value
+        return float(np.linalg.norm(self.A, 2) ** 2) * (1.0 + 0.01 * self._rank)
+
+    _rank = 0
+
 
 def _worker(rank, world, port, tmp):
     sys.path.insert(0, str(ROOT))
@@ -79,6 +111,24 @@ def _worker(rank, world, port, tmp):
     ref = np.vdot(fullc.adj_op(ksp), fullc.adj_op(ksp)).real
     assert abs(float(tot) - ref) / ref < 1e-12
     assert float(sh.reduce_scalar(local_dot)) == float(local_dot)  # SENSE: replicated iterate
+    # pinv_solver on coil-sharded data == the same solver on one rank (SENSE: replicated image,
+    # calibrationless: this rank's coils), with a rank-dependent Lipschitz estimate on purpose
+    from mrinufft_b200 import solvers
+
+    sh.local._rank = rank
+    shc.local._rank = rank
+    for name in ("lsqr", "lsmr", "cg"):
+        kw = dict(max_iter=6)
+        if name == "cg":
+            kw["lipschitz_cst"] = full.get_lipschitz_cst()
+        want = solvers.SOLVERS[name](full, ksp[None], **kw)
+        got = sh.pinv_solver(ksp[None, lo:hi], optim=name, max_iter=6)
+        assert got.shape == want.shape and np.allclose(got, want, rtol=1e-9, atol=1e-11), name
+        if name == "cg":
+            kw["lipschitz_cst"] = fullc.get_lipschitz_cst()
+        wantc = solvers.SOLVERS[name](fullc, ksp[None], damp=0.2, **kw)
+        gotc = shc.pinv_solver(ksp[None, lo:hi], optim=name, max_iter=6, damp=0.2)
+        assert np.allclose(gotc, wantc[:, lo:hi], rtol=1e-9, atol=1e-11), name
     Path(tmp, f"ok{rank}").write_text("ok")
     dist.destroy_process_group()
 

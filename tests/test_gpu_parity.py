@@ -393,6 +393,53 @@ def test_pinv_solver_residual_decreases(mods, optim):
     assert res[-1] <= res[0]
 
 
+def _collect_iterates(image, operator, kspace_data, damp=0.0, x0=None):
+    return np.array(image, copy=True).reshape(operator.img_full_shape)
+
+
+@pytest.mark.parametrize("case", ["solvers2D_sense", "solvers2D_batch_density", "solvers3D_sense_damp"])
+@pytest.mark.parametrize("optim", ["lsqr", "lsmr", "cg"])
+def test_device_solvers_replay_reference_iterates(mods, case, optim):
+    """The device-resident solvers on the CUDA operator against the iterates of the reference's own
+    solvers on its exact NDFT (tests/golden/make_solver_golden.py), iteration by iteration."""
+    mrinufft, _, _ = mods
+    g = load_golden(case)
+    dens = g["density"] if "density" in g else False
+    op = mrinufft.get_operator("b200")(g["samples"], g["shape"], n_coils=g["n_coils"], n_batchs=int(g["n_batchs"]),
+                                       smaps=g.get("smaps"), density=dens)
+    y = g["y"].copy()
+    np.random.seed(99)  # start of the power method behind cg's step size (base.py:1194)
+    x, its = op.pinv_solver(y, optim=optim, damp=float(g["damp"]), max_iter=8, callback=_collect_iterates,
+                            progressbar=False)
+    assert np.array_equal(y, g["y"])
+    ref = g[f"it_{optim}"]
+    assert len(its) == len(ref)
+    for k in range(len(ref)):
+        assert rel_l2(its[k], ref[k]) < 1e-3, (optim, k, rel_l2(its[k], ref[k]))
+    assert rel_l2(x.reshape(ref[-1].shape), ref[-1]) < 1e-3
+    if dens is not False:  # the density is switched off during the iteration and restored afterwards
+        assert op.uses_density and np.allclose(op.density, g["density"])
+
+
+@pytest.mark.parametrize("optim", ["lsqr", "lsmr"])
+def test_device_solvers_equal_reference_solvers_on_the_same_operator(mods, optim):
+    """``pinv_solver`` (device resident) == the reference's solver driving the same b200 operator through
+    host arrays (extras/optim.py via ``with_numpy_cupy``); torch CUDA in -> torch CUDA out."""
+    mrinufft, _, torch = mods
+    from mrinufft.extras import get_optimizer
+
+    g = load_golden("solvers2D_sense")
+    op = mrinufft.get_operator("b200")(g["samples"], g["shape"], n_coils=g["n_coils"], smaps=g["smaps"])
+    want = get_optimizer(optim)(operator=op, kspace_data=g["y"].copy(), max_iter=6, progressbar=False)
+    got = op.pinv_solver(g["y"], optim=optim, max_iter=6)
+    assert isinstance(got, np.ndarray) and got.shape == want.shape
+    assert rel_l2(got, want) < 2e-4
+    yt = torch.from_numpy(g["y"]).cuda()
+    got_t = op.pinv_solver(yt, optim=optim, max_iter=6)
+    assert torch.is_tensor(got_t) and got_t.is_cuda
+    assert rel_l2(got_t.cpu().numpy(), got) < 1e-5
+
+
 # ------------------------------------------------------------------ autodiff (tests/operators/test_autodiff.py)
 def test_autodiff_data_and_trajectory(mods):
     mrinufft, _, torch = mods

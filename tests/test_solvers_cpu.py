@@ -1,0 +1,171 @@
+"""CPU checks of the device-resident solvers (mrinufft_b200/solvers.py) against the reference's own
+``cg`` / ``lsqr`` / ``lsmr`` (src/mrinufft/extras/optim.py:249-902), iterate by iterate.
+
+Both sides run on the reference's exact-NDFT ``numpy`` backend: the reference solvers drive it
+directly, ours drive it through a thin wrapper that exposes the device-level surface the solvers use
+(``_op_device`` / ``_adj_device`` / ``_dc_device`` on torch tensors -- CPU tensors here).  No GPU and no
+CUDA library involved: this pins the solver logic, the GPU suite pins it on the CUDA operator.
+"""
+
+import numpy as np
+import pytest
+import torch
+
+import mrinufft
+from mrinufft.extras.optim import cg as ref_cg
+from mrinufft.extras.optim import lsmr as ref_lsmr
+from mrinufft.extras.optim import lsqr as ref_lsqr
+
+from mrinufft.operators.base import FourierOperatorCPU
+from mrinufft.operators.interfaces.nudft_numpy import RawNDFT
+
+from mrinufft_b200 import solvers
+
+
+class _NDFTFull(FourierOperatorCPU):
+    """Exact NDFT with the whole FourierOperatorCPU surface (batches, density); registers a test-only backend."""
+
+    backend = "ndft-full-test"
+    available = True
+
+
+class TorchFacade:
+    """The reference NDFT operator behind the device-level surface of MRIB200NUFFT (test only)."""
+
+    def __init__(self, ref):
+        self.ref = ref
+        self.device = torch.device("cpu")
+        self._cdt = torch.complex64
+
+    def __getattr__(self, name):
+        return getattr(self.ref, name)
+
+    @property
+    def density(self):
+        return self.ref.density
+
+    @density.setter
+    def density(self, value):
+        self.ref.density = value
+
+    @property
+    def squeeze_dims(self):
+        return self.ref.squeeze_dims
+
+    def _op_device(self, img):
+        y = self.ref.op(img.numpy().reshape(self.ref.img_full_shape))
+        return torch.from_numpy(np.ascontiguousarray(y).reshape(self.ref.ksp_full_shape).astype(np.complex64))
+
+    def _adj_device(self, ksp):
+        x = self.ref.adj_op(ksp.numpy().reshape(self.ref.ksp_full_shape))
+        return torch.from_numpy(np.ascontiguousarray(x).reshape(self.ref.img_full_shape).astype(np.complex64))
+
+    def _dc_device(self, img, obs):
+        g = self.ref.data_consistency(img.numpy().reshape(self.ref.img_full_shape),
+                                      obs.numpy().reshape(self.ref.ksp_full_shape))
+        return torch.from_numpy(np.ascontiguousarray(g).reshape(self.ref.img_full_shape).astype(np.complex64))
+
+
+def _problem(n_batchs, sense, density, seed=0):
+    rng = np.random.default_rng(seed)
+    shape, M, C = (10, 12), 400, 3
+    samples = rng.uniform(-0.5, 0.5, (M, 2)).astype(np.float32)
+    smaps = None
+    if sense:
+        smaps = (rng.standard_normal((C, *shape)) + 1j * rng.standard_normal((C, *shape))).astype(np.complex64)
+        smaps /= np.linalg.norm(smaps, axis=0, keepdims=True)
+    dens = rng.uniform(0.5, 1.5, M).astype(np.float32) if density else False
+    # MRInumpy itself takes neither n_batchs nor density (nudft_numpy.py:141-150): same raw NDFT, full base class
+    op = _NDFTFull(samples, shape, density=dens, n_coils=C, n_batchs=n_batchs, smaps=smaps,
+                   raw_op=RawNDFT(samples, shape), squeeze_dims=True)
+    x_true = (rng.standard_normal(op.img_full_shape) + 1j * rng.standard_normal(op.img_full_shape))
+    y = op.op(x_true.astype(np.complex64)).reshape(op.ksp_full_shape).astype(np.complex64)
+    y += 0.01 * (rng.standard_normal(y.shape) + 1j * rng.standard_normal(y.shape)).astype(np.complex64)
+    x0 = (0.1 * (rng.standard_normal(op.img_full_shape) + 1j * rng.standard_normal(op.img_full_shape))
+          ).astype(np.complex64)
+    return op, y, x0
+
+
+def _iterates(image, operator, kspace_data, damp=0.0, x0=None):
+    return np.array(image, copy=True).reshape(operator.img_full_shape)
+
+
+def _close(mine, ref, tol):
+    assert len(mine) == len(ref)
+    for k, (a, b) in enumerate(zip(mine, ref)):
+        err = np.linalg.norm(a - b) / np.linalg.norm(b)
+        assert err < tol, f"iterate {k}: rel err {err:.2e}"
+
+
+@pytest.mark.parametrize("name,ref_fn", [("lsqr", ref_lsqr), ("lsmr", ref_lsmr)])
+@pytest.mark.parametrize("n_batchs,sense,density,damp,use_x0", [
+    (1, True, False, 0.0, False),
+    (2, True, False, 0.0, False),
+    (1, False, False, 0.3, True),
+    (2, False, True, 0.0, False),
+    (1, True, True, 0.2, False),
+])
+def test_bidiagonalisation_solvers_match_reference_iterates(name, ref_fn, n_batchs, sense, density, damp, use_x0):
+    op, y, x0 = _problem(n_batchs, sense, density)
+    kw = dict(damp=damp, max_iter=12, callback=_iterates, progressbar=False)
+    if use_x0:
+        kw["x0"] = x0
+    dens_before = None if op.density is None else op.density.copy()
+    x_ref, it_ref = ref_fn(op, y.copy(), **{k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in kw.items()})
+    # the reference leaves the density switched off when a callback is given (optim.py:491-495): undo
+    if dens_before is not None:
+        op.density = dens_before
+    y_in = y.copy()
+    x, it = solvers.SOLVERS[name](TorchFacade(op), y_in, **kw)
+    assert np.array_equal(y_in, y)                      # inputs are never written to
+    assert isinstance(x, np.ndarray) and x.shape == x_ref.shape
+    _close(it, it_ref, 2e-4)
+    assert np.linalg.norm(x - x_ref) < 2e-4 * np.linalg.norm(x_ref)
+    if dens_before is not None:                          # ... and the density is back in place
+        assert op.density is not None and np.array_equal(op.density, dens_before)
+
+
+@pytest.mark.parametrize("n_batchs,sense,density,damp", [(1, True, False, 0.0), (1, False, False, 0.1),
+                                                         (1, True, True, 0.0)])
+def test_cg_matches_reference_iterates(n_batchs, sense, density, damp):
+    op, y, _ = _problem(n_batchs, sense, density, seed=4)
+    kw = dict(damp=damp, max_iter=8, callback=_iterates, progressbar=False)
+    dens_before = None if op.density is None else op.density.copy()
+    np.random.seed(7)   # the power method starts from np.random.random (base.py:1194)
+    x_ref, it_ref = ref_cg(op, y.copy(), **kw)
+    if dens_before is not None:
+        op.density = dens_before
+    np.random.seed(7)
+    x, it = solvers.cg(TorchFacade(op), y.copy(), **kw)
+    _close(it, it_ref, 2e-4)
+    assert np.linalg.norm(x - x_ref) < 2e-4 * np.linalg.norm(x_ref)
+
+
+def test_stopping_rule_and_zero_rhs():
+    op, y, _ = _problem(1, True, False, seed=2)
+    # a consistent system converges and stops on its own, at the same iteration as the reference
+    y_clean = op.op(op.adj_op(y)).reshape(op.ksp_full_shape).astype(np.complex64)
+    for name, ref_fn in (("lsqr", ref_lsqr), ("lsmr", ref_lsmr)):
+        _, it_ref = ref_fn(op, y_clean.copy(), max_iter=400, atol=1e-3, btol=1e-3, callback=_iterates,
+                           progressbar=False)
+        _, it = solvers.SOLVERS[name](TorchFacade(op), y_clean.copy(), max_iter=400, atol=1e-3, btol=1e-3,
+                                      callback=_iterates)
+        assert len(it) < 400 and abs(len(it) - len(it_ref)) <= 1
+        # y = 0: alpha * beta == 0 -> the start is returned as is (optim.py:373-374)
+        z = solvers.SOLVERS[name](TorchFacade(op), np.zeros_like(y))
+        assert z.shape == tuple(op.img_full_shape) and not np.any(z)
+
+
+def test_givens_follows_the_reference_branches():
+    from mrinufft.extras.optim import _sym_ortho
+
+    rng = np.random.default_rng(0)
+    cases = [(np.float32([3.0]), np.float32([4.0])), (np.float32([4.0]), np.float32([-3.0])),
+             (np.float32([0.0]), np.float32([2.0])), (np.float32([2.0]), np.float32([0.0])),
+             (rng.standard_normal(3).astype(np.float32), rng.standard_normal(3).astype(np.float32)),
+             (np.float32([1.0, 0.0]), np.float32([2.0, 1.0]))]
+    for a, b in cases:
+        got = solvers._givens(a, b)
+        want = _sym_ortho(a, b)
+        for g, w in zip(got, want):
+            assert np.allclose(g, w, rtol=1e-6, atol=0)
