@@ -275,12 +275,16 @@ class MRIB200NUFFT(FourierOperatorBase):
     @property
     def smaps(self):
         """Sensitivity maps (as given; a complex64 copy lives on the device)."""
+        if getattr(self, "_smaps_lazy_host", False) and self._smaps is not None:
+            self._smaps = self._smaps.cpu().numpy()
+            self._smaps_lazy_host = False
         return self._smaps
 
     @smaps.setter
     def smaps(self, new_smaps):
         # accepts numpy, torch (cpu/cuda) and cupy arrays; the base setter only takes numpy
         # (base.py:759-760) -- same override as cufinufft.py:277-315.
+        self._smaps_lazy_host = False
         if new_smaps is None:
             self._smaps = None
             self._smaps_d = None
@@ -305,7 +309,45 @@ class MRIB200NUFFT(FourierOperatorBase):
         if method is None:
             self.smaps = None
             return
+        name, kw = None, {}
+        if isinstance(method, str):
+            name = method
+        elif isinstance(method, dict) and isinstance(method.get("name"), str):
+            name = method["name"]
+            kw = {k: v for k, v in method.items() if k != "name"}
+        if name == "low_frequency" and not np.any(kw.get("mask", False)) and np.sum(kw.get("blurr_factor", 0.0)) == 0:
+            self.smaps = self._low_frequency_smaps(**kw)
+            self._smaps_lazy_host = True  # `.smaps` hands out numpy, like the reference; copied on first use
+            return
         super().compute_smaps(method)
+
+    def _low_frequency_smaps(self, kspace_data, threshold=0.1, max_iter=10, window_fun="ellipse",
+                             mask=False, blurr_factor=0.0):
+        """Low-frequency sensitivity maps (``low_frequency``, extras/smaps.py:220-306) for the default
+        ``mask=False, blurr_factor=0``: centre of k-space -> ``pinv_solver`` on a throw-away
+        calibrationless operator (device-resident lsqr) -> divide by the root sum of squares, all on
+        the device.  The reference function imports scikit-image up front, even when neither the mask
+        nor the blur is requested; those two options still go through it.
+        """
+        from mrinufft.extras.smaps import _extract_kspace_center
+
+        ksp = kspace_data
+        if module_name(ksp) == "torch":
+            ksp = ksp.detach().cpu().numpy()
+        elif not isinstance(ksp, np.ndarray):
+            ksp = ksp.get() if hasattr(ksp, "get") else np.asarray(ksp)
+        k_space, samples, _ = _extract_kspace_center(
+            kspace_data=ksp, kspace_loc=self.samples, threshold=threshold, density=self.density,
+            window_fun=window_fun,
+        )
+        # same constructor call as extras/smaps.py:280-285 (the centre samples go through
+        # proper_trajectory again, exactly as they do there)
+        centre = type(self)(samples, self.shape, n_coils=k_space.shape[-2], squeeze_dims=True,
+                            gpu_device_id=self.device.index, precision="double" if self._double else "single")
+        maps = centre.pinv_solver(to_device(k_space, self.device, self._cdt), max_iter=max_iter)
+        maps = maps.reshape(k_space.shape[-2], *self.shape)
+        sos = torch.sqrt(torch.sum(maps.real ** 2 + maps.imag ** 2, dim=0, keepdim=True))
+        return maps / sos
 
     @property
     def density(self):

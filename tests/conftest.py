@@ -50,3 +50,23 @@ def rel_l2(a, b):
 
 GOLDEN_CASES = ["random2D", "random2D_sense", "random3D", "random3D_sense", "nyquist_radial2D",
                 "spiral2D_sense", "grid2D", "cones3D"]
+
+
+_NDFT_FULL = None
+
+
+def ndft_full(samples, shape, **kw):
+    """The reference's exact NDFT (``RawNDFT``, nudft_numpy.py:82-130) behind its complete
+    ``FourierOperatorCPU`` surface -- ``MRInumpy`` itself takes neither ``n_batchs`` nor ``density``
+    (nudft_numpy.py:141-150).  Registers a test-only backend name."""
+    global _NDFT_FULL
+    from mrinufft.operators.base import FourierOperatorCPU
+    from mrinufft.operators.interfaces.nudft_numpy import RawNDFT
+
+    if _NDFT_FULL is None:
+        class NDFTFull(FourierOperatorCPU):
+            backend = "ndft-full-test"
+            available = True
+
+        _NDFT_FULL = NDFTFull
+    return _NDFT_FULL(samples, shape, raw_op=RawNDFT(samples, shape), **kw)

@@ -440,6 +440,40 @@ def test_device_solvers_equal_reference_solvers_on_the_same_operator(mods, optim
     assert rel_l2(got_t.cpu().numpy(), got) < 1e-5
 
 
+@pytest.mark.parametrize("window_fun", ["ellipse", "rect"])
+def test_low_frequency_smaps_on_device(mods, window_fun):
+    """``smaps={"name": "low_frequency", ...}`` (extras/smaps.py:220-306, default mask / blur): same steps
+    with the reference's centre extraction + its lsqr on the exact NDFT."""
+    mrinufft, _, torch = mods
+    from conftest import ndft_full
+    from mrinufft.extras.optim import lsqr
+    from mrinufft.extras.smaps import _extract_kspace_center
+    from mrinufft.trajectories import initialize_2D_radial
+
+    rng = np.random.default_rng(5)
+    shape, C = (24, 20), 3
+    samples = (initialize_2D_radial(32, 64).reshape(-1, 2) * 2 * np.pi).astype(np.float32)
+    ksp = (rng.standard_normal((C, len(samples))) + 1j * rng.standard_normal((C, len(samples)))).astype(np.complex64)
+    op = mrinufft.get_operator("b200")(samples, shape, n_coils=C, smaps={
+        "name": "low_frequency", "kspace_data": ksp, "threshold": 1.0, "max_iter": 6, "window_fun": window_fun})
+    assert op.uses_sense and op.n_coils == C
+    assert isinstance(op.smaps, np.ndarray) and op.smaps.shape == (C, *shape)
+    k_c, s_c, _ = _extract_kspace_center(kspace_data=ksp, kspace_loc=op.samples, threshold=1.0, density=None,
+                                         window_fun=window_fun)
+    assert (k_c.shape[-1] < len(samples)) == (window_fun == "rect")  # windows weight, "rect" selects
+    ref_op = ndft_full(s_c.astype(np.float64), shape, n_coils=C, squeeze_dims=True)
+    maps = lsqr(ref_op, k_c.copy(), max_iter=6, progressbar=False)
+    maps = maps / np.linalg.norm(maps, axis=0)
+    assert rel_l2(op.smaps, maps) < 1e-3
+    assert np.allclose(np.linalg.norm(op.smaps, axis=0), 1.0, atol=1e-5)
+    # the maps are live: SENSE op / adj_op run with them
+    x = (rng.standard_normal(shape) + 1j * rng.standard_normal(shape)).astype(np.complex64)
+    y = op.op(x)
+    assert y.shape == (C, len(samples))
+    want = ndft_full(samples.astype(np.float64), shape, n_coils=C, smaps=op.smaps).op(x)
+    assert rel_l2(y, want) < TOL_NDFT
+
+
 # ------------------------------------------------------------------ autodiff (tests/operators/test_autodiff.py)
 def test_autodiff_data_and_trajectory(mods):
     mrinufft, _, torch = mods

@@ -11,22 +11,13 @@ import numpy as np
 import pytest
 import torch
 
-import mrinufft
 from mrinufft.extras.optim import cg as ref_cg
 from mrinufft.extras.optim import lsmr as ref_lsmr
 from mrinufft.extras.optim import lsqr as ref_lsqr
 
-from mrinufft.operators.base import FourierOperatorCPU
-from mrinufft.operators.interfaces.nudft_numpy import RawNDFT
+from conftest import ndft_full
 
 from mrinufft_b200 import solvers
-
-
-class _NDFTFull(FourierOperatorCPU):
-    """Exact NDFT with the whole FourierOperatorCPU surface (batches, density); registers a test-only backend."""
-
-    backend = "ndft-full-test"
-    available = True
 
 
 class TorchFacade:
@@ -75,9 +66,7 @@ def _problem(n_batchs, sense, density, seed=0):
         smaps = (rng.standard_normal((C, *shape)) + 1j * rng.standard_normal((C, *shape))).astype(np.complex64)
         smaps /= np.linalg.norm(smaps, axis=0, keepdims=True)
     dens = rng.uniform(0.5, 1.5, M).astype(np.float32) if density else False
-    # MRInumpy itself takes neither n_batchs nor density (nudft_numpy.py:141-150): same raw NDFT, full base class
-    op = _NDFTFull(samples, shape, density=dens, n_coils=C, n_batchs=n_batchs, smaps=smaps,
-                   raw_op=RawNDFT(samples, shape), squeeze_dims=True)
+    op = ndft_full(samples, shape, density=dens, n_coils=C, n_batchs=n_batchs, smaps=smaps, squeeze_dims=True)
     x_true = (rng.standard_normal(op.img_full_shape) + 1j * rng.standard_normal(op.img_full_shape))
     y = op.op(x_true.astype(np.complex64)).reshape(op.ksp_full_shape).astype(np.complex64)
     y += 0.01 * (rng.standard_normal(y.shape) + 1j * rng.standard_normal(y.shape)).astype(np.complex64)
