@@ -10,12 +10,19 @@ formulas are the reference's:
 * d adj / d samples  = sum_{b,c} i y op_{+}(conj(dx) r_d)           (autodiff.py:69-86) with the
   opposite-sign plan and conjugated smaps (``grad_traj_plan``), which ``MRIB200NUFFT`` provides by
   flipping the sign of the same plan.
+* d op / d field_map  = conj(x) adj_op(dy t)                        (autodiff.py:44-55, with the
+  conjugate the reference omits -- see ``_backward_op_field_map``)
+* d adj / d field_map = conj(dx) adj_op(y t)                        (autodiff.py:89-100), ``t`` the
+  operator's ``full_readout_time``, for off-resonance-corrected operators (``MRIFourierCorrected``
+  and its batched b200 subclass) only.
 """
 
 from __future__ import annotations
 
 import numpy as np
 import torch
+
+from mrinufft.operators.off_resonance import MRIFourierCorrected
 
 from ._arrays import NP2TORCH
 
@@ -41,6 +48,29 @@ def _backward_op_samples(nufft, x, dy):
         for i in range(grid_r.size(0))
     ]
     return torch.stack(rows, dim=0).transpose(0, 1).to(NP2TORCH[np.dtype(nufft.dtype)])
+
+
+def _readout_time(nufft, like):
+    t = nufft.full_readout_time
+    if not torch.is_tensor(t):
+        t = torch.from_numpy(np.ascontiguousarray(np.asarray(t)))
+    return t.to(like.device)
+
+
+def _backward_op_field_map(nufft, x, dy):
+    if not nufft._grad_wrt_field_map or not isinstance(nufft, MRIFourierCorrected):
+        return None
+    # conj(x): y_m = sum_n A_mn exp(f_n t_m) x_n is holomorphic in f, so the VJP is conj(dy_m/df_n) dy_m.
+    # The reference multiplies by x itself (autodiff.py:54), which does not agree with torch's autograd
+    # through the dense model -- the check its own test intends (tests/operators/test_autodiff.py:248-259,
+    # whose atol = 1e-1 is far above the gradient's magnitude); see tests/test_autodiff_cpu.py.
+    return x.conj() * nufft.adj_op(dy * _readout_time(nufft, dy))
+
+
+def _backward_adj_field_map(nufft, y, dx):
+    if not nufft._grad_wrt_field_map or not isinstance(nufft, MRIFourierCorrected):
+        return None
+    return dx.conj() * nufft.adj_op(y * _readout_time(nufft, y))
 
 
 def _backward_adj_data(nufft, y, dx):
@@ -77,7 +107,7 @@ class _NUFFT_OP(torch.autograd.Function):
         gt = _backward_op_samples(ctx.nufft, x, dy)
         if gt is not None and traj_device(ctx) is not None:
             gt = gt.to(traj_device(ctx))
-        return (_backward_op_data(ctx.nufft, x, dy), gt, None, None)
+        return (_backward_op_data(ctx.nufft, x, dy), gt, _to_leaf(_backward_op_field_map(ctx.nufft, x, dy), ctx), None)
 
 
 class _NUFFT_ADJOP(torch.autograd.Function):
@@ -95,11 +125,21 @@ class _NUFFT_ADJOP(torch.autograd.Function):
         gt = _backward_adj_samples(ctx.nufft, y, dx)
         if gt is not None and traj_device(ctx) is not None:
             gt = gt.to(traj_device(ctx))
-        return (_backward_adj_data(ctx.nufft, y, dx), gt, None, None)
+        return (_backward_adj_data(ctx.nufft, y, dx), gt, _to_leaf(_backward_adj_field_map(ctx.nufft, y, dx), ctx), None)
 
 
 def traj_device(ctx):
     return getattr(ctx.nufft, "_traj_grad_device", None)
+
+
+def _to_leaf(grad, ctx):
+    """Field-map gradient in the shape / on the device of the field-map tensor (it may live on the host
+    while the data are CUDA tensors, like the samples)."""
+    if grad is None:
+        return None
+    dev = getattr(ctx.nufft, "_field_map_grad_device", None)
+    grad = grad.reshape(ctx.nufft.shape) if grad.numel() == int(np.prod(ctx.nufft.shape)) else grad.sum(dim=(0, 1))
+    return grad if dev is None else grad.to(dev)
 
 
 class MRINufftAutoGrad(torch.nn.Module):
@@ -113,35 +153,44 @@ class MRINufftAutoGrad(torch.nn.Module):
                  paired_batch=False):
         if any((wrt_data, wrt_traj, wrt_field_map)) and nufft_op.squeeze_dims:
             raise ValueError("Squeezing dimensions is not supported for autodiff.")
-        if wrt_field_map:
-            raise ValueError("Field-map gradients need an off-resonance corrected operator.")
         super().__init__()
         self.nufft_op = nufft_op
         self.nufft_op._grad_wrt_traj = wrt_traj
         self.nufft_op._grad_wrt_data = wrt_data
-        self.nufft_op._grad_wrt_field_map = False
+        self.nufft_op._grad_wrt_field_map = wrt_field_map
         if wrt_traj:
             self.nufft_op._make_plan_grad()
             self._samples_torch = torch.from_numpy(np.array(self.nufft_op.samples, copy=True))
             self._samples_torch.requires_grad = True
             self.nufft_op._traj_grad_device = self._samples_torch.device
+        self._field_map_torch = None
+        if wrt_field_map and isinstance(self.nufft_op, MRIFourierCorrected):
+            fm = self.nufft_op.field_map
+            fm = fm.detach().clone() if torch.is_tensor(fm) else torch.from_numpy(np.array(fm, copy=True))
+            self._field_map_torch = fm
+            self._field_map_torch.requires_grad = True
+            self.nufft_op._field_map_grad_device = fm.device
         self.paired_batch = paired_batch
+
+    def _field_map_arg(self, field_map):
+        corrected = isinstance(self.nufft_op, MRIFourierCorrected)
+        if field_map is not None and not corrected:
+            raise ValueError("Underlying nufft operator does not support field map.")
+        if corrected and field_map is None:
+            field_map = self.field_map
+        return field_map
 
     def op(self, x, smaps=None, samples=None, field_map=None):
         """Forward image -> k-space (autodiff.py:222-253)."""
-        if field_map is not None:
-            raise ValueError("Underlying nufft operator does not support field map.")
         if self.paired_batch:
             return self._op_batched(x, smaps, samples)
-        return _NUFFT_OP.apply(x, self.samples, None, self.nufft_op)
+        return _NUFFT_OP.apply(x, self.samples, self._field_map_arg(field_map), self.nufft_op)
 
     def adj_op(self, kspace, smaps=None, samples=None, field_map=None):
         """Adjoint k-space -> image (autodiff.py:255-289)."""
-        if field_map is not None:
-            raise ValueError("Underlying nufft operator does not support field map.")
         if self.paired_batch:
             return self._adj_op_batched(kspace, smaps, samples)
-        return _NUFFT_ADJOP.apply(kspace, self.samples, None, self.nufft_op)
+        return _NUFFT_ADJOP.apply(kspace, self.samples, self._field_map_arg(field_map), self.nufft_op)
 
     def _op_batched(self, batched_imgs, batched_smaps=None, batched_samples=None):
         self._check_input_shape(smaps=batched_smaps, imgs=batched_imgs, samples=batched_samples)
@@ -187,6 +236,27 @@ class MRINufftAutoGrad(torch.nn.Module):
         self._samples_torch = new_samples
         self.nufft_op._traj_grad_device = new_samples.device
         self.nufft_op.update_samples(new_samples.detach(), unsafe=unsafe)
+
+    @property
+    def field_map(self):
+        """The field map as a torch tensor (autodiff.py:385-393)."""
+        if not isinstance(self.nufft_op, MRIFourierCorrected):
+            raise ValueError("Underlying nufft operator does not support field map.")
+        if self._field_map_torch is not None:
+            return self._field_map_torch
+        return self.nufft_op.field_map
+
+    @field_map.setter
+    def field_map(self, value):
+        self.update_field_map(value)
+
+    def update_field_map(self, new_field_map):
+        """Update the field map and recompute the interpolators (autodiff.py:399-406)."""
+        if not isinstance(self.nufft_op, MRIFourierCorrected):
+            raise ValueError("Underlying nufft operator does not support field map.")
+        self._field_map_torch = new_field_map
+        self.nufft_op._field_map_grad_device = new_field_map.device
+        self.nufft_op.update_field_map(new_field_map.detach())
 
     def __getattr__(self, name):
         try:

@@ -90,6 +90,15 @@ class MRIB200FourierCorrected(MRIFourierCorrected):
         vop._density = fo._density
         return vop
 
+    # ------------------------------------------------------------------ autodiff
+    def make_autograd(self, *, wrt_data=True, wrt_traj=False, wrt_field_map=False, paired_batch=False):
+        """Torch autograd wrapper incl. the field-map gradient (off_resonance.py:399-446); the reference's
+        own wrapper hard-imports ``deepinv`` (autodiff.py:11)."""
+        from .autodiff import MRINufftAutoGrad
+
+        return MRINufftAutoGrad(self, wrt_data=wrt_data, wrt_traj=wrt_traj, wrt_field_map=wrt_field_map,
+                                paired_batch=paired_batch)
+
     # ------------------------------------------------------------------ operators
     def op(self, data, *args):
         """Forward model with off-resonance (off_resonance.py:232-281)."""

@@ -775,6 +775,36 @@ def test_off_resonance_batched_matches_reference_wrapper(mods, shape, C, sense):
     assert yt.is_cuda and np.allclose(yt.cpu().numpy(), ax, rtol=1e-5, atol=1e-6)
 
 
+@pytest.mark.parametrize("C,sense", [(1, False), (3, True)])
+def test_field_map_autograd_through_the_batched_orc_operator(mods, C, sense):
+    """``with_off_resonance_correction(...).make_autograd(wrt_field_map=True)`` (off_resonance.py:399-446,
+    autodiff.py:44-55, 89-100) on the batched b200 operator, CUDA tensors in and out, against torch's
+    autograd through the dense model (same check as tests/test_autodiff_cpu.py on the reference NDFT)."""
+    mrinufft, _, torch = mods
+    from conftest import check_orc_autograd
+
+    from mrinufft_b200.off_resonance import MRIB200FourierCorrected
+
+    rng = np.random.default_rng(3)
+    shape, NK = (8, 10), 48
+    unit = rng.uniform(-0.5, 0.5, (NK, 2)).astype(np.float32)
+    smaps = None
+    if sense:
+        smaps = (rng.standard_normal((C, *shape)) + 1j * rng.standard_normal((C, *shape))).astype(np.complex64)
+        smaps /= np.linalg.norm(smaps, axis=0)
+    b0 = (30 * rng.standard_normal(shape)).astype(np.float32)
+    t = np.linspace(0, 4e-3, NK).astype(np.float32)
+    op = mrinufft.get_operator("b200")(unit * 2 * np.pi, shape, n_coils=C, smaps=smaps, squeeze_dims=False)
+    orc = op.with_off_resonance_correction(t, b0, interpolator={"name": "mti", "L": 24})
+    assert isinstance(orc, MRIB200FourierCorrected)
+    ag = orc.make_autograd(wrt_data=True, wrt_field_map=True)
+    # (the field-map tensor stays on the host, like the samples of the trajectory gradient; re-assigning it
+    # would recompute the interpolators with default settings -- `update_field_map` drops the kwargs,
+    # off_resonance.py:199-206)
+    check_orc_autograd(ag, orc, unit, shape, t, smaps, C, "cuda", rng)
+    assert orc._fused is not None  # the interpolators rode the coil batch
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("sense", [False, True])
 def test_native_stacked_matches_generic_stacked(mods, sense):
