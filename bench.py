@@ -34,6 +34,7 @@ for _p in (ROOT, ROOT / "baseline" / "_ref"):
 METRIC = "3D 32-coil NUFFT op+adj_op throughput"
 # DRAM bytes (read + write) of one launch of the row kernels at cfg-C, `ncu --set full`:
 # profiles/r01_k_rows_stream_full.txt
+FP32_PEAK_TFMA = 36.8  # measured: profiles/r01_ffma2_rate.jsonl (fp32_fma_per_s of FFMA2)
 NCU_TRAFFIC_GB = {"spread": 39.7, "interp": 42.5}
 UNIT = "k-samples/s"
 
@@ -411,9 +412,18 @@ def run_b200(args):
         "peak_source": peak_src, "kernel_ms": kt, "algorithmic_bytes_per_launch": ab[dom_name],
         "step_algorithmic_bytes": ab["pair_all_coils"],
         "step_frac": ab["pair_all_coils"] / (ms_max * 1e-3) / 1e9 / peak,
-        "note": "the row kernels are bound by instruction issue and the L1/shared data pipe, not by HBM "
+        "note": "the row kernels are bound by the FP32 FMA pipe and instruction issue, not by HBM "
                 "(ncu: issue 54-56 %, dram 26-31 %); frac is quoted against the HBM floor as the "
-                "contract asks",
+                "contract asks, `fp32` is the bound that applies",
+    }
+    # the bound that does apply to the row kernels: w^3 complex accumulations per sample and coil on the
+    # FP32 pipe; peak = packed FFMA2 issue rate measured on this pool (tools/ffma2_rate.cu ->
+    # profiles/r01_ffma2_rate.jsonl: 0.495 warp instructions / clk / SM sub-partition)
+    fma = 2.0 * M * float(plan.w) ** 3 * C
+    roofline["fp32"] = {
+        "algorithmic_fma_per_launch": fma, "achieved_tfma_s": fma / (dom_ms * 1e-3) / 1e12,
+        "peak_tfma_s": FP32_PEAK_TFMA, "frac": fma / (dom_ms * 1e-3) / 1e12 / FP32_PEAK_TFMA,
+        "peak_source": "tools/ffma2_rate.cu, profiles/r01_ffma2_rate.jsonl",
     }
 
     cpu_baseline = None

@@ -81,7 +81,7 @@ struct StridedArgs {
 // pattern known at compile time: inputs n1 < R1/4 or n1 >= 3 R1/4, outputs k2 < R2/4 or k2 >= 3 R2/4 --
 // no per-element predicates.  0: generic (run-time `Keep`, all-kept included).
 template <int L, int DIR, bool MUL, int EMODE, int KIN, int KOUT>
-__global__ void __launch_bounds__(FT)
+__global__ void __launch_bounds__(FT, L <= 512 ? 3 : 1)
 k_fft_strided(StridedArgs A, const float2* __restrict__ tw) {
   constexpr bool EMPTY = EMODE != 0;
   constexpr int R1 = Split<L>::R1, R2 = Split<L>::R2;

@@ -6,7 +6,10 @@ API calls with device-resident torch inputs (CUDA events), one JSON line per con
 
 cfg-A  README demo: 2-D radial 100 x 500, 512^2, single coil (density: pipe instead of voronoi)
 cfg-B  2-D spiral 64 x 2048, 320^2, 32 coils with smaps: op / adj_op / data_consistency
-cfg-D  3-D 256^3, 16 coils, density="pipe" + pinv_solver(optim="cg", max_iter=10)
+cfg-D  3-D 256^3, 16 coils, density="pipe" + pinv_solver(optim="cg" | "lsqr", max_iter=10), and the
+       reference's host-driven lsqr on the same operator for two iterations (what device residency saves)
+cfg-E  2-D 256^2, 8 coils with smaps, M = 32768, off-resonance correction with L = 10 interpolators riding
+       the coil batch, one unrolled gradient step with torch autograd (data + field-map gradients)
 """
 import json
 import sys
@@ -79,7 +82,10 @@ def cfg_d(quick):
     op_d = mrinufft.get_operator("b200")(traj, shape, n_coils=C, density="pipe", squeeze_dims=False)
     torch.cuda.synchronize()
     setup = time.perf_counter() - t0
-    ksp = crandn(1, C, op_d.n_samples)
+    # consistent data: k-space of a random 16-coil volume plus 1 % noise
+    x_true = crandn(1, C, *shape)
+    ksp = op_d._op_device(x_true)
+    ksp += 0.01 * torch.linalg.norm(ksp) / np.sqrt(ksp.numel()) * crandn(*ksp.shape)
     # density-compensated adjoint as the starting point, then CG on the un-weighted normal equations.
     # (pinv_solver(optim="cg") on the density-weighted operator itself follows the reference statement by
     # statement -- extras/optim.py:832-842 takes the step size from the density-WEIGHTED operator and then
@@ -91,7 +97,10 @@ def cfg_d(quick):
     res = []
 
     def cb(x, operator, y, **kw):
-        res.append(float(torch.linalg.norm(operator.op(x) - y)))
+        res.append(float(torch.linalg.norm(operator.op(x) - y) / torch.linalg.norm(y)))
+
+    def err(x):
+        return float(torch.linalg.norm(x.reshape(x_true.shape) - x_true) / torch.linalg.norm(x_true))
 
     np.random.seed(0)
     torch.cuda.synchronize()
@@ -99,14 +108,65 @@ def cfg_d(quick):
     x, _ = op.pinv_solver(ksp, optim="cg", max_iter=10, x_init=x0, callback=cb)
     torch.cuda.synchronize()
     cg_s = time.perf_counter() - t0
-    return {"config": f"D: 3D {n}^3, 16 coils (calibrationless), M={op.n_samples}, density=pipe start + cg(max_iter=10)",
-            "setup_s_incl_pipe": setup, "cg_10_iterations_s_incl_callback": cg_s,
-            "residual_first_last": [res[0], res[-1]], "result_finite": bool(torch.isfinite(x).all())}
+    out = {"config": f"D: 3D {n}^3, 16 coils (calibrationless), M={op.n_samples}, k-space of a random volume + 1 % noise",
+           "setup_s_incl_pipe": setup, "cg_10_iterations_s_incl_callback": cg_s,
+           "cg_rel_residual_first_last": [res[0], res[-1]], "cg_rel_image_error": err(x),
+           "result_finite": bool(torch.isfinite(x).all())}
+    del x
+    # the reference's default optimiser, device resident (mrinufft_b200/solvers.py), from a zero start
+    res.clear()
+    x, _ = op.pinv_solver(ksp, optim="lsqr", max_iter=10, callback=cb)
+    out["lsqr_rel_residual_first_last"] = [res[0], res[-1]]
+    out["lsqr_rel_image_error"] = err(x)
+    del x
+    for name in ("lsqr", "lsmr"):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        op.pinv_solver(ksp, optim=name, max_iter=10)
+        torch.cuda.synchronize()
+        out[f"{name}_10_iterations_s"] = time.perf_counter() - t0
+    # the reference's lsqr (extras/optim.py:249-495) driving the same operator through host arrays
+    from mrinufft.extras import get_optimizer
+
+    ksp_h = ksp.cpu().numpy()
+    t0 = time.perf_counter()
+    get_optimizer("lsqr")(operator=op, kspace_data=ksp_h, max_iter=2, progressbar=False)
+    out["reference_lsqr_host_driven_s_per_iteration"] = (time.perf_counter() - t0) / 2
+    return out
+
+
+def cfg_e():
+    C, shape, L = 8, (256, 256), 10
+    traj = initialize_2D_spiral(16, 2048, nb_revolutions=8).astype(np.float32).reshape(-1, 2)
+    smaps = crandn(C, *shape)
+    smaps /= torch.linalg.norm(smaps, dim=0, keepdim=True)
+    op = mrinufft.get_operator("b200")(traj, shape, n_coils=C, smaps=smaps, squeeze_dims=False)
+    yy, xx = np.meshgrid(np.linspace(-1, 1, shape[0]), np.linspace(-1, 1, shape[1]), indexing="ij")
+    b0 = (60.0 * np.exp(-(xx ** 2 + yy ** 2) * 2)).astype(np.float32)
+    t = np.linspace(0, 20e-3, 2048).astype(np.float32)
+    orc = op.with_off_resonance_correction(t, b0, interpolator={"name": "mti", "L": L})
+    ag = orc.make_autograd(wrt_data=True, wrt_field_map=True)
+    y = crandn(1, C, op.n_samples)
+    x = crandn(1, 1, *shape).requires_grad_(True)
+
+    def step():
+        x.grad = None
+        ag.field_map.grad = None
+        loss = torch.mean(torch.abs(ag.op(x) - y) ** 2)
+        loss.backward()
+
+    r = {"config": f"E: 2D spiral 16x2048 (M={op.n_samples}), 256^2, {C} coils with smaps, ORC with {orc.n_interpolators} "
+                   "interpolators riding the coil batch, autograd (data + field map)",
+         "orc_op_ms": timed(lambda: orc.op(x.detach()), 20),
+         "orc_adj_op_ms": timed(lambda: orc.adj_op(y), 20),
+         "unrolled_step_forward_backward_ms": timed(step, 10),
+         "fused": orc._fused is not None}
+    return r
 
 
 if __name__ == "__main__":
     quick = "--quick" in sys.argv
-    for f in (cfg_a, cfg_b, lambda: cfg_d(quick)):
+    for f in (cfg_a, cfg_b, lambda: cfg_d(quick), cfg_e):
         try:
             print(json.dumps(f()), flush=True)
         except Exception as exc:  # noqa: BLE001
