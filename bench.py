@@ -193,7 +193,7 @@ def run_reference(args):
         "scaling": "weak", "vs_baseline": None, "dtype": "complex64", "data": "synthetic", "impl": "reference",
         "config": workload_config(args, M, 1),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{cs} of {args.coils} coils, full 256^3 / M=2^23 op+adj_op pair per step; "
+                         "sample": f"{cs} of {args.coils} coils, full {args.n}^3 / M={M} op+adj_op pair per step; "
                                    f"ms_per_step extrapolated to {args.coils} coils"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -204,11 +204,12 @@ def run_reference(args):
 def workload_config(args, M, n_gpus):
     return {
         "workload": f"3D {args.n}^3, {args.coils} coils/GPU with smaps, M={M} "
-                    f"({'phyllotaxis radial 16384x512' if args.traj == 'radial' else 'truncnorm random'}), "
+                    f"({f'phyllotaxis radial {args.spokes}x{args.ns}' if args.traj == 'radial' else 'truncnorm random'}), "
                     "complex64, eps=1e-6, sigma=2, one op + one adj_op per step",
         "coils_per_gpu": args.coils, "n_samples": int(M), "image": [args.n] * 3,
         "parallelism": f"coil-sharded x{n_gpus} (weak: {args.coils} coils per GPU, all-reduce of the SENSE adjoint image)",
-        "l2": "inputs (k-space 2.1 GB, smaps 4.3 GB, grids 34 GB) are far larger than the 126 MB L2",
+        "l2": (f"inputs (k-space {8e-9 * M * args.coils:.2g} GB, smaps {8e-9 * args.n ** 3 * args.coils:.2g} GB, "
+               f"grids {64e-9 * args.n ** 3 * args.coils:.2g} GB) against the 126 MB L2"),
     }
 
 
@@ -431,7 +432,7 @@ def run_b200(args):
         cs = args.cpu_sample_coils
         dt, t_setpts, cores = cpu_pair_time(traj, shape, smaps[:cs].cpu().numpy(), cs)
         cpu_baseline = {"value": M * cs / dt / 1e3, "unit": UNIT, "cores": cores, "kind": "port",
-                        "sample": f"{cs} of {C} coils of the same workload (full 256^3, M={M}), one op+adj_op pair, "
+                        "sample": f"{cs} of {C} coils of the same workload (full {args.n}^3, M={M}), one op+adj_op pair, "
                                   f"float32 finufft-algorithm oracle; {dt:.1f} s, setpts {t_setpts:.1f} s",
                         "seconds": dt}
 
