@@ -232,6 +232,11 @@ def run_b200(args):
         # for the one JSON line of the contract
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
+        # one process per GPU: keep it (and the page-locked buffers it touches first) on the GPU's socket
+        from mrinufft_b200.dist import bind_to_gpu_numa_node
+
+        numa = bind_to_gpu_numa_node(local_rank)
+        print(f"[rank {rank}] NUMA binding: {numa}", file=sys.stderr, flush=True)
     if not mrinufft_b200.MRIB200NUFFT.available:
         raise RuntimeError("b200 backend unavailable (libb200nufft.so missing or no GPU): no fallback")
 

@@ -23,6 +23,36 @@ import torch
 import torch.distributed as dist
 
 
+def bind_to_gpu_numa_node(device_index: int):
+    """Pin the calling process to the CPUs next to its GPU (one process per GPU).
+
+    Page-locked host buffers are placed by first touch, so with every rank's buffers on one socket the
+    host<->device copies of the other socket's GPUs cross the inter-socket link.  Best effort: uses the
+    PCI address of the device and ``/sys``; returns ``(numa_node, n_cpus)`` or ``None`` when the
+    topology is not visible or the process is not allowed on those CPUs (then nothing changes).
+    """
+    import os
+    from pathlib import Path
+
+    try:
+        pr = torch.cuda.get_device_properties(device_index)
+        bdf = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        node = int(Path(f"/sys/bus/pci/devices/{bdf}/numa_node").read_text())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in Path(f"/sys/devices/system/node/node{node}/cpulist").read_text().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return node, len(cpus)
+    except (OSError, ValueError, AttributeError, RuntimeError, AssertionError):
+        return None
+
+
 def coil_slice(n_coils: int, rank: int, world: int):
     """Contiguous, balanced partition of the coil axis: rank r owns [lo, hi)."""
     if n_coils < world:

@@ -116,3 +116,17 @@ def test_bench_algorithmic_bytes_match_survey():
     # the per-kernel figures add up to the per-transform figure (coordinates/image counted once)
     parts = ab["pad"] + ab["fft"] + ab["interp"]
     assert abs(parts - 32 * ab["per_transform_per_coil"]) / parts < 0.06
+
+
+def test_numa_binding_is_best_effort_without_a_gpu():
+    """`bind_to_gpu_numa_node` never raises and leaves the affinity alone when the topology is not visible."""
+    import os
+
+    from mrinufft_b200.dist import bind_to_gpu_numa_node
+
+    before = os.sched_getaffinity(0)
+    res = bind_to_gpu_numa_node(0)
+    assert res is None or (isinstance(res, tuple) and len(res) == 2)
+    if res is None:
+        assert os.sched_getaffinity(0) == before
+    os.sched_setaffinity(0, before)
