@@ -528,6 +528,149 @@ class MRIB200NUFFT(FourierOperatorBase):
                         grad[b, c0:c1].data_ptr(), c1 - c0, 0, inv_norm, self.stream)
         return grad
 
+    # ------------------------------------------------------------------ host arrays, several device calls
+    # When a batch of host (numpy) data runs as several library calls -- more coils than fit one
+    # workspace, or several batch volumes -- the k-space chunks cross PCIe on dedicated copy streams
+    # while the previous / next chunk is being transformed: the role of cufinufft's `async_transfer`
+    # pipelines (cufinufft.py:538-606, 647-700, 816-900), always on.  A single call (the 32 coils of one
+    # volume fit one workspace on a B200) has nothing to overlap with and takes the plain path.
+    def _host_pipeline_applies(self, arr) -> bool:
+        if not isinstance(arr, np.ndarray) or self._spread_only:
+            return False
+        return self.n_batchs * len(self._chunks()) > 1
+
+    def _copy_streams(self):
+        if getattr(self, "_h2d_stream", None) is None:
+            self._h2d_stream = torch.cuda.Stream(self.device)
+            self._d2h_stream = torch.cuda.Stream(self.device)
+        return self._h2d_stream, self._d2h_stream
+
+    @staticmethod
+    def _host_tensor(arr, dtype):
+        a = np.ascontiguousarray(np.asarray(arr).astype(
+            {torch.complex64: np.complex64, torch.complex128: np.complex128}[dtype], copy=False))
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore", UserWarning)  # read-only inputs are never written to
+            return torch.from_numpy(a)
+
+    def _op_host_pipelined(self, data) -> np.ndarray:
+        """``op`` on a host array: type 2 per chunk, device -> host copies of the finished chunk's
+        k-space overlapped with the next chunk's transform (calibrationless: its image chunk comes in
+        on the other copy stream meanwhile).  Returns the full ``(B, C, K)`` numpy array."""
+        B, C, K, XYZ = self.n_batchs, self.n_coils, self.n_samples, self.shape
+        dev, cdt, raw = self.device, self._cdt, self.raw_op
+        inv_norm = 1.0 if self._double else float(self.inv_norm_factor)
+        cur = torch.cuda.current_stream(dev)
+        h2d, d2h = self._copy_streams()
+        h2d.wait_stream(cur)   # the buffers below may be recycled blocks with work pending on `cur`
+        d2h.wait_stream(cur)
+        T = max(c1 - c0 for c0, c1 in self._chunks())
+        src = self._host_tensor(data, cdt)
+        out_h = torch.empty((B, C, K), dtype=cdt, pin_memory=True)
+        kbuf = [torch.empty((T, K), dtype=cdt, device=dev) for _ in range(2)]
+        if self.uses_sense:
+            img_d = src.reshape(B, *XYZ).to(dev, non_blocking=True)
+        else:
+            src = src.reshape(B, C, *XYZ)
+            ibuf = [torch.empty((T, *XYZ), dtype=cdt, device=dev) for _ in range(2)]
+        d2h_done, comp_done = [None, None], [None, None]
+        i = 0
+        for b in range(B):
+            for c0, c1 in self._chunks():
+                k, n = i % 2, c1 - c0
+                if d2h_done[k] is not None:
+                    cur.wait_event(d2h_done[k])          # kbuf[k] has been copied out
+                if self.uses_sense:
+                    raw.type2(img_d[b], self._smaps_d[c0:c1], kbuf[k][:n], inv_norm, self._conj_smaps)
+                else:
+                    with torch.cuda.stream(h2d):
+                        if comp_done[k] is not None:
+                            h2d.wait_event(comp_done[k])  # ibuf[k] has been consumed
+                        ibuf[k][:n].copy_(src[b, c0:c1], non_blocking=True)
+                        arrived = torch.cuda.Event()
+                        arrived.record(h2d)
+                    cur.wait_event(arrived)
+                    raw.type2(ibuf[k][:n], None, kbuf[k][:n], inv_norm)
+                if self._double:
+                    kbuf[k][:n] *= float(self.inv_norm_factor)
+                comp_done[k] = torch.cuda.Event()
+                comp_done[k].record(cur)
+                with torch.cuda.stream(d2h):
+                    d2h.wait_event(comp_done[k])
+                    out_h[b, c0:c1].copy_(kbuf[k][:n], non_blocking=True)
+                    d2h_done[k] = torch.cuda.Event()
+                    d2h_done[k].record(d2h)
+                i += 1
+        d2h.synchronize()
+        for t in kbuf:
+            t.record_stream(d2h)
+        if not self.uses_sense:
+            for t in ibuf:
+                t.record_stream(h2d)
+        return out_h.numpy()
+
+    def _adj_host_pipelined(self, coeffs) -> np.ndarray:
+        """``adj_op`` on a host array: the next chunk's k-space comes in on a copy stream while the
+        current chunk is transformed; SENSE accumulates the coil-combined image on the device,
+        calibrationless images leave chunk by chunk on the other copy stream."""
+        B, C, K, XYZ = self.n_batchs, self.n_coils, self.n_samples, self.shape
+        dev, cdt, raw = self.device, self._cdt, self.raw_op
+        inv_norm = 1.0 if self._double else float(self.inv_norm_factor)
+        cur = torch.cuda.current_stream(dev)
+        h2d, d2h = self._copy_streams()
+        h2d.wait_stream(cur)
+        d2h.wait_stream(cur)
+        T = max(c1 - c0 for c0, c1 in self._chunks())
+        src = self._host_tensor(coeffs, cdt).reshape(B, C, K)
+        kbuf = [torch.empty((T, K), dtype=cdt, device=dev) for _ in range(2)]
+        sense = self.uses_sense
+        if sense:
+            img_d = torch.empty((B, 1, *XYZ), dtype=cdt, device=dev)
+        else:
+            out_h = torch.empty((B, C, *XYZ), dtype=cdt, pin_memory=True)
+            obuf = [torch.empty((T, *XYZ), dtype=cdt, device=dev) for _ in range(2)]
+        comp_done, d2h_done = [None, None], [None, None]
+        i = 0
+        for b in range(B):
+            for j, (c0, c1) in enumerate(self._chunks()):
+                k, n = i % 2, c1 - c0
+                with torch.cuda.stream(h2d):
+                    if comp_done[k] is not None:
+                        h2d.wait_event(comp_done[k])      # kbuf[k] has been consumed
+                    kbuf[k][:n].copy_(src[b, c0:c1], non_blocking=True)
+                    arrived = torch.cuda.Event()
+                    arrived.record(h2d)
+                cur.wait_event(arrived)
+                if sense:
+                    raw.type1(kbuf[k][:n], self._density_d, self._smaps_d[c0:c1], img_d[b, 0],
+                              accumulate=j > 0, scale=inv_norm, conj_smaps=self._conj_smaps)
+                else:
+                    if d2h_done[k] is not None:
+                        cur.wait_event(d2h_done[k])       # obuf[k] has been copied out
+                    raw.type1(kbuf[k][:n], self._density_d, None, obuf[k][:n], accumulate=False,
+                              scale=inv_norm)
+                    if self._double:
+                        obuf[k][:n] *= float(self.inv_norm_factor)
+                comp_done[k] = torch.cuda.Event()
+                comp_done[k].record(cur)
+                if not sense:
+                    with torch.cuda.stream(d2h):
+                        d2h.wait_event(comp_done[k])
+                        out_h[b, c0:c1].copy_(obuf[k][:n], non_blocking=True)
+                        d2h_done[k] = torch.cuda.Event()
+                        d2h_done[k].record(d2h)
+                i += 1
+        for t in kbuf:
+            t.record_stream(h2d)
+        if sense:
+            if self._double:
+                img_d *= float(self.inv_norm_factor)
+            return from_device(img_d, "numpy", None)
+        d2h.synchronize()
+        for t in obuf:
+            t.record_stream(d2h)
+        return out_h.numpy()
+
     # ------------------------------------------------------------------ public API
     def op(self, data, ksp=None):
         r"""Non-Cartesian MRI forward operator :math:`\mathcal{F}\mathcal{S}_\ell x` (base.py:949-977).
@@ -535,6 +678,8 @@ class MRIB200NUFFT(FourierOperatorBase):
         Accepts numpy / torch / cupy arrays; the result has the type and device of ``data``.
         """
         self.check_shape(image=data, ksp=ksp)
+        if ksp is None and self._host_pipeline_applies(data):
+            return self._safe_squeeze(self._op_host_pipelined(data))
         img, kind, dev = self._in(data)
         out = None
         if ksp is not None and module_name(ksp) == "torch" and ksp.is_cuda and ksp.is_contiguous() \
@@ -550,6 +695,8 @@ class MRIB200NUFFT(FourierOperatorBase):
     def adj_op(self, coeffs, img=None):
         """Non-Cartesian MRI adjoint operator (base.py:1015-1035)."""
         self.check_shape(image=img, ksp=coeffs)
+        if img is None and self._host_pipeline_applies(coeffs):
+            return self._safe_squeeze(self._adj_host_pipelined(coeffs))
         ksp, kind, dev = self._in(coeffs)
         out = None
         if img is not None and module_name(img) == "torch" and img.is_cuda and img.is_contiguous() \

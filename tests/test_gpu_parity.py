@@ -365,6 +365,48 @@ def test_pipe_matches_cpu_oracle(mods):
     assert rel_l2(d, dd) < 2e-5
 
 
+@pytest.mark.parametrize("sense", [True, False])
+@pytest.mark.parametrize("precision", ["single", "double"])
+def test_host_arrays_in_several_chunks_are_pipelined_and_equal_the_device_path(mods, sense, precision):
+    """numpy in, several library calls per batch (coil_chunk < n_coils, n_batchs > 1): the copy-stream
+    pipeline (role of cufinufft's async_transfer, tests/operators/test_cufinufft_async.py:50-95) returns what
+    the plain device path returns; inputs may be read-only and are not modified."""
+    mrinufft, _, torch = mods
+    rng = np.random.default_rng(8)
+    shape, M, C, B = (20, 24, 16), 3000, 6, 2
+    rdt, cdt = (np.float32, np.complex64) if precision == "single" else (np.float64, np.complex128)
+    samples = rng.uniform(-np.pi, np.pi, (M, 3)).astype(rdt)
+    smaps = None
+    if sense:
+        smaps = (rng.standard_normal((C, *shape)) + 1j * rng.standard_normal((C, *shape))).astype(cdt)
+        smaps /= np.linalg.norm(smaps, axis=0)
+    op = mrinufft.get_operator("b200")(samples, shape, n_coils=C, n_batchs=B, smaps=smaps, squeeze_dims=False,
+                                       coil_chunk=2, precision=precision,
+                                       density=rng.uniform(0.5, 1.5, M).astype(rdt))
+    assert op._host_pipeline_applies(np.zeros(1)) and len(op._chunks()) == 3
+    x = (rng.standard_normal(op.img_full_shape) + 1j * rng.standard_normal(op.img_full_shape)).astype(cdt)
+    y = (rng.standard_normal((B, C, M)) + 1j * rng.standard_normal((B, C, M))).astype(cdt)
+    x0, y0 = x.copy(), y.copy()
+    x.setflags(write=False)
+    y.setflags(write=False)
+    ax = op.op(x)                                             # pipelined (numpy in)
+    ax_dev = op.op(torch.from_numpy(x0).cuda()).cpu().numpy() # plain device path (torch in)
+    assert isinstance(ax, np.ndarray) and ax.shape == (B, C, M) and ax.dtype == cdt
+    tol = 2e-6 if precision == "single" else 1e-11   # same kernels; atomics may commit in another order
+    assert rel_l2(ax, ax_dev) < tol
+    ahy = op.adj_op(y)
+    ahy_dev = op.adj_op(torch.from_numpy(y0).cuda()).cpu().numpy()
+    assert isinstance(ahy, np.ndarray) and ahy.shape == tuple(op.img_full_shape)
+    assert rel_l2(ahy, ahy_dev) < tol
+    assert np.array_equal(x, x0) and np.array_equal(y, y0)
+    # twice in a row: the rotating buffers and events of the first call do not leak into the second
+    assert rel_l2(op.op(x), ax) < tol and rel_l2(op.adj_op(y), ahy) < tol
+    # squeeze_dims follows the plain path
+    op1 = mrinufft.get_operator("b200")(samples, shape, n_coils=C, smaps=smaps, coil_chunk=2, precision=precision)
+    xs = x0[0, 0] if sense else x0[0]
+    assert op1.op(xs).shape == (C, M) and op1.adj_op(y0[0]).shape == (shape if sense else (C, *shape))
+
+
 # ------------------------------------------------------------------ solvers
 def test_cg_matches_reference_golden(mods):
     mrinufft, _, _ = mods
