@@ -789,16 +789,18 @@ k_rows(Geom g, int T, int nchunks, unsigned S, long long M, const uint4* __restr
     };
     // coil values of value block j (entries 16 j .. 16 j + 15 sit in lanes 16 (j & 1) .. of `is`, the
     // registers of packet block j >> 1): 2 points per instruction, 16 bytes per lane
+    // (destination and source-lane bases are formed once per call: inside the predicated copies the
+    // compiler re-derived them per point)
+    const unsigned vdst0 = vbuf_a + (unsigned)(hl * 32 + cl * 2) * 8u;
     auto values_issue = [&](int j, const uint2& is) {
       const int buf = j & 1;
       const unsigned sv = is.x < IDX_NONE ? is.y : IDX_NONE;
+      const unsigned vdst = vdst0 + (unsigned)buf * (VBLK * 256u);
+      const int lane0 = buf * VBLK + hl;
 #pragma unroll
       for (int i = 0; i < VBLK / 2; ++i) {
-        const int kk = 2 * i + hl;
-        const unsigned sk = __shfl_sync(FULL, sv, buf * VBLK + kk);
-        if (sk != IDX_NONE)
-          cp_async16(vbuf_a + (unsigned)((buf * VBLK + kk) * 32 + cl * 2) * 8u,
-                     ktl + (unsigned long long)sk * 256u);
+        const unsigned sk = __shfl_sync(FULL, sv, lane0 + 2 * i);
+        if (sk != IDX_NONE) cp_async16(vdst + (unsigned)i * 512u, ktl + (unsigned long long)sk * 256u);
       }
     };
 
