@@ -817,6 +817,32 @@ def test_off_resonance_batched_matches_reference_wrapper(mods, shape, C, sense):
     assert yt.is_cuda and np.allclose(yt.cpu().numpy(), ax, rtol=1e-5, atol=1e-6)
 
 
+def test_paired_batch_autograd_uses_each_items_own_maps(mods):
+    """``make_autograd(paired_batch=D)`` (autodiff.py:291-360) with torch CUDA maps per item: forward and data
+    gradients of item d are those of maps[d] (same check as tests/test_autodiff_cpu.py on the reference NDFT)."""
+    mrinufft, _, torch = mods
+    rng = np.random.default_rng(12)
+    shape, M, C, D = (12, 16), 300, 3, 3
+    samples = rng.uniform(-np.pi, np.pi, (M, 2)).astype(np.float32)
+    maps = (rng.standard_normal((D, C, *shape)) + 1j * rng.standard_normal((D, C, *shape))).astype(np.complex64)
+    maps /= np.linalg.norm(maps, axis=1, keepdims=True)
+    op = mrinufft.get_operator("b200")(samples, shape, n_coils=C, smaps=maps[0], squeeze_dims=False)
+    ag = op.make_autograd(wrt_data=True, paired_batch=D)
+    maps_t = torch.from_numpy(maps).cuda()
+    x = torch.from_numpy((rng.standard_normal((D, 1, 1, *shape)) + 1j * rng.standard_normal((D, 1, 1, *shape))
+                          ).astype(np.complex64)).cuda().requires_grad_(True)
+    w = torch.from_numpy((rng.standard_normal((D, 1, C, M)) + 1j * rng.standard_normal((D, 1, C, M))
+                          ).astype(np.complex64)).cuda()
+    y = ag.op(x, smaps=maps_t)
+    assert tuple(y.shape) == (D, 1, C, M)
+    torch.sum(torch.abs(y - w) ** 2).backward()
+    for d in range(D):
+        op.smaps = maps[d]
+        assert rel_l2(y[d].detach().cpu().numpy(), op.op(x[d].detach().cpu().numpy())) < 1e-6
+        want = 2 * op.adj_op((y[d] - w[d]).detach().cpu().numpy())
+        assert rel_l2(x.grad[d].cpu().numpy(), want) < 1e-5
+
+
 @pytest.mark.parametrize("C,sense", [(1, False), (3, True)])
 def test_field_map_autograd_through_the_batched_orc_operator(mods, C, sense):
     """``with_off_resonance_correction(...).make_autograd(wrt_field_map=True)`` (off_resonance.py:399-446,
