@@ -103,6 +103,7 @@ struct RowsState {
   long long nrows = 0, nsplit = 0, nvis = 0;
   unsigned S = 0;                // stream length in entries
   int nchunks = 0;
+  int lch = LCH;  // entries per chunk of this trajectory's stream (smaller for short streams, see build_stream)
   long long M = -1;
   bool valid = false;
   bool unsupported = false;      // too many visits / points for the 32-bit stream words
@@ -334,7 +335,7 @@ k_build_stream(Geom g, long long nrows, const int32_t* __restrict__ bin_start,
                const int32_t* __restrict__ tot, const uint32_t* __restrict__ start,
                const float* __restrict__ rec, uint4* __restrict__ ent,
                int32_t* __restrict__ chunk_row, int32_t* __restrict__ split_rows,
-               int* __restrict__ split_counter) {
+               int* __restrict__ split_counter, uint32_t lch) {
   const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (row >= nrows) return;
@@ -343,8 +344,8 @@ k_build_stream(Geom g, long long nrows, const int32_t* __restrict__ bin_start,
   const uint32_t hs = start[row], he = hs + 1u + (uint32_t)t;
   if (lane == 0) {
     ent[hs] = make_uint4(0u, 0u, IDX_HDR, (uint32_t)row);
-    for (uint32_t c = (hs + LCH - 1) / LCH; c * (uint32_t)LCH < he; ++c) chunk_row[c] = (int32_t)row;
-    if (hs / LCH != (he - 1) / LCH) split_rows[atomicAdd(split_counter, 1)] = (int32_t)row;
+    for (uint32_t c = (hs + lch - 1) / lch; c * lch < he; ++c) chunk_row[c] = (int32_t)row;
+    if (hs / lch != (he - 1) / lch) split_rows[atomicAdd(split_counter, 1)] = (int32_t)row;
   }
   if (t == 0) return;
   RowCoord rc;
@@ -606,11 +607,14 @@ __device__ __forceinline__ void prefetch_l2(const void* p) {
 // accumulators it holds changes whenever a header entry comes by.  Staging is pure data movement:
 // entries are read one packet block ahead (coalesced), the x weights and the coil values of their
 // points arrive through cp.async, and their cache lines are pulled into L2 another block earlier.
-template <int DIM, int W, bool SPREAD>
+// FIXED: chunks of LCH entries, a compile-time constant (the long streams the kernel is tuned on: with the
+// chunk length in a register the spreader spills three more words); otherwise 2^lch_log2 entries (short streams)
+template <int DIM, int W, bool SPREAD, bool FIXED>
 __global__ void __launch_bounds__(THREADS, 4)
 k_rows(Geom g, int T, int nchunks, unsigned S, long long M, const uint4* __restrict__ ent,
        const int32_t* __restrict__ chunk_row, const float* __restrict__ ptab,
-       float2* __restrict__ kt, float2* __restrict__ fw, int* __restrict__ counter, int dbg, int skip_empty) {
+       float2* __restrict__ kt, float2* __restrict__ fw, int* __restrict__ counter, int dbg, int skip_empty,
+       int lch_log2) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   constexpr int SMW = smem_per_warp(SPREAD);
   constexpr unsigned FULL = 0xffffffffu;
@@ -640,9 +644,11 @@ k_rows(Geom g, int T, int nchunks, unsigned S, long long M, const uint4* __restr
     if (lane == 0) c = atomicAdd(counter, 1);
     c = __shfl_sync(FULL, c, 0);
     if (c >= nchunks) break;
-    const unsigned base = (unsigned)c * LCH;
+    const int lg = FIXED ? 11 : lch_log2;
+    static_assert(LCH == 2048, "FIXED chunks are 2^11 entries");
+    const unsigned base = (unsigned)c << lg;
     const uint4* v = ent + base;
-    const int nw = (int)min((unsigned)LCH, S - base);
+    const int nw = (int)min(1u << lg, S - base);
     // consume blocks: 16 entries for the spreader (the granularity of its value copies), a whole packet
     // block of 32 for the interpolator (half the per-block bookkeeping)
     constexpr int SB = SPREAD ? VBLK : MBLK, SPB = MBLK / SB;
@@ -931,7 +937,13 @@ int build_stream(b200_plan* p, RowsState* ts, cudaStream_t st) {
   uint32_t S = 0;
   CUDA_TRY(cudaMemcpyAsync(&S, ts->d_start + nrows, 4, cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaStreamSynchronize(st));
-  const int nchunks = (int)((S + LCH - 1) / LCH);
+  // Chunk = unit of dynamically scheduled work.  2048 entries amortise the per-chunk set-up on long streams;
+  // a short stream (2-D, few samples) is cut finer so that every resident warp still gets several chunks
+  // (cfg-B: 7.7e5 entries = 376 chunks of 2048 for 2368 warp slots).
+  int lch = LCH;
+  while (lch > 256 && (long long)S / lch < 8LL * p->num_sms * 4 * WARPS) lch >>= 1;
+  ts->lch = lch;
+  const int nchunks = (int)((S + lch - 1) / lch);
   // + 64 entries of all-ones padding: the kernel looks one entry past the last chunk.
   // Buffers only ever grow: update_samples in a trajectory-learning loop must not pay cudaFree's
   // device synchronisation and a multi-GB cudaMalloc per step.
@@ -978,7 +990,7 @@ int build_stream(b200_plan* p, RowsState* ts, cudaStream_t st) {
   }
   k_build_stream<DIM, W><<<ceil_div(nrows * 32, 256), 256, 0, st>>>(
       p->g, nrows, p->d_bin_start, ts->d_tot, ts->d_start, ts->d_rec, ts->d_ent, ts->d_chunk_row,
-      ts->d_split_rows, ts->d_counters + 1);
+      ts->d_split_rows, ts->d_counters + 1, (uint32_t)ts->lch);
   CHECK_LAUNCH();
   int nsplit = 0;
   CUDA_TRY(cudaMemcpyAsync(&nsplit, ts->d_counters + 1, 4, cudaMemcpyDeviceToHost, st));
@@ -1024,9 +1036,9 @@ int prepare(b200_plan* p, RowsState* ts, cudaStream_t st) {
   return B200_OK;
 }
 
-template <int DIM, int W, bool SPREAD>
-int launch_rows(b200_plan* p, RowsState* ts, float2* fw, int T, cudaStream_t st) {
-  auto kern = k_rows<DIM, W, SPREAD>;
+template <int DIM, int W, bool SPREAD, bool FIXED>
+int launch_rows_v(b200_plan* p, RowsState* ts, float2* fw, int T, cudaStream_t st) {
+  auto kern = k_rows<DIM, W, SPREAD, FIXED>;
   const size_t smem = (size_t)WARPS * smem_per_warp(SPREAD);
   static bool attr_done = false;
   static int ctas_per_sm = 1;
@@ -1050,7 +1062,7 @@ int launch_rows(b200_plan* p, RowsState* ts, float2* fw, int T, cudaStream_t st)
   if (timed) cudaEventRecord(p->ev[8], st);
   kern<<<grid, THREADS, smem, st>>>(p->g, T, ts->nchunks, ts->S, p->M, ts->d_ent, ts->d_chunk_row,
                                     ts->d_ptab, ts->d_kt, fw, ts->d_counters, p->rows_dbg,
-                                    (SPREAD && p->spread_may_skip_empty) ? 1 : 0);
+                                    (SPREAD && p->spread_may_skip_empty) ? 1 : 0, 31 - __builtin_clz(ts->lch));
   if (SPREAD) {
     p->spread_empty = p->spread_may_skip_empty ? ts->d_empty : nullptr;
     p->empty_nyh = p->g.nf[DIM - 2] / 2;
@@ -1062,6 +1074,12 @@ int launch_rows(b200_plan* p, RowsState* ts, float2* fw, int T, cudaStream_t st)
   }
   CHECK_LAUNCH();
   return B200_OK;
+}
+
+template <int DIM, int W, bool SPREAD>
+int launch_rows(b200_plan* p, RowsState* ts, float2* fw, int T, cudaStream_t st) {
+  if (ts->lch == LCH) return launch_rows_v<DIM, W, SPREAD, true>(p, ts, fw, T, st);
+  return launch_rows_v<DIM, W, SPREAD, false>(p, ts, fw, T, st);
 }
 
 int ensure_kt(RowsState* ts, long long M) {
