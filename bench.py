@@ -411,7 +411,7 @@ def run_b200(args):
     achieved = ab[dom_name] / (dom_ms * 1e-3) / 1e9
     is_cfg_c = (args.n == 256 and C == 32 and M == 1 << 23 and args.traj == "radial")
     roofline = {
-        "bound": "hbm", "kernel": f"k_rows<3,{plan.w},{'true' if dom_name == 'spread' else 'false'}> ({dom_name})",
+        "bound": "hbm", "kernel": f"k_rows<3,{plan.w},{'true' if dom_name == 'spread' else 'false'},true> ({dom_name})",
         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
         # dram__bytes_read.sum + dram__bytes_write.sum of one launch, `ncu --set full` (profiles/)
         "traffic": (NCU_TRAFFIC_GB[dom_name] * 1e9 if is_cfg_c else None),
