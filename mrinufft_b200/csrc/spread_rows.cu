@@ -941,7 +941,7 @@ int build_stream(b200_plan* p, RowsState* ts, cudaStream_t st) {
   // a short stream (2-D, few samples) is cut finer so that every resident warp still gets several chunks
   // (cfg-B: 7.7e5 entries = 376 chunks of 2048 for 2368 warp slots).
   int lch = LCH;
-  while (lch > 256 && (long long)S / lch < 8LL * p->num_sms * 4 * WARPS) lch >>= 1;
+  while (lch > 128 && (long long)S / lch < 8LL * p->num_sms * 4 * WARPS) lch >>= 1;
   ts->lch = lch;
   const int nchunks = (int)((S + lch - 1) / lch);
   // + 64 entries of all-ones padding: the kernel looks one entry past the last chunk.
