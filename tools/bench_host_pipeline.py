@@ -1,6 +1,9 @@
+"""Host arrays spanning two coil chunks: pipelined copy streams against the sequential path and the device-resident one."""
 # host-array op / adj_op with several chunks: pipelined vs sequential (coil_chunk forces 2 calls of 16 coils... and a 64-coil case)
 import sys, time, json
-sys.path.insert(0, "/root/repo"); sys.path.insert(0, "/root/repo/baseline/_ref")
+ROOT = __import__("pathlib").Path(__file__).resolve().parent.parent
+for _p in (ROOT, ROOT / "baseline" / "_ref"):
+    sys.path.insert(0, str(_p))
 import numpy as np, torch, mrinufft, mrinufft_b200
 from mrinufft.trajectories import initialize_3D_phyllotaxis_radial
 traj = initialize_3D_phyllotaxis_radial(4096, 512).astype(np.float32).reshape(-1, 3)

@@ -1,5 +1,8 @@
+"""cfg-B: is a small configuration bound by the host (enqueue time, cProfile) or by the device (events)?"""
 import sys, time, cProfile, pstats, io
-sys.path.insert(0, "/root/repo"); sys.path.insert(0, "/root/repo/baseline/_ref")
+ROOT = __import__("pathlib").Path(__file__).resolve().parent.parent
+for _p in (ROOT, ROOT / "baseline" / "_ref"):
+    sys.path.insert(0, str(_p))
 import numpy as np, torch, mrinufft, mrinufft_b200
 from mrinufft.trajectories import initialize_2D_spiral
 traj = initialize_2D_spiral(64, 2048, nb_revolutions=8).astype(np.float32)

@@ -1,5 +1,8 @@
+"""Secondary configurations A / B / E and the per-stage library timings of cfg-B (one GPU)."""
 import sys, json
-sys.path.insert(0, "/root/repo"); sys.path.insert(0, "/root/repo/baseline/_ref"); sys.path.insert(0, "/root/repo/tools")
+ROOT = __import__("pathlib").Path(__file__).resolve().parent.parent
+for _p in (ROOT, ROOT / "baseline" / "_ref", ROOT / "tools"):
+    sys.path.insert(0, str(_p))
 import numpy as np, torch, mrinufft, mrinufft_b200
 from bench_configs import cfg_a, cfg_b, cfg_e
 from mrinufft.trajectories import initialize_2D_spiral
