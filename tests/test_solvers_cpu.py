@@ -158,3 +158,20 @@ def test_givens_follows_the_reference_branches():
         want = _sym_ortho(a, b)
         for g, w in zip(got, want):
             assert np.allclose(g, w, rtol=1e-6, atol=0)
+
+
+@pytest.mark.parametrize("name", ["lsqr", "lsmr"])
+def test_damped_batches_equal_the_batches_solved_one_by_one(name):
+    """``damp > 0`` with ``n_batchs > 1``: the reference's lsqr raises there (``if r1sq < 0`` on an array,
+    optim.py:448), so the check is against the same solver run on every batch volume separately -- the
+    per-batch scalars must not leak between volumes."""
+    op2, y2, _ = _problem(2, False, False, seed=5)
+    x2 = solvers.SOLVERS[name](TorchFacade(op2), y2.copy(), damp=0.3, max_iter=8)
+    op1, _, _ = _problem(1, False, False, seed=5)     # same samples (same seed), one volume at a time
+    assert np.array_equal(op1.samples, op2.samples)
+    for b in range(2):
+        x1 = solvers.SOLVERS[name](TorchFacade(op1), y2[b:b + 1].copy(), damp=0.3, max_iter=8)
+        assert np.linalg.norm(x2[b] - x1.reshape(x2[b].shape)) < 1e-4 * np.linalg.norm(x1)
+    if name == "lsqr":
+        with pytest.raises(ValueError):
+            ref_lsqr(op2, y2.copy(), damp=0.3, max_iter=3, progressbar=False)
