@@ -600,6 +600,55 @@ def test_large_sampled_ndft_and_linearity(mods, shape, M, C):
     assert abs(lhs - rhs) / abs(rhs) < 5e-6
 
 
+def test_baseline_config_at_its_full_size(mods):
+    """BASELINE.json configs[2] exactly -- 3-D 256^3, 32 coils with smaps, M = 2^23 phyllotaxis-radial samples,
+    complex64 -- through properties that do not need a full-size reference: the exact NDFT at sampled k-space
+    locations, linearity, adjointness (which ties `adj_op` to the checked `op`), and the sort's invariants."""
+    mrinufft, _, torch = mods
+    if torch.cuda.mem_get_info()[0] < 80e9:
+        pytest.skip("needs about 70 GB of device memory")
+    from mrinufft.trajectories import initialize_3D_phyllotaxis_radial
+    from oracle import es_nufft as E
+
+    shape, C, M = (256, 256, 256), 32, 1 << 23
+    traj = initialize_3D_phyllotaxis_radial(16384, 512).astype(np.float32).reshape(-1, 3)
+    gen = torch.Generator(device="cuda").manual_seed(0)
+
+    def crandn(*s):
+        return torch.view_as_complex(torch.randn(*s, 2, device="cuda", generator=gen))
+
+    smaps = crandn(C, *shape)
+    smaps /= torch.linalg.norm(smaps, dim=0, keepdim=True)
+    op = mrinufft.get_operator("b200")(traj, shape, n_coils=C, smaps=smaps, squeeze_dims=False)
+    assert op.n_samples == M and len(op._chunks()) == 1          # one library call for all 32 coils
+    img, img2, ksp = crandn(1, 1, *shape), crandn(1, 1, *shape), crandn(1, C, M)
+    y = op.op(img)
+    # exact NDFT at 16 sampled locations, first and last coil (tolerance: the NDFT bar of this file)
+    rng = np.random.default_rng(0)
+    idx = np.sort(rng.choice(M, 16, replace=False))
+    img_h = img[0, 0].cpu().numpy().astype(np.complex128)
+    for c in (0, C - 1):
+        ref = E.ndft_type2_sampled(op.samples, img_h * smaps[c].cpu().numpy(), idx) / op.norm_factor
+        assert rel_l2(y[0, c, idx].cpu().numpy(), ref) <= 2 * TOL_NDFT
+    # linearity
+    y12 = op.op(img + 2j * img2)
+    y12 -= y + 2j * op.op(img2)
+    assert float(torch.linalg.norm(y12) / torch.linalg.norm(y)) < 3e-6
+    del y12
+    # adjointness, inner products in float64 on the device
+    x = op.adj_op(ksp)
+    lhs = torch.sum(torch.conj(y.to(torch.complex128)) * ksp.to(torch.complex128))
+    rhs = torch.sum(torch.conj(img.to(torch.complex128)) * x.to(torch.complex128))
+    assert float(torch.abs(lhs - rhs) / torch.abs(rhs)) < 1e-5
+    # the sort (perm = stable argsort of the bin keys): keys ascending along perm, ties in caller order,
+    # permutation complete
+    _, _, key, perm = op.raw_op.sort_indices()
+    steps = np.diff(key[perm].astype(np.int64))
+    assert np.all(steps >= 0)
+    assert np.all(np.diff(perm.astype(np.int64))[steps == 0] > 0)
+    assert np.array_equal(np.sort(perm), np.arange(M, dtype=perm.dtype))
+
+
 def test_empty_and_tiny_inputs(mods):
     mrinufft, _, _ = mods
     rng = np.random.default_rng(0)
