@@ -2,7 +2,7 @@
 
 Run in the build container only (needs /root/reference):
 
-    cd /tmp && python /root/repo/tests/golden/make_solver_golden.py
+    cd /tmp && python /root/repo/tests/golden/make_solver_golden.py [output directory]
 
 The unmodified reference solvers (``src/mrinufft/extras/optim.py:249-902``) run on the reference's
 exact NDFT (``RawNDFT``, ``src/mrinufft/operators/interfaces/nudft_numpy.py:82-130``) wrapped in its
@@ -22,7 +22,7 @@ from mrinufft.operators.base import FourierOperatorCPU  # noqa: E402
 from mrinufft.operators.interfaces.nudft_numpy import RawNDFT  # noqa: E402
 from scipy.stats import truncnorm  # noqa: E402
 
-OUT = Path(__file__).resolve().parent
+OUT = Path(sys.argv[1]) if len(sys.argv) > 1 else Path(__file__).resolve().parent   # optional: output directory
 
 
 class NDFTFull(FourierOperatorCPU):

@@ -175,3 +175,27 @@ def test_damped_batches_equal_the_batches_solved_one_by_one(name):
     if name == "lsqr":
         with pytest.raises(ValueError):
             ref_lsqr(op2, y2.copy(), damp=0.3, max_iter=3, progressbar=False)
+
+
+@pytest.mark.timeout(300)
+def test_committed_solver_goldens_are_what_the_reference_produces(tmp_path):
+    """Re-run tests/golden/make_solver_golden.py against the reference checkout (build container only) and
+    compare with the committed fixtures the GPU suite replays."""
+    import subprocess
+    import sys
+    from pathlib import Path
+
+    if not Path("/root/reference/src/mrinufft").is_dir():
+        pytest.skip("the reference checkout is only present in the build container")
+    golden = Path(__file__).resolve().parent / "golden"
+    r = subprocess.run([sys.executable, str(golden / "make_solver_golden.py"), str(tmp_path)],
+                       capture_output=True, text=True, cwd=tmp_path, timeout=280)
+    assert r.returncode == 0, r.stderr[-2000:]
+    for name in ("solvers2D_sense", "solvers2D_batch_density", "solvers3D_sense_damp"):
+        with np.load(golden / f"{name}.npz") as a, np.load(tmp_path / f"{name}.npz") as b:
+            assert sorted(a.files) == sorted(b.files)
+            for k in a.files:
+                if k.startswith("it_cg"):   # cg's step size comes from a 10-step power method: looser
+                    assert np.allclose(a[k], b[k], rtol=1e-4, atol=1e-6), (name, k)
+                else:
+                    assert np.allclose(a[k], b[k], rtol=1e-6, atol=1e-8), (name, k)
