@@ -25,7 +25,7 @@ from mrinufft.trajectories import initialize_2D_radial, initialize_2D_spiral  # 
 from mrinufft.trajectories import initialize_3D_cones  # noqa: E402
 from scipy.stats import truncnorm  # noqa: E402
 
-OUT = Path(__file__).resolve().parent
+OUT = Path(sys.argv[1]) if len(sys.argv) > 1 else Path(__file__).resolve().parent   # optional: output directory
 
 
 def crandn(rng, *shape):

@@ -138,3 +138,26 @@ def test_empty_and_single_point():
     assert rel_l2(cpu.type1(np.array([1 + 2j])).ravel(), A.conj().T @ np.array([1 + 2j])) < 3e-6
     r = E.bin_sort(np.zeros((0, 2), np.float32), (32, 32), 7)
     assert r["perm"].shape == (0,)
+
+
+@pytest.mark.timeout(300)
+def test_committed_goldens_are_what_the_reference_produces(tmp_path):
+    """Re-run tests/golden/make_golden.py against the reference checkout (build container only) and compare
+    with the committed fixtures: they are outputs of the unmodified reference, not of anything in this repo."""
+    import subprocess
+    import sys
+    from pathlib import Path
+
+    if not Path("/root/reference/src/mrinufft").is_dir():
+        pytest.skip("the reference checkout is only present in the build container")
+    golden = Path(__file__).resolve().parent / "golden"
+    r = subprocess.run([sys.executable, str(golden / "make_golden.py"), str(tmp_path)],
+                       capture_output=True, text=True, cwd=tmp_path, timeout=280)
+    assert r.returncode == 0, r.stderr[-2000:]
+    made = sorted(p.name for p in tmp_path.glob("*.npz"))
+    assert made == sorted(f"{c}.npz" for c in GOLDEN_CASES + ["cg2D_sense"])
+    for name in made:
+        with np.load(golden / name) as a, np.load(tmp_path / name) as b:
+            assert sorted(a.files) == sorted(b.files)
+            for k in a.files:
+                assert np.allclose(a[k], b[k], rtol=1e-6, atol=1e-8), (name, k)
