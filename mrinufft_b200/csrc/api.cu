@@ -141,6 +141,19 @@ int grid_to_image(b200_plan* p, const float2* smaps, float2* img, int T, int acc
   return k4b_crop(p, p->d_fw, smaps, img, T, accumulate, scale, conj_smaps, st);
 }
 
+// residual buffer of data_consistency / pipe: [ntrans_max][M], grown whenever the current M needs more
+// than it holds (setpts only frees it when M exceeds the point capacity)
+int ensure_ksp_tmp(b200_plan* p) {
+  const size_t need = (size_t)p->ntrans_max * (size_t)(p->M > 0 ? p->M : 1) * sizeof(float2);
+  if (p->d_ksp_tmp && p->ksp_tmp_bytes >= need) return B200_OK;
+  if (p->d_ksp_tmp) CUDA_TRY(cudaFree(p->d_ksp_tmp));
+  p->d_ksp_tmp = nullptr;
+  p->ksp_tmp_bytes = 0;
+  CUDA_TRY(cudaMalloc(&p->d_ksp_tmp, need));
+  p->ksp_tmp_bytes = need;
+  return B200_OK;
+}
+
 int check_exec(b200_plan* p, int T, bool need_fft) {
   if (!p) {
     b200_set_error("null plan");
@@ -548,10 +561,7 @@ int b200_data_consistency(b200_plan* p, const void* img, const void* smaps, cons
   cudaStream_t st = (cudaStream_t)stream;
   if (p->dbl)
     return dbl_data_consistency(p, img, smaps, obs, density, grad, T, accumulate, (double)scale, st);
-  if (!p->d_ksp_tmp) {
-    CUDA_TRY(cudaMalloc(&p->d_ksp_tmp,
-                        (size_t)p->ntrans_max * (size_t)(p->M > 0 ? p->M : 1) * sizeof(float2)));
-  }
+  B200_TRY(ensure_ksp_tmp(p));
   B200_TRY(image_to_grid(p, (const float2*)img, (const float2*)smaps, T, -1, 0, st, true));
   // K5: residual fused into the interpolation epilogue
   B200_TRY(do_interp(p, p->d_fw, p->d_ksp_tmp, T, scale, (const float2*)obs, st));
@@ -628,8 +638,7 @@ int b200_pipe_iteration(b200_plan* p, float* d, void* stream) {
   B200_TRY(check_exec(p, 1, false));
   DeviceGuard guard(p->device);
   cudaStream_t st = (cudaStream_t)stream;
-  const size_t M = (size_t)(p->M > 0 ? p->M : 1);
-  if (!p->d_ksp_tmp) CUDA_TRY(cudaMalloc(&p->d_ksp_tmp, (size_t)p->ntrans_max * M * sizeof(float2)));
+  B200_TRY(ensure_ksp_tmp(p));
   if (!p->d_fw) {
     CUDA_TRY(cudaMalloc(&p->d_fw, (size_t)p->g.nftot * sizeof(float2)));
     p->ws_bytes += (size_t)p->g.nftot * sizeof(float2);

@@ -108,6 +108,7 @@ struct b200_plan {
   // workspace
   float2* d_fw = nullptr;       // [ntrans_max][nftot] oversampled grids
   float2* d_ksp_tmp = nullptr;  // [ntrans_max][M] residual of data_consistency
+  size_t ksp_tmp_bytes = 0;     // its capacity: M may grow again after it was sized for a smaller M
   float* d_pipe_tmp = nullptr;
   size_t ws_bytes = 0;
 

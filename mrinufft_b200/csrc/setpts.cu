@@ -133,6 +133,7 @@ static int ensure_point_capacity(b200_plan* p, long long M) {
   p->d_key_u = p->d_key_s = p->d_perm = p->d_iota = nullptr;
   p->d_sort_tmp = nullptr;
   p->d_ksp_tmp = nullptr;
+  p->ksp_tmp_bytes = 0;
   p->d_pipe_tmp = nullptr;
   p->Mcap = 0;
   size_t n = (size_t)M;

@@ -75,17 +75,43 @@ class MRIB200FourierCorrected(MRIFourierCorrected):
             density=False, eps=fo.eps, upsampfac=fo.upsampfac, gpu_device_id=dev.index,
             coil_chunk=min(32, L * C),
         )
+        if fo.raw_op.isign_flip != vop.raw_op.isign_flip:
+            vop.raw_op.toggle_grad_traj()
         self._fused = {"vop": vop, "B": Bd.reshape(-1, L).contiguous(), "L": L, "C": C,
-                       "smaps_id": id(fo._smaps_d)}
+                       "smaps_id": id(fo._smaps_d), "pts_id": id(fo.raw_op._pts)}
         return True
 
     def _vop(self):
-        fo, f = self._fourier_op, self._fused
+        """The batched operator, brought in line with the inner operator's current state, or ``None``
+        when the call has to take the reference loop.
+
+        ``update_samples`` / ``grad_traj_plan`` / the ``smaps`` and ``density`` setters reach the inner
+        operator through ``MRIFourierCorrected.__getattr__`` and never this class, so the state is
+        compared on every call: new sample locations are handed to the batched plan (the device copy
+        of the inner plan, no host round trip), a flipped FFT sign is mirrored, replaced maps rebuild
+        the virtual coils.  With conjugated maps (trajectory VJP of a SENSE operator,
+        ``base.py:1234-1238``) only ``S`` is conjugated, not ``C[l]``: ``conj(V)`` would be wrong, so
+        that state uses the reference loop on the inner (toggled) operator.
+        """
+        fo = self._fourier_op
+        if fo._conj_smaps:
+            return None
+        f = self._fused
         if fo.uses_sense and f["smaps_id"] != id(fo._smaps_d):  # smaps were replaced: rebuild
             self._fused = None
-            self._ensure_fused()
+            if not self._ensure_fused():
+                return None
             f = self._fused
         vop = f["vop"]
+        if f["pts_id"] != id(fo.raw_op._pts):
+            if fo.n_samples != int(self.n_shots) * int(self.n_samples_per_shot):
+                return None  # the temporal interpolator no longer matches the trajectory
+            vop.raw_op._set_pts(fo.raw_op._pts)
+            vop._samples = fo._samples
+            vop._toeplitz_kernel = None
+            f["pts_id"] = id(fo.raw_op._pts)
+        if vop.raw_op.isign_flip != fo.raw_op.isign_flip:
+            vop.raw_op.toggle_grad_traj()
         vop._density_d = fo._density_d  # density multiplies k-space before the adjoint only
         vop._density = fo._density
         return vop
@@ -106,6 +132,8 @@ class MRIB200FourierCorrected(MRIFourierCorrected):
             return super().op(data, *args)
         fo = self._fourier_op
         vop = self._vop()
+        if vop is None:
+            return super().op(data)
         f = self._fused
         L, C, Bn = f["L"], f["C"], fo.n_batchs
         NS, NK = int(self.n_shots), int(self.n_samples_per_shot)
@@ -121,6 +149,8 @@ class MRIB200FourierCorrected(MRIFourierCorrected):
             return super().adj_op(coeffs, *args)
         fo = self._fourier_op
         vop = self._vop()
+        if vop is None:
+            return super().adj_op(coeffs)
         f = self._fused
         L, C, Bn = f["L"], f["C"], fo.n_batchs
         NS, NK = int(self.n_shots), int(self.n_samples_per_shot)

@@ -401,8 +401,10 @@ class MRIB200NUFFT(FourierOperatorBase):
         else:
             self._samples = self._normalize_samples(new_samples)
             self.raw_op._set_pts(self._samples)
-        if self._density_method is not None:
-            self.compute_density(self._density_method)
+        # like the reference (finufft.py:181): `compute_density(self._density_method)` unconditionally, so a
+        # density given as an array (no method recorded) does not survive new sample locations -- its
+        # weights belong to the old ones, and its length may no longer match
+        self.compute_density(self._density_method)
         self._toeplitz_kernel = None
 
     # ------------------------------------------------------------------ toggles for the trajectory gradient
@@ -686,8 +688,10 @@ class MRIB200NUFFT(FourierOperatorBase):
                 and ksp.dtype == self._cdt and ksp.device == self.device:
             out = ksp
         res = self._op_device(img, out)
+        if out is not None:
+            return ksp  # written in place: hand the caller's buffer back, whatever the input type was
         res = self._safe_squeeze(res)
-        if ksp is not None and out is None:
+        if ksp is not None:
             _copy_into(ksp, res)
             return ksp
         return self._out(res, kind, dev)
@@ -703,8 +707,10 @@ class MRIB200NUFFT(FourierOperatorBase):
                 and img.dtype == self._cdt and img.device == self.device:
             out = img
         res = self._adj_device(ksp, out)
+        if out is not None:
+            return img
         res = self._safe_squeeze(res)
-        if img is not None and out is None:
+        if img is not None:
             _copy_into(img, res)
             return img
         return self._out(res, kind, dev)
