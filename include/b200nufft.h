@@ -201,8 +201,21 @@ int b200_launch_count(int64_t* kernels, int64_t* ffts, int reset);
  *          coil-value copies; results are then wrong -- never set outside a profiling session;
  *          bit 3: pretend the visit stream does not fit 32-bit indices, which exercises the
  *          hand-over to the point-driven kernels -- set before b200_plan_setpts)
+ *   key 4: smallest coil class of the tiled kernels (0 = by the call's coil count T, else 1, 2, 4, 8,
+ *          16 or 32: a call with T coils runs in the smallest class >= max(T, value); tests use it to
+ *          push a small batch through every class)
  */
 int b200_plan_set_option(b200_plan* plan, int key, int64_t value);
+
+/*
+ * Which coil class of the tiled spread / interp kernels a call with T coils runs in (the reference
+ * has no counterpart: finufft loops over `n_trans`, cost proportional to coils,
+ * src/mrinufft/operators/base.py:980-1010; here a warp's 32 lanes are T coils x 32/T row groups).
+ *   out[0] = class (1, 2, 4, 8, 16, 32; 0 if the tiled kernels do not serve this plan)
+ *   out[1] = (point, tile) visits of that class's visit stream, out[2] = stream entries
+ *            (both 0 until a transform has built the stream), out[3] = 1 if the stream does not fit
+ */
+int b200_plan_rows_class(b200_plan* plan, int T, int64_t out[4]);
 
 /*
  * Timing hooks for the roofline report: the plan records CUDA events around its

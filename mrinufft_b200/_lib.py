@@ -60,6 +60,7 @@ _SIGNATURES = {
     "b200_pipe_iteration": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "b200_launch_count": (C.c_int, [C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.c_int]),
     "b200_plan_set_option": (C.c_int, [C.c_void_p, C.c_int, C.c_int64]),
+    "b200_plan_rows_class": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int64)]),
     "b200_plan_last_timings": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
     "b200_plan_enable_timing": (C.c_int, [C.c_void_p, C.c_int]),
 }
@@ -206,6 +207,12 @@ class Plan:
 
     def set_option(self, key, value):
         check(self._lib.b200_plan_set_option(self._h, int(key), int(value)), "b200_plan_set_option")
+
+    def rows_class(self, n_trans):
+        """Coil class the tiled kernels run a call with ``n_trans`` coils in, and the size of its stream."""
+        out = (C.c_int64 * 4)()
+        check(self._lib.b200_plan_rows_class(self._h, int(n_trans), out), "b200_plan_rows_class")
+        return {"class": int(out[0]), "visits": int(out[1]), "entries": int(out[2]), "unsupported": bool(out[3])}
 
     def enable_timing(self, on=True):
         check(self._lib.b200_plan_enable_timing(self._h, int(on)), "b200_plan_enable_timing")

@@ -14,11 +14,12 @@ int interp_point_driven(b200_plan* p, const float2* fw, float2* ksp, int T, floa
 int spread_tiled(b200_plan* p, const float2* ksp, const float* density, float2* fw, int T,
                  cudaStream_t st);
 int interp_tiled(b200_plan* p, const float2* fw, float2* ksp, int T, float scale,
-                 const float2* obs, cudaStream_t st);
+                 const float2* obs, const uint32_t* unread, cudaStream_t st);
+void tiled_class_info(b200_plan* p, int T, int64_t out[4]);
 bool tiled_supported(const b200_plan* p, int T);
 void tiled_free(b200_plan* p);
 void tiled_invalidate(b200_plan* p);
-const uint32_t* tiled_empty_bits(b200_plan* p, cudaStream_t st);
+const uint32_t* tiled_empty_bits(b200_plan* p, int T, cudaStream_t st);
 
 namespace {
 
@@ -96,9 +97,15 @@ int do_interp(b200_plan* p, const float2* fw, float2* ksp, int T, float scale, c
   int method = p->interp_method;
   if (method == 0) method = tiled_supported(p, T) ? 2 : 1;
   if (method == 2 && !tiled_supported(p, T)) method = 1;
+  const uint32_t* unread = p->interp_unread;
+  p->interp_unread = nullptr;
   if (method == 2) {
-    const int rc = interp_tiled(p, fw, ksp, T, scale, obs, st);
+    const int rc = interp_tiled(p, fw, ksp, T, scale, obs, unread, st);
     if (rc != 1) return rc;
+  }
+  if (unread) {
+    b200_set_error("internal: the grid was produced for the row interpolator, which cannot serve this call");
+    return B200_ESTATE;
   }
   return interp_point_driven(p, fw, ksp, T, scale, obs, st);
 }
@@ -117,8 +124,9 @@ int image_to_grid(b200_plan* p, const float2* img, const float2* smaps, int T, i
     if (for_interp && p->pts_set && p->M > 0 && p->g.dim == 3) {
       int method = p->interp_method;
       if (method == 0) method = tiled_supported(p, T) ? 2 : 1;
-      if (method == 2 && tiled_supported(p, T)) unread = tiled_empty_bits(p, st);
+      if (method == 2 && tiled_supported(p, T)) unread = tiled_empty_bits(p, T, st);
     }
+    p->interp_unread = unread;
     Timed tm(p, EV_FFT, st);
     return fftp_type2(p, img, smaps, p->d_fw, T, isign, conj_smaps, st, nullptr, unread);
   }
@@ -413,6 +421,17 @@ int b200_plan_info(const b200_plan* p, int64_t info[16]) {
   return B200_OK;
 }
 
+int b200_plan_rows_class(b200_plan* p, int T, int64_t out[4]) {
+  if (!p || !out) {
+    b200_set_error("b200_plan_rows_class: null argument");
+    return B200_EINVAL;
+  }
+  out[0] = out[1] = out[2] = out[3] = 0;
+  if (p->dbl || !tiled_supported(p, T)) return B200_OK;
+  tiled_class_info(p, T, out);
+  return B200_OK;
+}
+
 int b200_plan_kernel_params(const b200_plan* p, double out[4]) {
   if (!p || !out) {
     b200_set_error("b200_plan_kernel_params: null argument");
@@ -435,6 +454,13 @@ int b200_plan_set_option(b200_plan* p, int key, int64_t value) {
     case 1: p->interp_method = (int)value; break;
     case 2: p->fft_method = (int)value; break;
     case 3: p->rows_dbg = (int)value; break;
+    case 4:
+      if (value != 0 && value != 1 && value != 2 && value != 4 && value != 8 && value != 16 && value != 32) {
+        b200_set_error("option 4 (smallest coil class of the row kernels) takes 0, 1, 2, 4, 8, 16 or 32");
+        return B200_EINVAL;
+      }
+      p->rows_class = (int)value;
+      break;
     default:
       b200_set_error("unknown option key %d", key);
       return B200_EINVAL;

@@ -125,11 +125,13 @@ struct b200_plan {
   // zero-filled by the spreader nor read by the first FFT pass (flag byte per tile, see spread_rows.cu)
   bool spread_may_skip_empty = false;       // set by the caller of do_spread
   const uint32_t* spread_empty = nullptr;   // set by the spreader: valid for the grid it just wrote
+  const uint32_t* interp_unread = nullptr;  // set by the type-2 FFT: tiles of the grid it left unwritten
   int empty_nyh = 0, empty_nbx = 0;
 
   // options
   int spread_method = 0, interp_method = 0, fft_method = 0;
   int rows_dbg = 0;  // option 3: timing-experiment switches of the spreading row kernel (see b200nufft.h)
+  int rows_class = 0;  // option 4: smallest coil class the row kernels may pick (0: by the call's coil count)
 
   // timing
   bool timing = false;

@@ -48,6 +48,36 @@ def max_threads() -> int:
     return int(_load("f64").oracle_max_threads())
 
 
+def set_threads(n: int | None = None) -> int:
+    """Use ``n`` OpenMP threads (default: every CPU this process may run on) in both builds of the
+    library -- ``torch.distributed.run`` exports ``OMP_NUM_THREADS=1`` to its ranks.  Returns ``n``."""
+    n = int(n) if n else len(os.sched_getaffinity(0))
+    for prec in ("f64", "f32"):
+        lib = _load(prec)
+        lib.oracle_set_threads.argtypes = [C.c_int]
+        lib.oracle_set_threads(n)
+    return n
+
+
+class PortRawOp:
+    """The port behind the reference's ``raw_op`` contract (``FourierOperatorSimple._op/_adj_op``,
+    base.py:1013, 1068-1073; finufft.py:64-76): ``op(coeffs_out, image_in)``, ``adj_op(coeffs_in,
+    image_out)`` on ``(T, *shape)`` / ``(T, M)`` arrays, no smaps, no normalisation.  Lets the timing legs
+    run the reference's own ``FourierOperatorCPU`` coil loop around the finufft-algorithm port."""
+
+    def __init__(self, samples, shape, eps=1e-6, precision="f32", workers=None):
+        self.cpu = CpuNufft(samples, shape, eps=eps, precision=precision, workers=workers)
+        self.shape, self.n_samples = self.cpu.shape, self.cpu.M
+
+    def op(self, coeffs, image):
+        np.copyto(coeffs.reshape(-1, self.n_samples), self.cpu.type2(image.reshape(-1, *self.shape)))
+        return coeffs
+
+    def adj_op(self, coeffs, image):
+        np.copyto(image.reshape(-1, *self.shape), self.cpu.type1(coeffs.reshape(-1, self.n_samples)))
+        return image
+
+
 def _ptr(a):
     return a.ctypes.data_as(C.c_void_p)
 
@@ -68,8 +98,9 @@ class CpuNufft:
     precision "f64": complex128 checker; "f32": complex64, the timing baseline.
     """
 
-    def __init__(self, samples, shape, eps=1e-6, sigma=2.0, precision="f64", bins=None):
+    def __init__(self, samples, shape, eps=1e-6, sigma=2.0, precision="f64", bins=None, workers=None):
         self.lib = _load(precision)
+        self.workers = -1 if workers is None else int(workers)  # scipy.fft threads
         self.rdt = np.float64 if precision == "f64" else np.float32
         self.cdt = np.complex128 if precision == "f64" else np.complex64
         self.samples = np.ascontiguousarray(samples, dtype=np.float32)
@@ -122,18 +153,18 @@ class CpuNufft:
         fw_hat[(slice(None), *np.ix_(*self._mode_idx))] = img * self._dgrid()[None]
         axes = tuple(range(1, self.d + 1))
         if isign < 0:
-            fw = sfft.fftn(fw_hat, axes=axes, workers=-1, overwrite_x=True)
+            fw = sfft.fftn(fw_hat, axes=axes, workers=self.workers, overwrite_x=True)
         else:
-            fw = sfft.ifftn(fw_hat, axes=axes, norm="forward", workers=-1, overwrite_x=True)
+            fw = sfft.ifftn(fw_hat, axes=axes, norm="forward", workers=self.workers, overwrite_x=True)
         return self.interp(fw)
 
     def type1(self, c, isign=+1):
         fw = self.spread(c)
         axes = tuple(range(1, self.d + 1))
         if isign > 0:
-            F = sfft.ifftn(fw, axes=axes, norm="forward", workers=-1, overwrite_x=True)
+            F = sfft.ifftn(fw, axes=axes, norm="forward", workers=self.workers, overwrite_x=True)
         else:
-            F = sfft.fftn(fw, axes=axes, workers=-1, overwrite_x=True)
+            F = sfft.fftn(fw, axes=axes, workers=self.workers, overwrite_x=True)
         return F[(slice(None), *np.ix_(*self._mode_idx))] * self._dgrid()[None]
 
     # the reference's operator semantics (base.py:949-1073): smaps, density, 1/norm on both sides

@@ -234,3 +234,11 @@ int oracle_max_threads(void) {
   return 1;
 #endif
 }
+/* torchrun exports OMP_NUM_THREADS=1 to its ranks: the timing legs set the thread count explicitly */
+void oracle_set_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}

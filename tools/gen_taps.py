@@ -9,18 +9,28 @@ the taps in asm, nvcc re-assigned the 32 accumulator pairs between the asm insta
 pipelined loop and paid ~9 register moves per visit (ncu, round 1).  The FMAs are Blackwell's
 packed `fma.rn.f32x2` (SASS FFMA2).
 
-Register layout of a warp's tile (2 grid rows x 16 cells, lane = coil):
+Register layout of a lane's share of the tile (2 grid rows x 16 cells):
     acc[r*16 + c*8 + j]   r = row (0, 1), c = 0 real / 1 imaginary part,
                           j = cell pair: 64-bit register = (cell 2j, cell 2j+1)
-A visit is staged in shared memory as a 48-byte packet (read with warp-broadcast loads)
-    P_0..P_3 : pair-packed x weights, P_q = (w[2q - par], w[2q + 1 - par]), par = x offset & 1
-    s0, s1   : row scales wy[dy] wz[dz], wy[dy + 1] wz[dz]
-    idx      : floor(x offset / 2) + W // 2  (>= 0): which cell pairs j = idx - W//2 + q are hit
-    s        : sorted point index
-and, for the spreader, the point's coil values in a [visit][32 coils] (re, im) array.
+
+Coil classes.  TC = 32: lane = coil, the warp's tile is 2 rows.  TC < 32 (batches of at most TC coils):
+lane = (row group g, coil t), g = lane / TC, t = lane % TC; the G = 32 / TC groups hold GY row pairs x
+GZ planes of a larger tile, so a point visits fewer tiles and no lane idles for want of coils.
+
+A visit is staged in shared memory as a packet (read with warp-broadcast loads)
+    TC = 32 (48 bytes):  P_0..P_3 | s0, s1, idx, s
+    TC < 32 (32 + ESZ):  P_0..P_3 | idx, s | wy[2 GY] | wz[GZ] | padding
+        P_q      pair-packed x weights, P_q = (w[2q - par], w[2q + 1 - par]), par = x offset & 1
+        s0, s1   row scales wy[dy] wz[dz], wy[dy + 1] wz[dz]; for TC < 32 a lane forms its own pair from
+                 the windows: s_r = wy[2 gy + r] * wz[gz]  (zero outside the point's footprint)
+        idx      floor(x offset / 2) + W // 2  (>= 0): which cell pairs j = idx - W//2 + q are hit
+        s        sorted point index
+and, for the spreader, the point's coil values in a [visit][TC coils] (re, im) array.
 
 spread:  acc[r][c][j] += P_q * (a, a),  a = (re | im of this lane's coil value) * s_r
-interp:  kt[s][lane] += sum_r s_r * sum_{q, lanes of the pair} acc[r][c][j] * P_q   (red.global.add.v2.f32)
+interp:  kt[s][t] += sum_r s_r * sum_{q, lanes of the pair} acc[r][c][j] * P_q   (red.global.add.v2.f32;
+         for TC < 32 every lane parks its partial sum in shared memory and the kernel adds the G row groups
+         of a coil after the run, see `taps_interp`)
 
 The loop is software-pipelined by hand over two register sets (A, B): the packet (and value) of
 visit k + 1 is loaded before the taps of visit k execute.  See `gen_loop` for the run structure.
@@ -28,6 +38,21 @@ visit k + 1 is loaded before the taps of visit k execute.  See `gen_loop` for th
 import sys
 
 NJ = 8  # cell pairs per row
+OBUF_STRIDE = 264  # bytes per visit of the interpolator's partial-sum buffer (32 lanes x 8 + bank skew)
+
+
+def class_geometry(dim, TC):
+    """(GY row pairs, GZ planes) of the tile of coil class TC: mirrors `Cls<DIM, TC>` in spread_rows.cu."""
+    G = 32 // TC
+    GZ = (8 if G >= 32 else 4 if G >= 8 else 2 if G >= 2 else 1) if dim == 3 else 1
+    return G // GZ, GZ
+
+
+def entry_bytes(dim, TC):
+    if TC == 32:
+        return 16
+    GY, GZ = class_geometry(dim, TC)
+    return (8 + 8 * GY + 4 * GZ + 15) // 16 * 16
 
 
 def cases(W):
@@ -35,29 +60,53 @@ def cases(W):
     return jb0, NJ + jb0  # idx offset, number of cases (jb = -jb0 .. NJ-1)
 
 
-def load_set(X, off_pk, off_vb, pred, spread):
-    """Load visit packet (+ coil value) into register set X; under `pred` (no further visit) only mark it."""
+class Layout:
+    def __init__(self, dim, TC):
+        self.dim, self.TC = dim, TC
+        self.esz = entry_bytes(dim, TC)
+        self.pkt = 32 + self.esz
+        self.vstride = TC * 8
+        self.generic = TC != 32
+
+
+def load_set(lay, X, k, pred, spread):
+    """Load visit packet k (relative to pk) (+ coil value) into register set X; under `pred` (no further
+    visit) only mark it."""
+    off_pk, off_vb = k * lay.pkt, k * lay.vstride
     L = []
     if pred:
         L.append(f"@{pred} mov.u32 i{X}, 0xffffffff;")
     p = f"@!{pred} " if pred else ""
     L += [f"{p}ld.shared.v2.b64 {{P{X}0, P{X}1}}, [pk+{off_pk}];",
-          f"{p}ld.shared.v2.b64 {{P{X}2, P{X}3}}, [pk+{off_pk + 16}];",
-          f"{p}ld.shared.v4.b32 {{s{X}0, s{X}1, i{X}, n{X}}}, [pk+{off_pk + 32}];"]
+          f"{p}ld.shared.v2.b64 {{P{X}2, P{X}3}}, [pk+{off_pk + 16}];"]
+    if lay.generic:
+        L += [f"{p}ld.shared.v2.b32 {{i{X}, n{X}}}, [pk+{off_pk + 32}];",
+              f"{p}ld.shared.v2.b32 {{s{X}0, s{X}1}}, [pky+{off_pk}];",
+              f"{p}ld.shared.b32 z{X}, [pkz+{off_pk}];"]
+    else:
+        L.append(f"{p}ld.shared.v4.b32 {{s{X}0, s{X}1, i{X}, n{X}}}, [pk+{off_pk + 32}];")
     if spread:
         L.append(f"{p}ld.shared.b64 v{X}, [vb+{off_vb}];")
     return L
 
 
-def taps_spread(W, X, c):
+def lane_scales(lay, X):
+    """TC < 32: the lane's two row scales from its window entries."""
+    if not lay.generic:
+        return []
+    return [f"mul.f32 s{X}0, s{X}0, z{X};", f"mul.f32 s{X}1, s{X}1, z{X};"]
+
+
+def taps_spread(lay, W, X, c, slot=0):
     """acc += P (x) A for tap-kernel case c, visit in register set X (straight-line code)."""
     jb0, _ = cases(W)
     NP = W // 2 + 1
     jb = c - jb0
-    L = [f"mov.b64 {{vx, vy}}, v{X};",
-         f"mul.f32 t0, vx, s{X}0;", f"mul.f32 t1, vy, s{X}0;",
-         f"mul.f32 t2, vx, s{X}1;", f"mul.f32 t3, vy, s{X}1;",
-         "mov.b64 A0, {t0, t0};", "mov.b64 A1, {t1, t1};", "mov.b64 A2, {t2, t2};", "mov.b64 A3, {t3, t3};"]
+    L = lane_scales(lay, X)
+    L += [f"mov.b64 {{vx, vy}}, v{X};",
+          f"mul.f32 t0, vx, s{X}0;", f"mul.f32 t1, vy, s{X}0;",
+          f"mul.f32 t2, vx, s{X}1;", f"mul.f32 t3, vy, s{X}1;",
+          "mov.b64 A0, {t0, t0};", "mov.b64 A1, {t1, t1};", "mov.b64 A2, {t2, t2};", "mov.b64 A3, {t3, t3};"]
     for q in range(NP):
         j = jb + q
         if j < 0 or j >= NJ:
@@ -69,7 +118,7 @@ def taps_spread(W, X, c):
     return L
 
 
-def taps_interp(W, X, c):
+def taps_interp(lay, W, X, c, slot):
     """kt[s] += sum of the taps of case c read from the tile registers, visit in register set X."""
     jb0, _ = cases(W)
     NP = W // 2 + 1
@@ -92,17 +141,25 @@ def taps_interp(W, X, c):
                 else:
                     L.append(f"fma.rn.f32x2 S{o}, %{a}, P{X}{q}, S{o};")
     # row scales applied on the packed pairs, then one horizontal add per component
+    L += lane_scales(lay, X)
     L += [f"mov.b64 A0, {{s{X}0, s{X}0}};", f"mov.b64 A1, {{s{X}1, s{X}1}};",
           "mul.rn.f32x2 S0, S0, A0;", "mul.rn.f32x2 S1, S1, A0;",
           "fma.rn.f32x2 S0, S2, A1, S0;", "fma.rn.f32x2 S1, S3, A1, S1;",
           "mov.b64 {lo, hi}, S0;", "add.f32 t0, lo, hi;",
-          "mov.b64 {lo, hi}, S1;", "add.f32 t1, lo, hi;",
-          f"mad.wide.u32 addr, n{X}, 256, ktl;",
-          "red.global.add.v2.f32 [addr], {t0, t1};"]
+          "mov.b64 {lo, hi}, S1;", "add.f32 t1, lo, hi;"]
+    if lay.generic:
+        # the G row groups of a coil each hold a partial sum: parked in shared memory ([visit][lane], rows of
+        # OBUF_STRIDE bytes), summed and added to k-space by the kernel after the run (one compact loop
+        # instead of shuffles + a predicated red in every tap-kernel case: the visit loops stay small
+        # enough for the instruction cache)
+        L += [f"st.shared.v2.f32 [ob+{slot * OBUF_STRIDE}], {{t0, t1}};"]
+    else:
+        L += [f"mad.wide.u32 addr, n{X}, 256, ktl;",
+              "red.global.add.v2.f32 [addr], {t0, t1};"]
     return L
 
 
-def gen_loop(W, spread):
+def gen_loop(W, spread, dim=3, TC=32):
     """One asm block that consumes a run of `n` staged visits.
 
     The stream builder groups the visits of a tile by tap-kernel case, so consecutive visits mostly
@@ -111,54 +168,97 @@ def gen_loop(W, spread):
     back through the dispatcher.  Two register sets (A, B) alternate: the packet of the next visit
     is loaded before the taps of the current one execute.
     """
-    name = f"rows_loop_{'spread' if spread else 'interp'}_w{W}"
+    lay = Layout(dim, TC)
+    name = f"rows_loop_{'spread' if spread else 'interp'}_w{W}" + (f"_d{dim}c{TC}" if lay.generic else "")
     taps = taps_spread if spread else taps_interp
     _, ncase = cases(W)
-    step = ["add.u32 pk, pk, 48;"] + (["add.u32 vb, vb, 256;"] if spread else []) + ["add.s32 n, n, -1;"]
-    step2 = ["add.u32 pk, pk, 96;"] + (["add.u32 vb, vb, 512;"] if spread else []) + ["add.s32 n, n, -2;"]
+
+    def step(k):
+        s = [f"add.u32 pk, pk, {k * lay.pkt};"]
+        if lay.generic:
+            s += [f"add.u32 pky, pky, {k * lay.pkt};", f"add.u32 pkz, pkz, {k * lay.pkt};"]
+        if spread:
+            s.append(f"add.u32 vb, vb, {k * lay.vstride};")
+        elif lay.generic:
+            s.append(f"add.u32 ob, ob, {k * OBUF_STRIDE};")
+        s.append(f"add.s32 n, n, -{k};")
+        return s
+
     body = ["{",
             ".reg .b64 PA<4>, PB<4>, vA, vB, A<4>, S<4>, addr, ktl;",
-            ".reg .b32 sA<2>, sB<2>, iA, iB, nA, nB, vx, vy, lo, hi, t<4>, pk, vb, n;",
+            ".reg .b32 sA<2>, sB<2>, iA, iB, nA, nB, zA, zB, vx, vy, lo, hi, t<4>, pk, pky, pkz, vb, ob, n;",
             ".reg .pred p1, p2, p3, p4, p5;",
             "mov.u32 pk, %32;", "mov.u32 n, %33;"]
-    body.append("mov.u32 vb, %34;" if spread else "mov.u64 ktl, %34;")
-    body += load_set("A", 0, 0, None, spread)
-    for X, Y in (("A", "B"), ("B", "A")):
-        body += [f"D{X}:", "setp.lt.s32 p5, n, 1;", "@p5 bra.uni DONE;",
-                 f"tbl{X}: .branchtargets " + ", ".join(f"R{X}{i}" for i in range(ncase)) + ";",
-                 f"brx.idx.uni i{X}, tbl{X};"]
-        for c in range(ncase):
-            body += [f"R{X}{c}:", "setp.lt.s32 p1, n, 2;"]
-            body += load_set(Y, 48, 256, "p1", spread)
-            body += taps(W, X, c)
-            body += [f"setp.ne.u32 p2, i{Y}, {c};", f"@p2 bra.uni X{X}{c};", "setp.lt.s32 p3, n, 3;"]
-            body += load_set(X, 96, 512, "p3", spread)
-            body += taps(W, Y, c)
-            body += step2
-            body += [f"setp.eq.u32 p4, i{X}, {c};", f"@p4 bra.uni R{X}{c};", f"bra.uni D{X};",
-                     f"X{X}{c}:"]
-            body += step
-            body += [f"bra.uni D{Y};"]
+    if spread:
+        body.append("mov.u32 vb, %34;")
+    elif lay.generic:
+        body.append("mov.u32 ob, %34;")
+    else:
+        body.append("mov.u64 ktl, %34;")
+    if lay.generic:
+        body += ["add.u32 pky, pk, %35;", "add.u32 pkz, pk, %36;"]
+    body += load_set(lay, "A", 0, None, spread)
+    # One order of the register sets (A then B).  A run that leaves a case after an odd number of visits
+    # moves set B into set A (the already loaded next visit) and goes back through the dispatcher: ~10 moves
+    # per change of case instead of a second copy of all the tap kernels with the roles of A and B swapped
+    # -- the visit loops are half the size, which the instruction cache (32 KB) rewards.
+    moves = [f"mov.b64 PA{q}, PB{q};" for q in range(4)] + ["mov.b32 sA0, sB0;", "mov.b32 sA1, sB1;",
+                                                             "mov.b32 iA, iB;", "mov.b32 nA, nB;"]
+    if lay.generic:
+        moves.append("mov.b32 zA, zB;")
+    if spread:
+        moves.append("mov.b64 vA, vB;")
+    X, Y = "A", "B"
+    body += ["DA:", "setp.lt.s32 p5, n, 1;", "@p5 bra.uni DONE;",
+             "tblA: .branchtargets " + ", ".join(f"RA{i}" for i in range(ncase)) + ";",
+             "brx.idx.uni iA, tblA;"]
+    for c in range(ncase):
+        body += [f"RA{c}:", "setp.lt.s32 p1, n, 2;"]
+        body += load_set(lay, Y, 1, "p1", spread)
+        body += taps(lay, W, X, c, 0)
+        body += [f"setp.ne.u32 p2, i{Y}, {c};", "@p2 bra.uni XA;", "setp.lt.s32 p3, n, 3;"]
+        body += load_set(lay, X, 2, "p3", spread)
+        body += taps(lay, W, Y, c, 1)
+        body += step(2)
+        body += [f"setp.eq.u32 p4, i{X}, {c};", f"@p4 bra.uni RA{c};", "bra.uni DA;"]
+    body += ["XA:"] + step(1) + moves + ["bra.uni DA;"]
     body += ["DONE:", "}"]
+    args = "unsigned vb" if spread else ("unsigned ob" if lay.generic else "const void* ktl")
+    if lay.generic:
+        args += ", unsigned yo, unsigned zo"
     L = [f"__device__ __forceinline__ void {name}(",
-         "    unsigned long long (&acc)[32], unsigned pk, int n, "
-         + ("unsigned vb) {" if spread else "const void* ktl) {"),
+         f"    unsigned long long (&acc)[32], unsigned pk, int n, {args}) {{",
          "  asm volatile("]
     L += [f'      "{b}\\n"' for b in body]
     L.append("      : " + ", ".join(f'"+l"(acc[{i}])' for i in range(32)))
-    L.append('      : "r"(pk), "r"(n), ' + ('"r"(vb)' if spread else '"l"(ktl)'))
+    ins = '"r"(pk), "r"(n), ' + ('"r"(vb)' if spread else ('"r"(ob)' if lay.generic else '"l"(ktl)'))
+    if lay.generic:
+        ins += ', "r"(yo), "r"(zo)'
+    L.append("      : " + ins)
     L.append('      : "memory");')
     L.append("}")
     return "\n".join(L)
 
 
+CLASSES = {3: (16, 8, 4, 2, 1), 2: (16, 8)}  # coil classes below 32 per dimension
+
+
 def main():
-    out = ["// GENERATED by tools/gen_taps.py -- do not edit.  See that script for the layout.",
-           "#pragma once", ""]
+    """Without arguments: csrc/taps_generated.inc (TC = 32) and csrc/taps_generated_d{dim}c{TC}.inc for the
+    smaller coil classes (one file per class: each is compiled in its own translation unit)."""
+    base = sys.argv[1] if len(sys.argv) > 1 else "mrinufft_b200/csrc"
+    head = ["// GENERATED by tools/gen_taps.py -- do not edit.  See that script for the layout.",
+            "#pragma once", ""]
+    out = list(head)
     for W in (4, 5, 6, 7):
         out += [gen_loop(W, True), "", gen_loop(W, False), ""]
-    path = sys.argv[1] if len(sys.argv) > 1 else "mrinufft_b200/csrc/taps_generated.inc"
-    open(path, "w").write("\n".join(out))
+    open(f"{base}/taps_generated.inc", "w").write("\n".join(out))
+    for dim, tcs in CLASSES.items():
+        for TC in tcs:
+            out = list(head)
+            for W in (4, 5, 6, 7):
+                out += [gen_loop(W, True, dim, TC), "", gen_loop(W, False, dim, TC), ""]
+            open(f"{base}/taps_generated_d{dim}c{TC}.inc", "w").write("\n".join(out))
 
 
 if __name__ == "__main__":
