@@ -7,8 +7,10 @@ Workload (``config.workload``, BASELINE.json configs[2], the configuration the m
 3-D 256^3 image, 32 coils with sensitivity maps, M = 2^23 samples of a phyllotaxis radial
 trajectory (``initialize_3D_phyllotaxis_radial(16384, 512)``), complex64, eps = 1e-6.
 A step is one ``op`` (type 2, all coils) + one ``adj_op`` (type 1, all coils, SENSE combine).
-Multi-GPU (torchrun, one rank per GPU): weak scaling, every rank owns 32 coils of a 32*N-coil
-acquisition; the SENSE adjoint image is summed over ranks with one NCCL all-reduce per step.
+Multi-GPU (torchrun, one rank per GPU): STRONG scaling of that workload through
+``mrinufft_b200.dist.CoilShardedOperator`` -- the 32 coils are sharded, 32 / N per rank, the SENSE
+adjoint image is summed over ranks with one NCCL all-reduce per step.  (The weak-scaling figure of
+round 1, 32 coils per GPU, is kept under ``extras``.)
 
 Prints ONE JSON line on rank 0 (see the driver contract in the task statement).
 """
@@ -46,18 +48,22 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--n", type=int, default=256, help="image size per axis")
-    ap.add_argument("--coils", type=int, default=32, help="coils per GPU")
+    ap.add_argument("--coils", type=int, default=32, help="coils of the acquisition IN TOTAL (sharded over the GPUs)")
     ap.add_argument("--spokes", type=int, default=16384)
     ap.add_argument("--ns", type=int, default=512, help="samples per spoke")
     ap.add_argument("--traj", default="radial", choices=["radial", "random"])
-    ap.add_argument("--cpu-sample-coils", type=int, default=1)
+    ap.add_argument("--cpu-sample-coils", type=int, default=4)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-weak", action="store_true", help="N > 1: skip the extra weak-scaling measurement")
+    ap.add_argument("--no-configs", action="store_true", help="skip BASELINE's secondary configurations (extras.configs)")
     ap.add_argument("--spread-method", type=int, default=0)
     ap.add_argument("--interp-method", type=int, default=0)
     ap.add_argument("--fft-method", type=int, default=0, help="0 auto, 1 cuFFT + pad/crop kernels, 2 fused zero-padding-aware passes")
     ap.add_argument("--rows-dbg", type=int, default=0, help="debug switches of the row kernels (timing experiments)")
-    return ap.parse_args()
+    args = ap.parse_args()
+    args.total_coils = args.coils
+    return args
 
 
 def make_trajectory(args):
@@ -242,25 +248,71 @@ def run_reference(args):
 
 
 def workload_config(args, M, n_gpus):
+    C = args.total_coils
     return {
-        "workload": f"3D {args.n}^3, {args.coils} coils/GPU with smaps, M={M} "
+        "workload": f"3D {args.n}^3, {C} coils with smaps, M={M} "
                     f"({f'phyllotaxis radial {args.spokes}x{args.ns}' if args.traj == 'radial' else 'truncnorm random'}), "
                     "complex64, eps=1e-6, sigma=2, one op + one adj_op per step",
-        "coils_per_gpu": args.coils, "n_samples": int(M), "image": [args.n] * 3,
-        "parallelism": f"coil-sharded x{n_gpus} (weak: {args.coils} coils per GPU, all-reduce of the SENSE adjoint image)",
-        "l2": (f"inputs (k-space {8e-9 * M * args.coils:.2g} GB, smaps {8e-9 * args.n ** 3 * args.coils:.2g} GB, "
-               f"grids {64e-9 * args.n ** 3 * args.coils:.2g} GB) against the 126 MB L2"),
+        "coils_total": C, "coils_per_gpu": C // max(n_gpus, 1), "n_samples": int(M), "image": [args.n] * 3,
+        "parallelism": (f"coil-sharded x{n_gpus} through mrinufft_b200.dist.CoilShardedOperator (strong: {C} coils in "
+                        f"total, {C // max(n_gpus, 1)} per GPU; NCCL all-reduce of the SENSE adjoint image)"),
+        "value_path": "CoilShardedOperator._op_device / ._adj_device on device-resident tensors (the public op / "
+                      "adj_op minus the array-type shim); e2e = CoilShardedOperator.op / .adj_op on host numpy arrays",
+        "l2": (f"per-GPU inputs (k-space {8e-9 * M * C / max(n_gpus, 1):.2g} GB, smaps {8e-9 * args.n ** 3 * C / max(n_gpus, 1):.2g} GB, "
+               f"grids {64e-9 * args.n ** 3 * C / max(n_gpus, 1):.2g} GB) against the 126 MB L2"),
     }
 
 
 # ------------------------------------------------------------------------------------------ GPU leg
+def timed_steps(torch, dist, world, dev, fn, steps, warmup):
+    """W warm-up calls, then exactly K calls between barrier + synchronize on both sides, CUDA events on the
+    stream the library launches on (torch's current stream); returns the max over ranks of ms per call."""
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t = torch.tensor([e0.elapsed_time(e1) / steps], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def wall_steps(torch, dist, world, dev, fn, steps, warmup=1):
+    """Host-clock version for calls that end with a device -> host copy (max over ranks, seconds per call)."""
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        fn()
+    torch.cuda.synchronize()
+    dt = (time.perf_counter() - t0) / steps
+    t = torch.tensor([dt], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
 
-    import mrinufft
+    import mrinufft  # noqa: F401
     import mrinufft_b200
     from mrinufft_b200 import _lib
+    from mrinufft_b200.dist import CoilShardedOperator, bind_to_gpu_numa_node, coil_slice
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -273,71 +325,64 @@ def run_b200(args):
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
         # one process per GPU: keep it (and the page-locked buffers it touches first) on the GPU's socket
-        from mrinufft_b200.dist import bind_to_gpu_numa_node
-
         numa = bind_to_gpu_numa_node(local_rank)
         print(f"[rank {rank}] NUMA binding: {numa}", file=sys.stderr, flush=True)
     if not mrinufft_b200.MRIB200NUFFT.available:
         raise RuntimeError("b200 backend unavailable (libb200nufft.so missing or no GPU): no fallback")
 
     shape = (args.n,) * 3
-    C = args.coils
+    C = args.total_coils
+    if C % world:
+        raise SystemExit(f"{C} coils do not split evenly over {world} GPUs")
+    lo, hi = coil_slice(C, rank, world)
+    Cl = hi - lo
     traj = make_trajectory(args)
     M = traj.shape[0]
-    rng = np.random.default_rng(100 + rank)
     g = torch.Generator(device=dev).manual_seed(100 + rank)
 
     def crandn(*s):
         return torch.view_as_complex(torch.randn(*s, 2, device=dev, generator=g, dtype=torch.float32))
 
-    smaps = crandn(C, *shape)
-    smaps /= torch.linalg.norm(smaps, dim=0, keepdim=True)
-    op = mrinufft.get_operator("b200")(traj, shape, n_coils=C, smaps=smaps, squeeze_dims=False,
-                                       coil_chunk=C)
-    plan = op.raw_op.plan
-    plan.set_option(0, args.spread_method)
-    plan.set_option(1, args.interp_method)
-    plan.set_option(2, args.fft_method)
-    plan.set_option(3, args.rows_dbg)
+    def make_operator(n_local):
+        smaps = crandn(n_local, *shape)
+        smaps /= torch.linalg.norm(smaps, dim=0, keepdim=True) * np.sqrt(world)
+        sop = CoilShardedOperator(traj, shape, n_coils=n_local * world, smaps=smaps, squeeze_dims=False,
+                                  coil_chunk=n_local)
+        pl = sop.local.raw_op.plan
+        pl.set_option(0, args.spread_method)
+        pl.set_option(1, args.interp_method)
+        pl.set_option(2, args.fft_method)
+        pl.set_option(3, args.rows_dbg)
+        return sop, smaps
+
+    # the product path: this rank's shard of the 32-coil operator (strong scaling: C / N coils per GPU)
+    sop, smaps = make_operator(Cl)
+    op, plan = sop.local, sop.local.raw_op.plan
     img_d = crandn(1, 1, *shape)
-    ksp_d = crandn(1, C, M)
+    if world > 1:
+        dist.broadcast(torch.view_as_real(img_d), src=0)  # the SENSE image is replicated
+    ksp_d = crandn(1, Cl, M)
 
     def step():
-        y = op._op_device(img_d)
-        x = op._adj_device(ksp_d)
-        if world > 1:
-            dist.all_reduce(torch.view_as_real(x))
+        y = sop._op_device(img_d)     # type 2, this rank's coils: no communication
+        x = sop._adj_device(ksp_d)    # type 1 + SENSE combine + NCCL all-reduce of the image over ranks
         return y, x
 
-    for _ in range(max(args.warmup, 3)):
+    W = max(args.warmup, 3)
+    for _ in range(W):
         step()
     torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
     _lib.launch_count(reset=True)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize()
-    e0.record()
-    for _ in range(args.steps):
-        step()
-    e1.record()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    ms = e0.elapsed_time(e1) / args.steps
+    ms_max = timed_steps(torch, dist, world, dev, step, args.steps, 0)
     kernels, ffts = _lib.launch_count()
     clocks = sampler.stop() if rank == 0 else None
-    ms_t = torch.tensor([ms], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(ms_t, op=dist.ReduceOp.MAX)
-    ms_max = float(ms_t.item())
-    value = M * C * world / (ms_max * 1e-3) / 1e3
+    value = M * C / (ms_max * 1e-3) / 1e3
 
     # per-kernel timings: CUDA events recorded by the library on the stream it launches on (torch's
-    # current stream), averaged over the timed steps' worth of extra iterations
+    # current stream), averaged over a few extra iterations
     plan.enable_timing(True)
     kt = {"spread_ms": [], "interp_ms": [], "fft_ms": [], "grid_ms": [], "spread_rows_ms": [],
           "interp_rows_ms": []}
@@ -354,87 +399,118 @@ def run_b200(args):
         kt["grid_ms"].append(t2["grid_ms"] + t1["grid_ms"])
     plan.enable_timing(False)
     kt = {k: float(np.mean(v)) for k, v in kt.items()}
+    cls = plan.rows_class(Cl)
+    plan_w, op_nf, ws_gb = plan.w, tuple(plan.nf), plan.workspace_bytes / 1e9
 
-    # secondary: Toeplitz Gram operator (A^H A through two zero-padding-aware FFTs per coil) against the
-    # op + adj_op pair it replaces inside CG-type solvers; device resident, not part of `value`
     extras = {}
-    try:
-        op.compute_toeplitz_kernel()
-        for _ in range(2):
-            op._gram_device(img_d)
-        torch.cuda.synchronize()
-        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        g0.record()
-        for _ in range(3):
-            op._gram_device(img_d)
-        g1.record()
-        torch.cuda.synchronize()
-        extras["toeplitz_gram_ms"] = g0.elapsed_time(g1) / 3
-        op._toeplitz_kernel = None
-    except Exception as exc:  # noqa: BLE001
-        extras["toeplitz_gram_error"] = str(exc)[:200]
+    if world == 1:
+        # secondary: Toeplitz Gram operator (A^H A through two zero-padding-aware FFTs per coil) against the
+        # op + adj_op pair it replaces inside CG-type solvers; device resident, not part of `value`
+        try:
+            op.compute_toeplitz_kernel()
+            extras["toeplitz_gram_ms"] = timed_steps(torch, dist, 1, dev, lambda: op._gram_device(img_d), 3, 2)
+            op._toeplitz_kernel = None
+        except Exception as exc:  # noqa: BLE001
+            extras["toeplitz_gram_error"] = str(exc)[:200]
+        # secondary: cost of new sample locations (fold + sort + visit-stream rebuild), i.e. what
+        # `update_samples` adds to the first transform after it (trajectory-learning loops pay it per step)
+        try:
+            pts_d = op.raw_op._pts
 
-    # secondary: cost of new sample locations (fold + sort + visit-stream rebuild), i.e. what
-    # `update_samples` adds to the first transform after it (trajectory-learning loops pay it per step)
-    try:
-        pts_d = op.raw_op._pts
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        for _ in range(3):
-            op.raw_op._set_pts(pts_d)
-            op._op_device(img_d)
-        torch.cuda.synchronize()
-        t_with = (time.perf_counter() - t0) / 3
-        t0 = time.perf_counter()
-        for _ in range(3):
-            op._op_device(img_d)
-        torch.cuda.synchronize()
-        t_without = (time.perf_counter() - t0) / 3
-        extras["setpts_and_stream_rebuild_ms"] = (t_with - t_without) * 1e3
-    except Exception as exc:  # noqa: BLE001
-        extras["setpts_error"] = str(exc)[:200]
+            def with_setpts():
+                op.raw_op._set_pts(pts_d)
+                op._op_device(img_d)
 
-    # end-to-end through the public API with HOST buffers (pinned), copies inside the timed region
+            t_with = wall_steps(torch, dist, 1, dev, with_setpts, 3)
+            t_without = wall_steps(torch, dist, 1, dev, lambda: op._op_device(img_d), 3)
+            extras["setpts_and_stream_rebuild_ms"] = (t_with - t_without) * 1e3
+        except Exception as exc:  # noqa: BLE001
+            extras["setpts_error"] = str(exc)[:200]
+
+    # end-to-end through the public API with HOST buffers, copies inside the timed region.  Host arrays run as
+    # chunks of 8 coils whose PCIe copies overlap the neighbouring chunk's transform (operator.py, `_chunks`).
     e2e = None
     if not args.no_e2e:
         img_h = torch.empty((1, 1, *shape), dtype=torch.complex64, pin_memory=True)
-        ksp_h = torch.empty((1, C, M), dtype=torch.complex64, pin_memory=True)
+        ksp_h = torch.empty((1, Cl, M), dtype=torch.complex64, pin_memory=True)
         img_h.copy_(img_d)
         ksp_h.copy_(ksp_d)
         img_np, ksp_np = img_h.numpy(), ksp_h.numpy()
 
-        def e2e_step():
-            y = op.op(img_np)          # H2D image, D2H k-space (numpy out, page-locked)
-            x = op.adj_op(ksp_np)      # H2D k-space, D2H image
-            if world > 1:
-                xt = torch.from_numpy(x).to(dev)
-                dist.all_reduce(torch.view_as_real(xt))
-                x = xt.cpu().numpy()
+        def e2e_step(i_np=img_np, k_np=ksp_np):
+            y = sop.op(i_np)          # H2D image, D2H this rank's k-space (numpy out, page-locked)
+            x = sop.adj_op(k_np)      # H2D k-space, all-reduce on the device, D2H image
             return y, x
 
-        e2e_step()
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        t0 = time.perf_counter()
         n_e2e = max(2, min(args.steps, 3))
-        for _ in range(n_e2e):
-            e2e_step()
-        torch.cuda.synchronize()
-        dt = (time.perf_counter() - t0) / n_e2e
-        dt_t = torch.tensor([dt], device=dev, dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(dt_t, op=dist.ReduceOp.MAX)
-        dt = float(dt_t.item())
-        e2e = {"value": M * C * world / dt / 1e3, "unit": UNIT,
-               "h2d_bytes_per_step": int(img_np.nbytes + ksp_np.nbytes),
-               "d2h_bytes_per_step": int(img_np.nbytes + ksp_np.nbytes),
-               "ms_per_step": dt * 1e3}
+        dt = wall_steps(torch, dist, world, dev, e2e_step, n_e2e)
+        nbytes = int(img_np.nbytes + ksp_np.nbytes)
+        e2e = {"value": M * C / dt / 1e3, "unit": UNIT, "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes,
+               "ms_per_step": dt * 1e3, "host_memory": "page-locked (numpy views of pinned tensors)",
+               "host_chunks": [c1 - c0 for c0, c1 in op._chunks(host=True)]}
+        # the same with plain (pageable) numpy arrays: the library page-locks the caller's buffers in place on
+        # first sight (cudaHostRegister, cached by address) -- the warm-up call pays for that
+        try:
+            img_pg, ksp_pg = np.array(img_np), np.array(ksp_np)
+            t0 = time.perf_counter()
+            e2e_step(img_pg, ksp_pg)
+            torch.cuda.synchronize()
+            first = time.perf_counter() - t0
+            dtp = wall_steps(torch, dist, world, dev, lambda: e2e_step(img_pg, ksp_pg), n_e2e, warmup=0)
+            e2e["pageable"] = {"value": M * C / dtp / 1e3, "ms_per_step": dtp * 1e3,
+                               "first_call_ms_incl_cudaHostRegister": first * 1e3}
+            del img_pg, ksp_pg
+        except Exception as exc:  # noqa: BLE001
+            e2e["pageable"] = {"error": str(exc)[:200]}
+        # where the end-to-end time goes: this rank's PCIe rates with every rank copying at the same time
+        try:
+            def rate(fn, nb):
+                return nb / (wall_steps(torch, dist, world, dev, fn, 2) + 1e-12) / 1e9
+
+            kd = torch.empty_like(ksp_d)
+            h2d = rate(lambda: kd.copy_(ksp_h, non_blocking=True), ksp_h.numel() * 8)
+            d2h = rate(lambda: ksp_h.copy_(kd, non_blocking=True), ksp_h.numel() * 8)
+            del kd
+            e2e["pcie_gbs_per_rank_all_ranks_busy"] = {"h2d": h2d, "d2h": d2h}
+            e2e["copy_floor_ms"] = nbytes / 1e9 / h2d * 1e3 / 2 + nbytes / 1e9 / d2h * 1e3 / 2
+        except Exception as exc:  # noqa: BLE001
+            e2e["pcie_error"] = str(exc)[:200]
+        del img_h, ksp_h
+
+    # N > 1: the weak-scaling number of round 1 (32 coils PER GPU, a 32 N-coil acquisition) next to the strong one
+    if world > 1 and not args.no_weak:
+        try:
+            del sop, op, plan, smaps, ksp_d
+            torch.cuda.empty_cache()
+            wop, wsm = make_operator(C)
+            wk = crandn(1, C, M)
+
+            def wstep():
+                wop._op_device(img_d)
+                wop._adj_device(wk)
+
+            wms = timed_steps(torch, dist, world, dev, wstep, max(2, min(args.steps, 3)), 2)
+            extras["weak_scaling_32_coils_per_gpu"] = {"ms_per_step": wms, "value": M * C * world / (wms * 1e-3) / 1e3,
+                                                        "unit": UNIT, "coils_total": C * world}
+            del wop, wsm, wk
+        except Exception as exc:  # noqa: BLE001
+            extras["weak_scaling_error"] = str(exc)[:200]
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
+
+    # secondary configurations of BASELINE.json (A, B, D, E) on this GPU, a few seconds in total
+    if world == 1 and not args.no_configs:
+        try:
+            torch.cuda.empty_cache()
+            sys.path.insert(0, str(ROOT / "tools"))
+            import bench_configs
+
+            extras["configs"] = bench_configs.run_all(quick=args.n < 256)
+        except Exception as exc:  # noqa: BLE001
+            extras["configs_error"] = repr(exc)[:300]
 
     peaks = {}
     try:
@@ -443,29 +519,31 @@ def run_b200(args):
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "6650 GB/s (of fallback)"
-    Nf = int(np.prod(plan.nf))
-    ab = algorithmic_bytes(int(np.prod(shape)), Nf, M, 3, C)
-    # dominant own kernel: the row kernel of the spreader or of the interpolator (k_rows<.., SPREAD>)
+    Nf = int(np.prod(op_nf))
+    ab = algorithmic_bytes(int(np.prod(shape)), Nf, M, 3, Cl)
+    # dominant own kernel: the row kernel of the spreader or of the interpolator (k_rows<.., SPREAD, .., class>)
     dom_name, dom_ms = max(("spread", kt["spread_rows_ms"]), ("interp", kt["interp_rows_ms"]),
                            key=lambda kv: kv[1])
     achieved = ab[dom_name] / (dom_ms * 1e-3) / 1e9
-    is_cfg_c = (args.n == 256 and C == 32 and M == 1 << 23 and args.traj == "radial")
+    is_cfg_c = (args.n == 256 and Cl == 32 and M == 1 << 23 and args.traj == "radial")
     roofline = {
-        "bound": "hbm", "kernel": f"k_rows<3,{plan.w},{'true' if dom_name == 'spread' else 'false'},true> ({dom_name})",
+        "bound": "hbm",
+        "kernel": f"k_rows<3,{plan_w},{'true' if dom_name == 'spread' else 'false'},{'true' if cls['class'] == 32 else 'false'},"
+                  f"{cls['class']}> ({dom_name}, coil class {cls['class']})",
         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
         # dram__bytes_read.sum + dram__bytes_write.sum of one launch, `ncu --set full` (profiles/)
         "traffic": (NCU_TRAFFIC_GB[dom_name] * 1e9 if is_cfg_c else None),
         "peak_source": peak_src, "kernel_ms": kt, "algorithmic_bytes_per_launch": ab[dom_name],
-        "step_algorithmic_bytes": ab["pair_all_coils"],
-        "step_frac": ab["pair_all_coils"] / (ms_max * 1e-3) / 1e9 / peak,
-        "note": "the row kernels are bound by the FP32 FMA pipe and instruction issue, not by HBM "
-                "(ncu: issue 54-56 %, dram 26-31 %); frac is quoted against the HBM floor as the "
-                "contract asks, `fp32` is the bound that applies",
+        "step_algorithmic_bytes": ab["pair_all_coils"] * world,
+        "step_frac": ab["pair_all_coils"] * world / (ms_max * 1e-3) / 1e9 / (peak * world),
+        "rows_class": cls,
+        "note": "the row kernels are bound by the FP32 FMA pipe and instruction issue, not by HBM; frac is quoted "
+                "against the HBM floor as the contract asks, `fp32` is the bound that applies",
     }
     # the bound that does apply to the row kernels: w^3 complex accumulations per sample and coil on the
     # FP32 pipe; peak = packed FFMA2 issue rate measured on this pool (tools/ffma2_rate.cu ->
     # profiles/r01_ffma2_rate.jsonl: 0.495 warp instructions / clk / SM sub-partition)
-    fma = 2.0 * M * float(plan.w) ** 3 * C
+    fma = 2.0 * M * float(plan_w) ** 3 * Cl
     roofline["fp32"] = {
         "algorithmic_fma_per_launch": fma, "achieved_tfma_s": fma / (dom_ms * 1e-3) / 1e12,
         "peak_tfma_s": FP32_PEAK_TFMA, "frac": fma / (dom_ms * 1e-3) / 1e12 / FP32_PEAK_TFMA,
@@ -475,22 +553,28 @@ def run_b200(args):
     cpu_baseline = None
     if not args.no_cpu and world == 1:
         cs = args.cpu_sample_coils
-        dt, t_setpts, cores = cpu_pair_time(traj, shape, smaps[:cs].cpu().numpy(), cs)
-        cpu_baseline = {"value": M * cs / dt / 1e3, "unit": UNIT, "cores": cores, "kind": "port",
-                        "sample": f"{cs} of {C} coils of the same workload (full {args.n}^3, M={M}), one op+adj_op pair, "
-                                  f"float32 finufft-algorithm oracle; {dt:.1f} s, setpts {t_setpts:.1f} s",
-                        "seconds": dt}
+        rng = np.random.default_rng(1)
+        sm = (rng.standard_normal((cs, *shape)) + 1j * rng.standard_normal((cs, *shape))).astype(np.complex64)
+        sm /= np.sqrt(np.sum(np.abs(sm) ** 2, axis=0, keepdims=True))
+        cop, kind, cores, t_setpts = make_cpu_operator(traj, shape, cs, sm)
+        im = (rng.standard_normal((1, 1, *shape)) + 1j * rng.standard_normal((1, 1, *shape))).astype(np.complex64)
+        ks = (rng.standard_normal((1, cs, M)) + 1j * rng.standard_normal((1, cs, M))).astype(np.complex64)
+        dt = cpu_pair_time(cop, im, ks)
+        cpu_baseline = {"value": M * cs / dt / 1e3, "unit": UNIT, "cores": cores, "kind": kind,
+                        "sample": f"{cs} of {C} coils of the same workload (full {args.n}^3, M={M}) with smaps, one op+adj_op "
+                                  f"pair through the reference's FourierOperatorCPU coil loop, float32; {dt:.1f} s, "
+                                  f"setpts {t_setpts:.1f} s", "seconds": dt}
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-        "warmup": max(args.warmup, 3), "ms_per_step": ms_max, "higher_is_better": True, "scaling": "weak",
+        "warmup": W, "ms_per_step": ms_max, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "complex64", "data": "synthetic",
         "config": workload_config(args, M, world),
-        "pairs_per_s": 1e3 / ms_max * world,
+        "pairs_per_s": 1e3 / ms_max,
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(kernels + ffts),
         "gpu_launches_detail": {"own_kernels": int(kernels), "cufft_execs": int(ffts)},
         "roofline": roofline, "cpu_baseline": cpu_baseline,
-        "kernel_width": plan.w, "fine_grid": list(plan.nf), "workspace_gb": plan.workspace_bytes / 1e9,
+        "kernel_width": plan_w, "fine_grid": list(op_nf), "workspace_gb": ws_gb,
         "extras": extras,
     }
     print(json.dumps(line), flush=True)

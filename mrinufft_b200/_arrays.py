@@ -9,6 +9,7 @@ argument decide the type of the result.  cupy is not required: anything exposing
 from __future__ import annotations
 
 import warnings
+import weakref
 
 import numpy as np
 import torch
@@ -21,6 +22,57 @@ NP2TORCH = {
     np.dtype("int32"): torch.int32,
     np.dtype("int64"): torch.int64,
 }
+
+
+# ---------------------------------------------------------------- page-locking caller memory in place
+# Large pageable numpy arrays cross PCIe through the driver's staging buffer at a fraction of the link
+# speed and cannot overlap with compute.  Like the reference's GPU peer
+# (``_host_register``, src/mrinufft/operators/interfaces/cufinufft.py:421-458) the caller's buffer is
+# page-locked in place with ``cudaHostRegister`` -- no copy -- and the registration is cached by address
+# for as long as the owning array lives (registering costs about as much as one staged copy; a
+# reconstruction loop hands in the same buffers again and again).
+PIN_MIN_BYTES = 8 << 20
+_pinned = {}
+
+
+def _owner(a: np.ndarray) -> np.ndarray:
+    while isinstance(a.base, np.ndarray):
+        a = a.base
+    return a
+
+
+def pin_in_place(a: np.ndarray) -> bool:
+    """Page-lock the memory of the contiguous array ``a`` (cached); False if that is not possible."""
+    if a.nbytes < PIN_MIN_BYTES or not a.flags.c_contiguous or not torch.cuda.is_available():
+        return False
+    key = (a.ctypes.data, a.nbytes)
+    fin = _pinned.get(key)
+    if fin is not None and fin.alive:
+        return True
+    try:
+        if torch.from_numpy(a.view(np.uint8).reshape(-1)[:1]).is_pinned():
+            return True  # already page-locked (e.g. a view of a pinned torch tensor)
+    except Exception:  # noqa: BLE001  (read-only arrays warn, exotic dtypes raise: fall through)
+        pass
+    rt = torch.cuda.cudart()
+    # ranges that overlap an older registration (a parent buffer, a stale entry) cannot be registered twice
+    err = rt.cudaHostRegister(key[0], key[1], 0)
+    if int(err) != 0:
+        return False
+
+    def _release(ptr=key[0], key=key):
+        _pinned.pop(key, None)
+        try:
+            rt.cudaHostUnregister(ptr)
+        except Exception:  # noqa: BLE001  (interpreter shutdown)
+            pass
+
+    try:
+        _pinned[key] = weakref.finalize(_owner(a), _release)
+    except TypeError:
+        rt.cudaHostUnregister(key[0])
+        return False
+    return True
 
 
 def module_name(arr) -> str:
@@ -47,9 +99,8 @@ def to_device(arr, device: torch.device, dtype: torch.dtype | None = None) -> to
     """Convert any supported array to a contiguous torch tensor on ``device`` (never mutates ``arr``).
 
     Host arrays that already live in page-locked memory (e.g. numpy views of pinned torch tensors)
-    are copied asynchronously on the current stream; pageable ones go through the driver's staged
-    copy.  The reference instead registers the caller's memory per call
-    (``src/mrinufft/operators/interfaces/cufinufft.py:421-458``).
+    are copied asynchronously on the current stream; large pageable ones are page-locked in place
+    first (``pin_in_place``), small ones go through the driver's staged copy.
     """
     root = module_name(arr)
     if root == "torch":
@@ -68,8 +119,11 @@ def to_device(arr, device: torch.device, dtype: torch.dtype | None = None) -> to
         with warnings.catch_warnings():
             warnings.simplefilter("ignore", UserWarning)  # read-only inputs are never written to
             t = torch.from_numpy(a)
-        if device.type == "cuda" and t.numel() > 0 and t.is_pinned():
-            return t.to(device, non_blocking=True)
+        if device.type == "cuda" and t.numel() > 0:
+            # (a converted temporary is not worth a registration: only the caller's own buffer is pinned)
+            own = isinstance(arr, np.ndarray) and a.ctypes.data == arr.ctypes.data
+            if t.is_pinned() or (own and pin_in_place(a)):
+                return t.to(device, non_blocking=True)
         return t.to(device)
     # __cuda_array_interface__ (cupy, numba, ...): zero-copy view
     t = torch.as_tensor(arr, device=device)

@@ -77,11 +77,12 @@ class CoilShardedOperator:
     """
 
     def __init__(self, samples, shape, n_coils, smaps=None, group=None, local_factory=None, **kwargs):
-        if not dist.is_initialized():
-            raise RuntimeError("torch.distributed is not initialised")
         self.group = group
-        self.rank = dist.get_rank(group)
-        self.world = dist.get_world_size(group)
+        if dist.is_initialized():
+            self.rank = dist.get_rank(group)
+            self.world = dist.get_world_size(group)
+        else:  # a single process: one shard that holds every coil, no collectives
+            self.rank, self.world = 0, 1
         self.n_coils = int(n_coils)
         self.lo, self.hi = coil_slice(self.n_coils, self.rank, self.world)
         self.shape = tuple(int(s) for s in shape)
@@ -121,14 +122,34 @@ class CoilShardedOperator:
         return self.local.op(image)
 
     def adj_op(self, ksp_local):
-        """This rank's k-space slice -> image; SENSE: all-reduced (identical on every rank)."""
-        img = self.local.adj_op(ksp_local)
+        """This rank's k-space slice -> image; SENSE: all-reduced (identical on every rank).  On the b200
+        operator the sum over ranks happens on the device (NCCL), before a host caller's image is copied
+        out: a host array never goes back up just to be reduced."""
+        loc = self.local
+        if self.uses_sense and self.world > 1 and hasattr(loc, "_host_pipeline_applies"):
+            loc.check_shape(ksp=ksp_local)
+            if loc._host_pipeline_applies(ksp_local):
+                img, kind, dev = loc._adj_host_pipelined(ksp_local, keep_on_device=True), "numpy", None
+            else:
+                ksp, kind, dev = loc._in(ksp_local)
+                img = loc._adj_device(ksp)
+            self._allreduce_tensor(img)
+            return loc._out(loc._safe_squeeze(img), kind, dev)
+        img = loc.adj_op(ksp_local)
         if self.uses_sense and self.world > 1:
             img = self._allreduce(img)
         return img
 
     def data_consistency(self, image, obs_local):
-        g = self.local.data_consistency(image, obs_local)
+        loc = self.local
+        if self.uses_sense and self.world > 1 and hasattr(loc, "_host_pipeline_applies"):
+            loc.check_shape(image=image, ksp=obs_local)
+            img, kind, dev = loc._in(image)
+            obs, _, _ = loc._in(obs_local)
+            g = loc._dc_device(img, obs)
+            self._allreduce_tensor(g)
+            return loc._out(loc._safe_squeeze(g), kind, dev)
+        g = loc.data_consistency(image, obs_local)
         if self.uses_sense and self.world > 1:
             g = self._allreduce(g)
         return g

@@ -30,7 +30,7 @@ from mrinufft._utils import proper_trajectory
 from mrinufft.operators.base import FourierOperatorBase
 
 from . import _lib
-from ._arrays import describe, from_device, module_name, to_device
+from ._arrays import describe, from_device, module_name, pin_in_place, to_device
 from .toeplitz import assemble_toeplitz_kernel, modulated_weights
 
 log = logging.getLogger("mrinufft_b200")
@@ -158,6 +158,7 @@ class MRIB200NUFFT(FourierOperatorBase):
         upsampfac=2.0,
         gpu_device_id=None,
         coil_chunk=None,
+        host_chunk=None,
         spreadinterponly=0,
         isign=None,
         precision="single",
@@ -207,6 +208,7 @@ class MRIB200NUFFT(FourierOperatorBase):
         self._user_isign_flip = isign is not None and int(isign) > 0
         self._conj_smaps = False
         self._coil_chunk = coil_chunk
+        self._host_chunk = int(host_chunk) if host_chunk else None
 
         self.raw_op = RawB200Plan(
             samples, self.shape, n_trans=self._pick_chunk(), eps=self.eps, upsampfac=self.upsampfac,
@@ -427,9 +429,15 @@ class MRIB200NUFFT(FourierOperatorBase):
         """Nothing to build: the plan handles both signs (cf. finufft.py:183-193)."""
 
     # ------------------------------------------------------------------ device-level transforms
-    def _chunks(self):
+    def _chunks(self, host=False):
+        """Coil ranges of the library calls.  Device arrays: as many coils per call as the workspace holds.
+        Host arrays (``host=True``): smaller chunks, so that the k-space of one chunk crosses PCIe while
+        the next one is transformed -- the row kernels run a call of T coils in a coil class whose cost
+        follows T (rows_common.cuh), so four calls of 8 coils cost little more than one call of 32."""
         T = self.raw_op.n_trans
         C = self.n_coils
+        if host and not self._spread_only:
+            T = min(T, self._host_chunk if self._host_chunk else (8 if C >= 16 else T))
         return [(c0, min(c0 + T, C)) for c0 in range(0, C, T)]
 
     def _op_device(self, img: torch.Tensor, ksp: torch.Tensor | None = None) -> torch.Tensor:
@@ -539,7 +547,7 @@ class MRIB200NUFFT(FourierOperatorBase):
     def _host_pipeline_applies(self, arr) -> bool:
         if not isinstance(arr, np.ndarray) or self._spread_only:
             return False
-        return self.n_batchs * len(self._chunks()) > 1
+        return self.n_batchs * len(self._chunks(host=True)) > 1
 
     def _copy_streams(self):
         if getattr(self, "_h2d_stream", None) is None:
@@ -551,6 +559,8 @@ class MRIB200NUFFT(FourierOperatorBase):
     def _host_tensor(arr, dtype):
         a = np.ascontiguousarray(np.asarray(arr).astype(
             {torch.complex64: np.complex64, torch.complex128: np.complex128}[dtype], copy=False))
+        if isinstance(arr, np.ndarray) and a.ctypes.data == arr.ctypes.data:
+            pin_in_place(a)  # pageable caller memory: page-locked in place (cached), copies become asynchronous
         with warnings.catch_warnings():
             warnings.simplefilter("ignore", UserWarning)  # read-only inputs are never written to
             return torch.from_numpy(a)
@@ -566,7 +576,7 @@ class MRIB200NUFFT(FourierOperatorBase):
         h2d, d2h = self._copy_streams()
         h2d.wait_stream(cur)   # the buffers below may be recycled blocks with work pending on `cur`
         d2h.wait_stream(cur)
-        T = max(c1 - c0 for c0, c1 in self._chunks())
+        T = max(c1 - c0 for c0, c1 in self._chunks(host=True))
         src = self._host_tensor(data, cdt)
         out_h = torch.empty((B, C, K), dtype=cdt, pin_memory=True)
         kbuf = [torch.empty((T, K), dtype=cdt, device=dev) for _ in range(2)]
@@ -578,7 +588,7 @@ class MRIB200NUFFT(FourierOperatorBase):
         d2h_done, comp_done = [None, None], [None, None]
         i = 0
         for b in range(B):
-            for c0, c1 in self._chunks():
+            for c0, c1 in self._chunks(host=True):
                 k, n = i % 2, c1 - c0
                 if d2h_done[k] is not None:
                     cur.wait_event(d2h_done[k])          # kbuf[k] has been copied out
@@ -611,7 +621,7 @@ class MRIB200NUFFT(FourierOperatorBase):
                 t.record_stream(h2d)
         return out_h.numpy()
 
-    def _adj_host_pipelined(self, coeffs) -> np.ndarray:
+    def _adj_host_pipelined(self, coeffs, keep_on_device=False):
         """``adj_op`` on a host array: the next chunk's k-space comes in on a copy stream while the
         current chunk is transformed; SENSE accumulates the coil-combined image on the device,
         calibrationless images leave chunk by chunk on the other copy stream."""
@@ -622,7 +632,7 @@ class MRIB200NUFFT(FourierOperatorBase):
         h2d, d2h = self._copy_streams()
         h2d.wait_stream(cur)
         d2h.wait_stream(cur)
-        T = max(c1 - c0 for c0, c1 in self._chunks())
+        T = max(c1 - c0 for c0, c1 in self._chunks(host=True))
         src = self._host_tensor(coeffs, cdt).reshape(B, C, K)
         kbuf = [torch.empty((T, K), dtype=cdt, device=dev) for _ in range(2)]
         sense = self.uses_sense
@@ -634,7 +644,7 @@ class MRIB200NUFFT(FourierOperatorBase):
         comp_done, d2h_done = [None, None], [None, None]
         i = 0
         for b in range(B):
-            for j, (c0, c1) in enumerate(self._chunks()):
+            for j, (c0, c1) in enumerate(self._chunks(host=True)):
                 k, n = i % 2, c1 - c0
                 with torch.cuda.stream(h2d):
                     if comp_done[k] is not None:
@@ -667,6 +677,8 @@ class MRIB200NUFFT(FourierOperatorBase):
         if sense:
             if self._double:
                 img_d *= float(self.inv_norm_factor)
+            if keep_on_device:  # (the coil-sharded operator sums over ranks before the image leaves the device)
+                return img_d
             return from_device(img_d, "numpy", None)
         d2h.synchronize()
         for t in obuf:

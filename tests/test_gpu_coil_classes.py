@@ -190,7 +190,7 @@ def test_classes_with_a_dense_centre_split_over_chunks(mods, cls):
 def test_one_plan_serves_calls_of_different_coil_counts(mods):
     """cfg-D's pattern: 16-coil transforms and the single-coil power method on the same plan, interleaved;
     every class keeps its own stream, `update_samples` invalidates all of them."""
-    mrinufft, _, _ = mods
+    mrinufft, _, torch = mods
     rng = np.random.default_rng(8)
     shape, M, C = (32, 32, 32), 20_000, 16
     samples = rng.uniform(-0.5, 0.5, (M, 3)).astype(np.float32)
@@ -198,18 +198,22 @@ def test_one_plan_serves_calls_of_different_coil_counts(mods):
     smaps /= np.linalg.norm(smaps, axis=0)
     op = mrinufft.get_operator("b200")(samples, shape, n_coils=C, smaps=smaps, squeeze_dims=False)
     plan = op.raw_op.plan
-    img, ksp = _c(rng, 1, 1, *shape), _c(rng, 1, C, M)
-    y0 = op.op(img)
+    # device arrays: all 16 coils in one call (host arrays run as chunks of 8 coils, see `_chunks`)
+    img, ksp = torch.from_numpy(_c(rng, 1, 1, *shape)).cuda(), torch.from_numpy(_c(rng, 1, C, M)).cuda()
+    y0 = op.op(img).cpu().numpy()
     np.random.seed(0)
     lip0 = op.get_lipschitz_cst(max_iter=5)
     assert plan.rows_class(16)["visits"] > 0 and plan.rows_class(1)["visits"] > 0
-    assert rel_l2(op.op(img), y0) <= 1e-6  # (the interpolator adds its partial sums with atomics)
+    assert rel_l2(op.op(img).cpu().numpy(), y0) <= 1e-6  # (the interpolator adds its partial sums with atomics)
     moved = (samples + rng.uniform(-0.01, 0.01, samples.shape)).astype(np.float32)
     op.samples = moved
     assert plan.rows_class(16)["visits"] == 0 and plan.rows_class(1)["visits"] == 0
     fresh = mrinufft.get_operator("b200")(moved, shape, n_coils=C, smaps=smaps, squeeze_dims=False)
-    assert rel_l2(op.op(img), fresh.op(img)) <= 1e-6
-    assert rel_l2(op.adj_op(ksp), fresh.adj_op(ksp)) <= 1e-6
+    assert rel_l2(op.op(img).cpu().numpy(), fresh.op(img).cpu().numpy()) <= 1e-6
+    assert rel_l2(op.adj_op(ksp).cpu().numpy(), fresh.adj_op(ksp).cpu().numpy()) <= 1e-6
+    # host arrays take the same plan through chunks of 8 coils: a third class on the same points
+    assert rel_l2(op.op(img.cpu().numpy()), fresh.op(img).cpu().numpy()) <= 1e-6
+    assert op.raw_op.plan.rows_class(8)["visits"] > 0
     np.random.seed(0)
     lip1 = fresh.get_lipschitz_cst(max_iter=5)
     np.random.seed(0)

@@ -4,10 +4,10 @@ API calls with device-resident torch inputs (CUDA events), one JSON line per con
 
     python tools/bench_configs.py [--quick]
 
-cfg-A  README demo: 2-D radial 100 x 500, 512^2, single coil (density: pipe instead of voronoi)
+cfg-A  README demo: 2-D radial 100 x 500, 512^2, single coil, density="voronoi"
 cfg-B  2-D spiral 64 x 2048, 320^2, 32 coils with smaps: op / adj_op / data_consistency
-cfg-D  3-D 256^3, 16 coils, density="pipe" + pinv_solver(optim="cg" | "lsqr", max_iter=10), and the
-       reference's host-driven lsqr on the same operator for two iterations (what device residency saves)
+cfg-D  3-D 256^3, 16 coils with smaps, density="pipe" + pinv_solver(optim="cg", max_iter=10) on a smooth
+       phantom: NRMSE per iteration, as written and with the step size of the operator that is iterated on
 cfg-E  2-D 256^2, 8 coils with smaps, M = 32768, off-resonance correction with L = 10 interpolators riding
        the coil batch, one unrolled gradient step with torch autograd (data + field-map gradients)
 """
@@ -48,14 +48,16 @@ def crandn(*s):
 
 
 def cfg_a():
+    """BASELINE configs[0], the README demo as written: density="voronoi" through the constructor."""
     traj = initialize_2D_radial(100, 500).astype(np.float32)
     t0 = time.perf_counter()
-    op = mrinufft.get_operator("b200")(traj, (512, 512), density="pipe")
+    op = mrinufft.get_operator("b200")(traj, (512, 512), density="voronoi")
     torch.cuda.synchronize()
     setup = time.perf_counter() - t0
     img, ksp = crandn(512, 512), crandn(op.n_samples)
-    return {"config": "A: 2D radial 100x500, 512^2, 1 coil, density=pipe", "setup_s_incl_pipe": setup,
-            "op_ms": timed(lambda: op.op(img)), "adj_op_ms": timed(lambda: op.adj_op(ksp))}
+    return {"config": "A: README demo, 2D radial 100x500, 512^2, 1 coil, density=voronoi", "setup_s_incl_voronoi": setup,
+            "op_ms": timed(lambda: op.op(img), 20), "adj_op_ms": timed(lambda: op.adj_op(ksp), 20),
+            "rows_class": op.raw_op.plan.rows_class(1)["class"]}
 
 
 def cfg_b():
@@ -74,64 +76,100 @@ def cfg_b():
     return r
 
 
+def smooth_phantom(n, dev):
+    """Sum of soft-edged ellipsoids and Gaussian blobs, complex with a slowly varying phase: a volume whose
+    spectrum lives inside the ball a radial trajectory samples (a white-noise volume does not)."""
+    ax = torch.linspace(-1, 1, n, device=dev)
+    z, y, x = torch.meshgrid(ax, ax, ax, indexing="ij")
+    vol = torch.zeros((n, n, n), device=dev)
+    for (cz, cy, cx, rz, ry, rx, amp) in [(0, 0, 0, .8, .7, .6, 1.0), (.1, -.2, .15, .35, .3, .25, -.4),
+                                          (-.25, .2, -.2, .2, .25, .15, .6), (.3, .3, .1, .12, .1, .15, .8)]:
+        r = torch.sqrt(((z - cz) / rz) ** 2 + ((y - cy) / ry) ** 2 + ((x - cx) / rx) ** 2)
+        vol += amp * torch.sigmoid((1 - r) * 8)
+    phase = 0.6 * torch.sin(2.0 * x + 1.0) * torch.cos(1.5 * y) + 0.3 * z
+    return (vol * torch.exp(1j * phase)).to(torch.complex64)
+
+
+def smooth_smaps(C, n, dev):
+    """Birdcage-like sensitivity maps: coils on a sphere around the volume, magnitude falling with distance,
+    a linear phase per coil, normalised to unit root-sum-of-squares."""
+    ax = torch.linspace(-1, 1, n, device=dev)
+    z, y, x = torch.meshgrid(ax, ax, ax, indexing="ij")
+    maps = torch.empty((C, n, n, n), dtype=torch.complex64, device=dev)
+    for c in range(C):
+        th, ph = np.pi * (c + 0.5) / C, 2 * np.pi * ((c * 0.618) % 1.0)
+        cz, cy, cx = 1.4 * np.cos(th), 1.4 * np.sin(th) * np.sin(ph), 1.4 * np.sin(th) * np.cos(ph)
+        d2 = (z - cz) ** 2 + (y - cy) ** 2 + (x - cx) ** 2
+        maps[c] = torch.exp(-d2 / 1.5) * torch.exp(1j * (1.2 * (cx * x + cy * y + cz * z) + 0.4 * c))
+    maps /= torch.sqrt(torch.sum(maps.real ** 2 + maps.imag ** 2, dim=0, keepdim=True))
+    return maps
+
+
 def cfg_d(quick):
+    """BASELINE configs[3] as written: 3-D 256^3, 16 coils with sensitivity maps, density="pipe" through the
+    constructor, pinv_solver(optim="cg", max_iter=10) -- a SENSE reconstruction of a smooth phantom from its
+    noisy radial k-space, NRMSE against the truth after every iteration.
+
+    The reference's `cg` takes its step size from the density-WEIGHTED operator and then iterates on the
+    un-weighted one (extras/optim.py:839-842): with Pipe's normalisation the weighted Lipschitz constant is a
+    fraction of the un-weighted one and the iteration leaves the (good) density-compensated start it was given
+    and diverges -- on the reference's own exact NDFT too (tests/test_solvers_cpu.py pins that).  `as_written`
+    mirrors it; `step_from_iterated_operator` hands `cg` the Lipschitz constant of the operator it iterates
+    on (`lipschitz_cst=`, the argument the coil-sharded solver uses) and is the reconstruction."""
     n = 128 if quick else 256
     traj = initialize_3D_phyllotaxis_radial(4096 if quick else 16384, 512).astype(np.float32).reshape(-1, 3)
-    C, shape = 16, (n, n, n)
+    C, shape, dev = 16, (n, n, n), torch.device("cuda")
+    smaps = smooth_smaps(C, n, dev)
+    x_true = smooth_phantom(n, dev).reshape(1, 1, *shape)
+    torch.cuda.synchronize()
     t0 = time.perf_counter()
-    op_d = mrinufft.get_operator("b200")(traj, shape, n_coils=C, density="pipe", squeeze_dims=False)
+    op = mrinufft.get_operator("b200")(traj, shape, n_coils=C, smaps=smaps, density="pipe", squeeze_dims=False)
     torch.cuda.synchronize()
     setup = time.perf_counter() - t0
-    # consistent data: k-space of a random 16-coil volume plus 1 % noise
-    x_true = crandn(1, C, *shape)
-    ksp = op_d._op_device(x_true)
+    ksp = op._op_device(x_true)
     ksp += 0.01 * torch.linalg.norm(ksp) / np.sqrt(ksp.numel()) * crandn(*ksp.shape)
-    # density-compensated adjoint as the starting point, then CG on the un-weighted normal equations.
-    # (pinv_solver(optim="cg") on the density-weighted operator itself follows the reference statement by
-    # statement -- extras/optim.py:832-842 takes the step size from the density-WEIGHTED operator and then
-    # iterates on the un-weighted one -- and therefore diverges on a centre-heavy radial trajectory.)
-    x0 = op_d._adj_device(ksp)
-    del op_d
-    torch.cuda.empty_cache()
-    op = mrinufft.get_operator("b200")(traj, shape, n_coils=C, squeeze_dims=False)
-    res = []
+    nt = torch.linalg.norm(x_true)
+    hist = []
 
     def cb(x, operator, y, **kw):
-        res.append(float(torch.linalg.norm(operator.op(x) - y) / torch.linalg.norm(y)))
+        hist.append(float(torch.linalg.norm(x.reshape(x_true.shape) - x_true) / nt))
 
-    def err(x):
-        return float(torch.linalg.norm(x.reshape(x_true.shape) - x_true) / torch.linalg.norm(x_true))
-
+    out = {"config": f"D: 3D {n}^3, 16 coils with smaps, M={op.n_samples} radial, density=pipe, "
+                     "pinv_solver(optim=cg, max_iter=10), smooth phantom + 1 % noise",
+           "setup_s_incl_pipe_density": setup, "rows_class_16_coils": op.raw_op.plan.rows_class(C)["class"]}
+    x_dc = op._adj_device(ksp)
+    x_dc *= torch.vdot(x_dc.ravel(), x_true.ravel()) / torch.vdot(x_dc.ravel(), x_dc.ravel())
+    out["nrmse_density_compensated_adjoint_best_scale"] = float(torch.linalg.norm(x_dc - x_true) / nt)
+    del x_dc
     np.random.seed(0)
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    x, _ = op.pinv_solver(ksp, optim="cg", max_iter=10, x_init=x0, callback=cb)
-    torch.cuda.synchronize()
-    cg_s = time.perf_counter() - t0
-    out = {"config": f"D: 3D {n}^3, 16 coils (calibrationless), M={op.n_samples}, k-space of a random volume + 1 % noise",
-           "setup_s_incl_pipe": setup, "cg_10_iterations_s_incl_callback": cg_s,
-           "cg_rel_residual_first_last": [res[0], res[-1]], "cg_rel_image_error": err(x),
-           "result_finite": bool(torch.isfinite(x).all())}
-    del x
-    # the reference's default optimiser, device resident (mrinufft_b200/solvers.py), from a zero start
-    res.clear()
-    x, _ = op.pinv_solver(ksp, optim="lsqr", max_iter=10, callback=cb)
-    out["lsqr_rel_residual_first_last"] = [res[0], res[-1]]
-    out["lsqr_rel_image_error"] = err(x)
-    del x
-    for name in ("lsqr", "lsmr"):
+    lip_w = float(op.get_lipschitz_cst())
+    dens = op.density
+    op.density = None
+    np.random.seed(0)
+    lip_u = float(op.get_lipschitz_cst())
+    op.density = dens
+    out["lipschitz_density_weighted"], out["lipschitz_unweighted"] = lip_w, lip_u
+    for name, kw in (("as_written", {}), ("step_from_iterated_operator", {"lipschitz_cst": lip_u})):
+        hist.clear()
+        np.random.seed(0)
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        op.pinv_solver(ksp, optim=name, max_iter=10)
+        x, _ = op.pinv_solver(ksp, optim="cg", max_iter=10, callback=cb, **kw)
         torch.cuda.synchronize()
-        out[f"{name}_10_iterations_s"] = time.perf_counter() - t0
-    # the reference's lsqr (extras/optim.py:249-495) driving the same operator through host arrays
-    from mrinufft.extras import get_optimizer
-
-    ksp_h = ksp.cpu().numpy()
+        out[name] = {"cg_10_iterations_s_incl_callback": time.perf_counter() - t0,
+                     "nrmse_per_iteration": [round(h, 5) if np.isfinite(h) else str(h) for h in hist],
+                     "monotone": bool(all(b <= a for a, b in zip(hist, hist[1:]))),
+                     "result_finite": bool(torch.isfinite(x).all())}
+        del x
+    # the reference's default optimiser, device resident (mrinufft_b200/solvers.py), from a zero start
+    hist.clear()
+    torch.cuda.synchronize()
     t0 = time.perf_counter()
-    get_optimizer("lsqr")(operator=op, kspace_data=ksp_h, max_iter=2, progressbar=False)
-    out["reference_lsqr_host_driven_s_per_iteration"] = (time.perf_counter() - t0) / 2
+    x, _ = op.pinv_solver(ksp, optim="lsqr", max_iter=10, callback=cb)
+    torch.cuda.synchronize()
+    out["lsqr"] = {"lsqr_10_iterations_s_incl_callback": time.perf_counter() - t0,
+                   "nrmse_per_iteration": [round(h, 5) for h in hist]}
+    del x
     return out
 
 
@@ -164,10 +202,18 @@ def cfg_e():
     return r
 
 
-if __name__ == "__main__":
-    quick = "--quick" in sys.argv
+def run_all(quick=False):
+    """Every configuration, one dict each (bench.py puts them under ``extras.configs``)."""
+    out = []
     for f in (cfg_a, cfg_b, lambda: cfg_d(quick), cfg_e):
         try:
-            print(json.dumps(f()), flush=True)
+            out.append(f())
         except Exception as exc:  # noqa: BLE001
-            print(json.dumps({"error": repr(exc)[:300]}), flush=True)
+            out.append({"error": repr(exc)[:300]})
+        torch.cuda.empty_cache()
+    return out
+
+
+if __name__ == "__main__":
+    for r in run_all("--quick" in sys.argv):
+        print(json.dumps(r), flush=True)
