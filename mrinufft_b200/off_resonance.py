@@ -78,7 +78,7 @@ class MRIB200FourierCorrected(MRIFourierCorrected):
         if fo.raw_op.isign_flip != vop.raw_op.isign_flip:
             vop.raw_op.toggle_grad_traj()
         self._fused = {"vop": vop, "B": Bd.reshape(-1, L).contiguous(), "L": L, "C": C,
-                       "smaps_id": id(fo._smaps_d), "pts_id": id(fo.raw_op._pts)}
+                       "smaps_id": getattr(fo, "_smaps_version", 0), "pts_id": fo.raw_op.pts_version}
         return True
 
     def _vop(self):
@@ -97,24 +97,39 @@ class MRIB200FourierCorrected(MRIFourierCorrected):
         if fo._conj_smaps:
             return None
         f = self._fused
-        if fo.uses_sense and f["smaps_id"] != id(fo._smaps_d):  # smaps were replaced: rebuild
+        if fo.uses_sense and f["smaps_id"] != getattr(fo, "_smaps_version", 0):  # smaps were replaced: rebuild
             self._fused = None
             if not self._ensure_fused():
                 return None
             f = self._fused
         vop = f["vop"]
-        if f["pts_id"] != id(fo.raw_op._pts):
+        if f["pts_id"] != fo.raw_op.pts_version:
             if fo.n_samples != int(self.n_shots) * int(self.n_samples_per_shot):
                 return None  # the temporal interpolator no longer matches the trajectory
             vop.raw_op._set_pts(fo.raw_op._pts)
             vop._samples = fo._samples
             vop._toeplitz_kernel = None
-            f["pts_id"] = id(fo.raw_op._pts)
+            f["pts_id"] = fo.raw_op.pts_version
         if vop.raw_op.isign_flip != fo.raw_op.isign_flip:
             vop.raw_op.toggle_grad_traj()
         vop._density_d = fo._density_d  # density multiplies k-space before the adjoint only
         vop._density = fo._density
         return vop
+
+    def update_samples(self, new_samples, *, unsafe: bool = False):
+        """New sample locations for the inner operator (and, through `_vop`, the batched one).  The reference
+        wrapper inherits `FourierOperatorBase.update_samples` (base.py:809-830), which only stores the array
+        on the wrapper and leaves the inner operator on the old trajectory."""
+        self._fourier_op.update_samples(new_samples, unsafe=unsafe)
+        self._samples = self._fourier_op.samples
+
+    @property
+    def samples(self):
+        return self._fourier_op.samples
+
+    @samples.setter
+    def samples(self, new_samples):
+        self.update_samples(new_samples)
 
     # ------------------------------------------------------------------ autodiff
     def make_autograd(self, *, wrt_data=True, wrt_traj=False, wrt_field_map=False, paired_batch=False):

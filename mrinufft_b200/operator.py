@@ -68,6 +68,7 @@ class RawB200Plan:
                               spread_only=spread_only, device=self.device.index, double=self.double)
         self.n_samples = 0
         self._pts = None
+        self.pts_version = 0  # bumped by every _set_pts (object ids are recycled, a counter is not)
         self._set_pts(samples)
 
     @property
@@ -80,6 +81,7 @@ class RawB200Plan:
         if pts.ndim != 2 or pts.shape[1] != self.ndim:
             raise ValueError(f"samples should have shape (M, {self.ndim}), got {tuple(pts.shape)}")
         self._pts = pts
+        self.pts_version += 1
         self.n_samples = int(pts.shape[0])
         self.plan.setpts(pts.data_ptr(), self.n_samples, self.stream)
 
@@ -287,6 +289,7 @@ class MRIB200NUFFT(FourierOperatorBase):
         # accepts numpy, torch (cpu/cuda) and cupy arrays; the base setter only takes numpy
         # (base.py:759-760) -- same override as cufinufft.py:277-315.
         self._smaps_lazy_host = False
+        self._smaps_version = getattr(self, "_smaps_version", 0) + 1
         if new_smaps is None:
             self._smaps = None
             self._smaps_d = None

@@ -57,6 +57,10 @@ def main():
         a_full = full.adj_op(y_full)
         a = sh.adj_op(y)
         errs["adj_op"] = rel(a, a_full if sense else a_full[:, lo:hi])
+        # host arrays in, host arrays out: the sum over ranks still happens on the device
+        a_h = sh.adj_op(y.cpu().numpy())
+        assert isinstance(a_h, np.ndarray)
+        errs["adj_op_host_arrays"] = rel(a_h, a_full if sense else a_full[:, lo:hi])
         g_full = full.data_consistency(x, 0.5 * y_full)
         g = sh.data_consistency(x if sense else x[:, lo:hi].contiguous(), 0.5 * y)
         errs["data_consistency"] = rel(g, g_full if sense else g_full[:, lo:hi])
