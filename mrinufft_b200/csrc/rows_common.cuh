@@ -106,13 +106,13 @@ struct Cls {
   static constexpr int TFS = 18;                     // class 32: flush planes [16 coils][16 cells], float stride
   static constexpr int TCS = 144;                    // class < 32: byte stride of the transpose rows [32 lanes][16 cells] of
                                                      // interleaved (re, im): 16-byte aligned, conflict-free 128-bit column reads
-  static constexpr int SM_TBUF = GENERIC ? 32 * TCS : 2 * 32 * TBS * 4;
-  static_assert(!GENERIC || 2 * 32 * TFS * 4 <= SM_TBUF, "the interpolator's planes [2][32 lanes][TFS] share that memory");
   // interpolator, class < 32: partial sums of OBV visits, [visit][lane] (re, im) in rows of OBS bytes (the
-  // 8 bytes of skew keep the column reads of the one-coil class off a single bank); shares the transpose
-  // planes' memory (a tile is loaded between runs of visits, never during one)
-  static constexpr int OBV = 16, OBS = 264;
-  static_assert(!GENERIC || OBV * OBS <= SM_TBUF, "partial-sum buffer must fit in the transpose buffer");
+  // skew keeps the column reads of the reduction -- half a warp = 16 / TC visits x TC coils -- off each
+  // other's banks; tools/gen_taps.py `obuf_stride`); shares the transpose planes' memory (a tile is loaded
+  // between runs of visits, never during one)
+  static constexpr int OBV = 16, OBS = TC >= 16 ? 256 : 256 + 8 * TC;
+  static constexpr int SM_TBUF = GENERIC ? (32 * TCS > OBV * OBS ? 32 * TCS : OBV * OBS) : 2 * 32 * TBS * 4;
+  static_assert(!GENERIC || 2 * 32 * TFS * 4 <= SM_TBUF, "the interpolator's planes [2][32 lanes][TFS] share that memory");
   static_assert(GENERIC || 2 * 16 * TFS * 4 <= SM_TBUF, "flush planes must fit in the transpose buffer");
   __host__ __device__ static constexpr int smem_per_warp(bool spread) { return (spread ? SM_VBUF : 0) + SM_META + SM_TBUF; }
 };

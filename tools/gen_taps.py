@@ -38,7 +38,13 @@ visit k + 1 is loaded before the taps of visit k execute.  See `gen_loop` for th
 import sys
 
 NJ = 8  # cell pairs per row
-OBUF_STRIDE = 264  # bytes per visit of the interpolator's partial-sum buffer (32 lanes x 8 + bank skew)
+
+
+def obuf_stride(TC):
+    """Bytes per visit of the interpolator's partial-sum buffer: 32 lanes x 8 plus a skew that keeps the
+    column reads of the reduction (half a warp = 16 / TC visits x TC coils) off each other's banks.
+    Mirrors `Cls::OBS` in rows_common.cuh."""
+    return 256 if TC >= 16 else 256 + 8 * TC
 
 
 def class_geometry(dim, TC):
@@ -67,6 +73,7 @@ class Layout:
         self.pkt = 32 + self.esz
         self.vstride = TC * 8
         self.generic = TC != 32
+        self.obs = obuf_stride(TC)
 
 
 def load_set(lay, X, k, pred, spread):
@@ -149,10 +156,10 @@ def taps_interp(lay, W, X, c, slot):
           "mov.b64 {lo, hi}, S1;", "add.f32 t1, lo, hi;"]
     if lay.generic:
         # the G row groups of a coil each hold a partial sum: parked in shared memory ([visit][lane], rows of
-        # OBUF_STRIDE bytes), summed and added to k-space by the kernel after the run (one compact loop
+        # `obuf_stride` bytes), summed and added to k-space by the kernel after the run (one compact loop
         # instead of shuffles + a predicated red in every tap-kernel case: the visit loops stay small
         # enough for the instruction cache)
-        L += [f"st.shared.v2.f32 [ob+{slot * OBUF_STRIDE}], {{t0, t1}};"]
+        L += [f"st.shared.v2.f32 [ob+{slot * lay.obs}], {{t0, t1}};"]
     else:
         L += [f"mad.wide.u32 addr, n{X}, 256, ktl;",
               "red.global.add.v2.f32 [addr], {t0, t1};"]
@@ -180,7 +187,7 @@ def gen_loop(W, spread, dim=3, TC=32):
         if spread:
             s.append(f"add.u32 vb, vb, {k * lay.vstride};")
         elif lay.generic:
-            s.append(f"add.u32 ob, ob, {k * OBUF_STRIDE};")
+            s.append(f"add.u32 ob, ob, {k * lay.obs};")
         s.append(f"add.s32 n, n, -{k};")
         return s
 

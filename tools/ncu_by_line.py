@@ -53,7 +53,11 @@ def main():
             cur["hdr"] = row
         elif cur is not None and row:
             cur["rows"].append(row)
-    blk = [b for b in blocks][kidx]
+    # (ncu prints every kernel twice when the report holds source and SASS views: keep one of each pair)
+    if len(blocks) >= 2 and all(blocks[i]["name"] == blocks[i + 1]["name"] and len(blocks[i]["rows"]) == len(blocks[i + 1]["rows"])
+                                for i in range(0, len(blocks) - 1, 2)):
+        blocks = blocks[::2]
+    blk = blocks[kidx]
     h = blk["hdr"]
     ie, ss = h.index("Instructions Executed"), h.index("# Samples")
     extra = [c for c in ("stall_no_inst", "stall_long_sb", "stall_wait", "stall_short_sb", "stall_branch_resolving",
