@@ -61,6 +61,7 @@ def parse_args():
     ap.add_argument("--interp-method", type=int, default=0)
     ap.add_argument("--fft-method", type=int, default=0, help="0 auto, 1 cuFFT + pad/crop kernels, 2 fused zero-padding-aware passes")
     ap.add_argument("--rows-dbg", type=int, default=0, help="debug switches of the row kernels (timing experiments)")
+    ap.add_argument("--fft-lookahead", type=int, default=-1, help="L2 prefetch look-ahead of the FFT passes in CTAs (-1: library default)")
     args = ap.parse_args()
     args.total_coils = args.coils
     return args
@@ -353,6 +354,8 @@ def run_b200(args):
         pl.set_option(1, args.interp_method)
         pl.set_option(2, args.fft_method)
         pl.set_option(3, args.rows_dbg)
+        if args.fft_lookahead >= 0:
+            pl.set_option(5, args.fft_lookahead)
         return sop, smaps
 
     # the product path: this rank's shard of the 32-coil operator (strong scaling: C / N coils per GPU)

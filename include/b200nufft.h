@@ -196,7 +196,8 @@ int b200_launch_count(int64_t* kernels, int64_t* ffts, int reset);
  * Select kernel variants at run time (A/B measurements; 0 = default for every key).
  *   key 0: spread method   (0 auto, 1 global-atomic point driven, 2 tiled)
  *   key 1: interp method   (0 auto, 1 point driven, 2 tiled)
- *   key 2: FFT method      (0 auto, 1 cuFFT + pad/crop kernels, 2 fused zero-padding-aware passes)
+ *   key 2: FFT method      (0 auto, 1 cuFFT + pad/crop kernels, 2 fused zero-padding-aware passes,
+ *          3 the same with the tiles of the strided passes loaded by TMA bulk tensor copies)
  *   key 3: timing experiments on the tiled spreader (bit 0: skip the tile flush, bit 1: skip the
  *          coil-value copies; results are then wrong -- never set outside a profiling session;
  *          bit 3: pretend the visit stream does not fit 32-bit indices, which exercises the
@@ -204,6 +205,7 @@ int b200_launch_count(int64_t* kernels, int64_t* ffts, int reset);
  *   key 4: smallest coil class of the tiled kernels (0 = by the call's coil count T, else 1, 2, 4, 8,
  *          16 or 32: a call with T coils runs in the smallest class >= max(T, value); tests use it to
  *          push a small batch through every class)
+ *   key 5: look-ahead, in CTAs, of the L2 prefetch of the strided FFT passes (0 = off)
  */
 int b200_plan_set_option(b200_plan* plan, int key, int64_t value);
 

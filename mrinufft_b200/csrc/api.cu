@@ -111,7 +111,7 @@ int do_interp(b200_plan* p, const float2* fw, float2* ksp, int T, float scale, c
 }
 
 bool use_fftp(const b200_plan* p) {
-  return p->fft_method != 1 && fftp_supported(p);
+  return p->fft_method != 1 && fftp_supported(p);  // (2: forced, 3: with bulk tensor loads)
 }
 
 // image(s) -> transformed oversampled grid (K4a + FFT)
@@ -376,6 +376,7 @@ int b200_plan_destroy(b200_plan* p) {
   };
   tiled_free(p);
   dbl_free(p);
+  fftp_free(p);
   fr(p->d_poly);
   for (int a = 0; a < 3; ++a) {
     fr(p->d_deapod[a]);
@@ -460,6 +461,9 @@ int b200_plan_set_option(b200_plan* p, int key, int64_t value) {
         return B200_EINVAL;
       }
       p->rows_class = (int)value;
+      break;
+    case 5:
+      p->fft_lookahead = value > 0 ? (int)value : 0;
       break;
     default:
       b200_set_error("unknown option key %d", key);

@@ -121,6 +121,8 @@ struct b200_plan {
   void* tiled = nullptr;
   // complex128 path (double_path.cu): non-null for plans created with B200_DOUBLE
   void* dbl = nullptr;
+  // tensor maps of the TMA variant of the FFT passes (fft_pruned.cu)
+  void* tma = nullptr;
   // spreading into a grid that the fused FFT passes consume next: tiles without visitors are neither
   // zero-filled by the spreader nor read by the first FFT pass (flag byte per tile, see spread_rows.cu)
   bool spread_may_skip_empty = false;       // set by the caller of do_spread
@@ -131,6 +133,7 @@ struct b200_plan {
   // options
   int spread_method = 0, interp_method = 0, fft_method = 0;
   int rows_dbg = 0;  // option 3: timing-experiment switches of the spreading row kernel (see b200nufft.h)
+  int fft_lookahead = 0;  // option 5: look-ahead (in CTAs) of the L2 prefetch of the strided FFT passes (0: off)
   int rows_class = 0;  // option 4: smallest coil class the row kernels may pick (0: by the call's coil count)
 
   // timing
@@ -172,6 +175,7 @@ int fftp_type2(b200_plan* p, const float2* img, const float2* smaps, float2* fw,
 int k_mul_real(b200_plan* p, float2* fw, const float* kern, int T, cudaStream_t st);
 int fftp_type1(b200_plan* p, float2* fw, const float2* smaps, float2* img, int T, int accumulate,
                int isign, float scale, int conj_smaps, cudaStream_t st, const uint32_t* empty = nullptr);
+void fftp_free(b200_plan* p);
 
 // complex128 path (double_path.cu)
 int dbl_init(b200_plan* p);

@@ -24,6 +24,8 @@
 // cuFFT + k_pad / k_crop (api.cu).  Replaces finufft's FFTW call + deconvolve step reached through
 // `Plan.execute` / `Plan.execute_adjoint` (src/mrinufft/operators/interfaces/finufft.py:69,76) and
 // the smaps / coil-combine passes of src/mrinufft/operators/base.py:988-993, 1045-1051.
+#include <cuda.h>  // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint)
+
 #include "common.cuh"
 #include "device_utils.cuh"
 #include "fft_reg.cuh"
@@ -73,19 +75,55 @@ struct StridedArgs {
   int empty_3d;            // 1: transformed axis = z, outer index = y; 0 (2-D): transformed axis = y
   int empty_out;           // 0: applies to the inputs (type 1), 1: to the outputs (type 2)
   int nyh, nbx;
+  int tma_z;               // TMA variant: 1 = the transformed axis is dimension 2 of the tensor map (3-D z-pass),
+                           // 0 = dimension 1 (3-D y-pass, 2-D pass)
+  int lookahead;           // > 0: every CTA pulls the input lines of the tile `lookahead` CTAs behind it in launch
+                           // order into L2 (prefetch.global.L2), so that tile's loads are L2 hits when it runs
 };
+
+// ---- TMA (cp.async.bulk.tensor) + mbarrier plumbing of the bulk-load variant of the strided pass
+__device__ __forceinline__ unsigned smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@!p bra WAIT_%=;\n"
+      "}\n" ::"r"(smem_addr(bar)), "r"(parity)
+      : "memory");
+}
+// one box of the 4-D tensor (x, y, z, coil) -> shared memory, completion counted in bytes on `bar`
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, int c0, int c1, int c2, int c3,
+                                            unsigned long long* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];\n" ::
+          "r"(smem_addr(dst)), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_addr(bar))
+      : "memory");
+}
 
 // EMODE 0: plain; 1: the spreader's empty tiles are not read (type 1, first pass); 2: tiles that no
 // point visits are not written (type 2, last pass: the row interpolator never reads them)
 // KIN / KOUT = 1: the non-zero inputs / wanted outputs are the modes of an N = L / 2 image (sigma = 2), a
 // pattern known at compile time: inputs n1 < R1/4 or n1 >= 3 R1/4, outputs k2 < R2/4 or k2 >= 3 R2/4 --
 // no per-element predicates.  0: generic (run-time `Keep`, all-kept included).
-template <int L, int DIR, bool MUL, int EMODE, int KIN, int KOUT>
+// TMA = true: the tile is brought into shared memory with bulk tensor copies (cp.async.bulk.tensor, boxes of
+// 16 columns x BZ = 32 grid rows / planes = 4 KB, issued by one thread, completion on an mbarrier) instead of R1
+// global loads per thread; step A then works in place on the tile.  Boxes that hold only zero padding, or
+// only tiles the spreader left unwritten, are not issued.
+template <int L, int DIR, bool MUL, int EMODE, int KIN, int KOUT, bool TMA>
 __global__ void __launch_bounds__(FT, L <= 512 ? 3 : 1)
-k_fft_strided(StridedArgs A, const float2* __restrict__ tw) {
+k_fft_strided(StridedArgs A, const float2* __restrict__ tw, const __grid_constant__ CUtensorMap tmap) {
   constexpr bool EMPTY = EMODE != 0;
   constexpr int R1 = Split<L>::R1, R2 = Split<L>::R2;
-  extern __shared__ float2 S[];  // [L][TX]
+  extern __shared__ __align__(128) float2 S[];  // [L][TX]
   const int lo = kept_index(blockIdx.y, A.outer_L, A.outer_keep);
   // with the Toeplitz multiply the coil index varies fastest over the grid of CTAs: the 32 CTAs that
   // need the same tile of the (coil-independent) factor run together and share it through L2
@@ -111,12 +149,59 @@ k_fft_strided(StridedArgs A, const float2* __restrict__ tw) {
       return;
     }
   }
+  // Look-ahead prefetch: the strided passes are bound by the latency of their (independent, but per CTA
+  // serialised) loads; the tile of a CTA that starts a wave later is requested now, without holding
+  // registers or warps for it.  One 128-byte line per thread and prefetched row.
+  if (!MUL && A.lookahead > 0) {
+    const long long nx = gridDim.x, ny = gridDim.y, nz = gridDim.z;
+    const long long id = blockIdx.x + nx * (blockIdx.y + ny * (long long)blockIdx.z) + A.lookahead;
+    if (id < nx * ny * nz) {
+      const int pbx = (int)(id % nx), pby = (int)((id / nx) % ny), pbt = (int)(id / (nx * ny));
+      const int plo = kept_index(pby, A.outer_L, A.outer_keep);
+      const char* pg = reinterpret_cast<const char*>(A.base + (long long)pbt * A.coil_stride +
+                                                     (long long)plo * A.outer_stride + (long long)pbx * TX);
+      for (int n = threadIdx.x; n < L; n += FT) {
+        bool live = KIN == 1 ? (n < L / 4 || n >= 3 * L / 4) : kept(n, L, A.in);
+        if (EMODE == 1 && live) {
+          const long long col = (long long)(plo >> 1) * A.nbx + pbx;
+          live = !((__ldg(A.empty + col * (L / 32) + (n >> 5)) >> (n & 31)) & 1u);
+        }
+        if (live) asm volatile("prefetch.global.L2 [%0];\n" ::"l"(pg + (long long)n * A.stride_n * (long long)sizeof(float2)));
+      }
+    }
+  }
+  if constexpr (TMA) {
+    constexpr int BZ = L / 4 < 32 ? L / 4 : 32, NB = L / BZ;  // rows / planes per box, boxes per tile
+    static_assert(EMODE != 1 || BZ == 32, "one word of tile flags per box");
+    __shared__ __align__(8) unsigned long long bar;
+    if (threadIdx.x == 0) {
+      mbar_init(&bar, 1);
+      fence_proxy_async();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      unsigned need = 0;
+#pragma unroll
+      for (int b = 0; b < NB; ++b) {
+        bool want = KIN == 1 ? (b * BZ < L / 4 || b * BZ >= 3 * L / 4)
+                             : (b * BZ < A.in.np || (b + 1) * BZ > L - A.in.nm);
+        if (EMODE == 1) want = want && ebits[b] != 0xffffffffu;
+        need |= want ? (1u << b) : 0u;
+      }
+      mbar_arrive_expect_tx(&bar, (unsigned)__popc(need) * (unsigned)(BZ * TX * sizeof(float2)));
+#pragma unroll
+      for (int b = 0; b < NB; ++b)
+        if ((need >> b) & 1u)
+          tma_load_4d(S + b * BZ * TX, &tmap, bx * TX, A.tma_z ? lo : b * BZ, A.tma_z ? b * BZ : lo, bt, &bar);
+    }
+    mbar_wait(&bar, 0);
+  }
   // step A: R1-point FFTs over n1 (n = n1 R2 + n2), twiddle W_L^(n2 k1)
   for (int item = threadIdx.x; item < R2 * TX; item += FT) {
     const int n2 = item / TX, tx = item % TX;
     float2 a[R1];
-    const float2* gin = g + (long long)n2 * A.stride_n + tx;
-    const long long sR2 = A.stride_n * R2;
+    const float2* gin = TMA ? S + n2 * TX + tx : g + (long long)n2 * A.stride_n + tx;
+    const long long sR2 = TMA ? (long long)TX * R2 : A.stride_n * R2;
     sfor<0, R1>([&](auto I) {
       constexpr int n1 = decltype(I)::value;
       constexpr bool static_zero = KIN == 1 && n1 >= R1 / 4 && n1 < 3 * R1 / 4;
@@ -647,16 +732,83 @@ int set_smem(K kern, size_t bytes) {
     }                                                                \
   } while (0)
 
+// tensor maps of the TMA variant, cached per plan: [0] boxes along dimension 1, [1] along dimension 2
+struct TmaMaps {
+  CUtensorMap map[2];
+  bool ok[2] = {false, false};
+  const void* base = nullptr;
+  int T = 0;
+};
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// The grid as a 4-D tensor (x, y, z, coil) of 8-byte elements; box = 16 columns x BZ rows (kind 0) or planes
+// (kind 1).  Returns nullptr when the driver has no encoder (the caller then takes the plain-load variant).
+const CUtensorMap* tma_map(b200_plan* p, float2* fw, int kind, int L) {
+  if (!p->tma) p->tma = new TmaMaps();
+  TmaMaps* tm = (TmaMaps*)p->tma;
+  if (tm->base != fw || tm->T != p->ntrans_max) {
+    tm->ok[0] = tm->ok[1] = false;
+    tm->base = fw;
+    tm->T = p->ntrans_max;
+  }
+  if (tm->ok[kind]) return &tm->map[kind];
+  static EncodeTiledFn encode = nullptr;
+  static bool looked = false;
+  if (!looked) {
+    looked = true;
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      encode = (EncodeTiledFn)fn;
+    else
+      cudaGetLastError();
+  }
+  if (!encode) return nullptr;
+  const Geom& g = p->g;
+  const cuuint64_t d0 = g.nf[g.dim - 1], d1 = g.nf[g.dim - 2], d2 = g.dim == 3 ? g.nf[0] : 1;
+  const cuuint64_t dims[4] = {d0, d1, d2, (cuuint64_t)p->ntrans_max};
+  const cuuint64_t strides[3] = {d0 * 8, d0 * d1 * 8, (cuuint64_t)g.nftot * 8};
+  const cuuint32_t bz = (cuuint32_t)(L / 4 < 32 ? L / 4 : 32);
+  const cuuint32_t box[4] = {(cuuint32_t)TX, kind == 0 ? bz : 1u, kind == 1 ? bz : 1u, 1u};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  const CUresult r = encode(&tm->map[kind], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, fw, dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                            CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return nullptr;
+  tm->ok[kind] = true;
+  return &tm->map[kind];
+}
+
 template <int L, int DIR, bool MUL, int EMODE, int KIN, int KOUT>
-int launch_strided_m(const StridedArgs& A, int ntx, int nouter, int T, const float2* tw, cudaStream_t st) {
-  auto kern = k_fft_strided<L, DIR, MUL, EMODE, KIN, KOUT>;
+int launch_strided_m(const StridedArgs& A, int ntx, int nouter, int T, const float2* tw, cudaStream_t st,
+                     const CUtensorMap* tmap) {
   const size_t smem = (size_t)L * TX * sizeof(float2);
+  const dim3 grid = MUL ? dim3(T, nouter, ntx) : dim3(ntx, nouter, T);
+  if constexpr (L >= 128 && !MUL) {
+    if (tmap) {
+      auto kern = k_fft_strided<L, DIR, MUL, EMODE, KIN, KOUT, true>;
+      static bool done = false;
+      if (!done) {
+        B200_TRY(set_smem(kern, smem));
+        done = true;
+      }
+      kern<<<grid, FT, smem, st>>>(A, tw, *tmap);
+      CHECK_LAUNCH();
+      return B200_OK;
+    }
+  }
+  auto kern = k_fft_strided<L, DIR, MUL, EMODE, KIN, KOUT, false>;
   static bool done = false;
   if (!done) {
     B200_TRY(set_smem(kern, smem));
     done = true;
   }
-  kern<<<MUL ? dim3(T, nouter, ntx) : dim3(ntx, nouter, T), FT, smem, st>>>(A, tw);
+  static const CUtensorMap none{};
+  kern<<<grid, FT, smem, st>>>(A, tw, none);
   CHECK_LAUNCH();
   return B200_OK;
 }
@@ -664,22 +816,23 @@ int launch_strided_m(const StridedArgs& A, int ntx, int nouter, int T, const flo
 // (32-column tiles -- 256-byte segments per grid row, 512 threads, one CTA per SM -- were measured at
 // cfg-C: 50.0 ms for the six passes against 42.4 ms with 16-column tiles; not kept.)
 template <int L, int DIR>
-int launch_strided(const StridedArgs& A, int ntx, int nouter, int T, const float2* tw, cudaStream_t st) {
+int launch_strided(const StridedArgs& A, int ntx, int nouter, int T, const float2* tw, cudaStream_t st,
+                   const CUtensorMap* tmap) {
   // sigma = 2 patterns: modes of an N = L / 2 image <-> Keep{L / 4, L / 4}; everything <-> Keep{L, 0}
   const bool in_half = A.in.np == L / 4 && A.in.nm == L / 4, in_all = A.in.np == L && A.in.nm == 0;
   const bool out_half = A.out.np == L / 4 && A.out.nm == L / 4, out_all = A.out.np == L && A.out.nm == 0;
-  if (A.mul) return launch_strided_m<L, DIR, true, 0, 0, 0>(A, ntx, nouter, T, tw, st);
+  if (A.mul) return launch_strided_m<L, DIR, true, 0, 0, 0>(A, ntx, nouter, T, tw, st, nullptr);
   if (in_half && out_all) {  // type 2
-    if (A.empty && A.empty_out) return launch_strided_m<L, DIR, false, 2, 1, 0>(A, ntx, nouter, T, tw, st);
-    if (!A.empty) return launch_strided_m<L, DIR, false, 0, 1, 0>(A, ntx, nouter, T, tw, st);
+    if (A.empty && A.empty_out) return launch_strided_m<L, DIR, false, 2, 1, 0>(A, ntx, nouter, T, tw, st, tmap);
+    if (!A.empty) return launch_strided_m<L, DIR, false, 0, 1, 0>(A, ntx, nouter, T, tw, st, tmap);
   }
   if (in_all && out_half) {  // type 1
-    if (A.empty && !A.empty_out) return launch_strided_m<L, DIR, false, 1, 0, 1>(A, ntx, nouter, T, tw, st);
-    if (!A.empty) return launch_strided_m<L, DIR, false, 0, 0, 1>(A, ntx, nouter, T, tw, st);
+    if (A.empty && !A.empty_out) return launch_strided_m<L, DIR, false, 1, 0, 1>(A, ntx, nouter, T, tw, st, tmap);
+    if (!A.empty) return launch_strided_m<L, DIR, false, 0, 0, 1>(A, ntx, nouter, T, tw, st, tmap);
   }
-  if (A.empty && A.empty_out) return launch_strided_m<L, DIR, false, 2, 0, 0>(A, ntx, nouter, T, tw, st);
-  if (A.empty) return launch_strided_m<L, DIR, false, 1, 0, 0>(A, ntx, nouter, T, tw, st);
-  return launch_strided_m<L, DIR, false, 0, 0, 0>(A, ntx, nouter, T, tw, st);
+  if (A.empty && A.empty_out) return launch_strided_m<L, DIR, false, 2, 0, 0>(A, ntx, nouter, T, tw, st, tmap);
+  if (A.empty) return launch_strided_m<L, DIR, false, 1, 0, 0>(A, ntx, nouter, T, tw, st, tmap);
+  return launch_strided_m<L, DIR, false, 0, 0, 0>(A, ntx, nouter, T, tw, st, tmap);
 }
 
 template <int L, int DIR, bool HALF>
@@ -767,13 +920,24 @@ int strided_pass(b200_plan* p, float2* fw, int T, int a, int dir, Keep in, Keep 
     nouter = 1;
   }
   const int L = g.nf[a];
-  DISPATCH_L(L, dir, return (launch_strided<LL, DD>(A, nfx / TX, nouter, T, p->d_tw[a], st)));
+  // option 2 = 3: bulk tensor loads (TMA) for the tiles of the strided passes; the tensor map describes the
+  // plan's own workspace, which is what every caller passes
+  const CUtensorMap* tmap = nullptr;
+  A.tma_z = (g.dim == 3 && a == 0) ? 1 : 0;
+  A.lookahead = p->fft_lookahead;
+  if (p->fft_method == 3 && L >= 128 && !mul && fw == p->d_fw) tmap = tma_map(p, fw, A.tma_z, L);
+  DISPATCH_L(L, dir, return (launch_strided<LL, DD>(A, nfx / TX, nouter, T, p->d_tw[a], st, tmap)));
   return B200_OK;
 }
 
 bool pow2_ok(int L) { return L >= 32 && L <= 1024 && (L & (L - 1)) == 0; }
 
 }  // namespace
+
+void fftp_free(b200_plan* p) {
+  if (p->tma) delete (TmaMaps*)p->tma;
+  p->tma = nullptr;
+}
 
 bool fftp_supported(const b200_plan* p) {
   const Geom& g = p->g;

@@ -479,6 +479,14 @@ template <int W, int DIM, int TC>
 __device__ __forceinline__ void rows_loop_interp(u64 (&acc)[NACC], unsigned pk, int n, const void* ktl, unsigned ob,
                                                  unsigned yo, unsigned zo);
 
+template <int N, int I = 0, class F>
+__device__ __forceinline__ void static_for(F&& f) {
+  if constexpr (I < N) {
+    f(std::integral_constant<int, I>());
+    static_for<N, I + 1>(f);
+  }
+}
+
 __device__ __forceinline__ u64 pack2(float lo, float hi) {
   return ((u64)__float_as_uint(hi) << 32) | (u64)__float_as_uint(lo);
 }
@@ -619,6 +627,7 @@ k_rows(Geom g, int T, int nchunks, unsigned S, long long M, const uint4* __restr
     // ---- the tile in the accumulators
     u64* gbase = nullptr;  // class 32, grid-side role of this lane: cell c8 of coil g4, row 0 of the tile
     u64* fbase = nullptr;  // class 32: ... in the spreader's flush: cell cl of coil hl; class < 32: cell cl, coil 0
+    u64* fb_hl = nullptr;  // class < 32: fbase + this half-warp's share of a transposed access (coil hl; one coil: row group hl)
     int xlim = 0;          // cells of this tile inside the grid (16, less for a short last tile)
     unsigned gmask = 0;      // class < 32: row groups of this tile that lie inside the grid
     int ylim = 0, zlim = 0;  // class < 32: rows / planes of this tile inside the grid
@@ -642,6 +651,7 @@ k_rows(Geom g, int T, int nchunks, unsigned S, long long M, const uint4* __restr
         if (SPREAD) fbase = fw64 + ((long long)z * nfy + y) * nfx + bx * CX + cl + (long long)hl * g.nftot;
       } else {
         fbase = fw64 + ((long long)z * nfy + y) * nfx + bx * CX + cl;
+        fb_hl = fbase + (TC >= 2 ? (long long)hl * g.nftot : (long long)hl * 2 * nfx);
         ylim = nfy - y;
         zlim = nz - z;
         ucol = (y >> 1) * nbx + bx;
@@ -702,17 +712,21 @@ k_rows(Geom g, int T, int nchunks, unsigned S, long long M, const uint4* __restr
           }
           __syncwarp();
           if (cl < xlim) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const int L = 2 * i + hl;  // source lane: coil L % TC of row group L / TC
-              const int t = L & (TC - 1), gg = L / TC, yy = 2 * (gg % C::GY), zz = gg / C::GY;
+            static_for<16>([&](auto I) {
+              constexpr int i = decltype(I)::value;
+              // source lane L = 2 i + hl: coil L % TC of row group L / TC.  Everything but the hl term is a
+              // compile-time or warp-uniform quantity (fb_hl carries the hl term, see tile_setup)
+              const int L = 2 * i + hl;
+              constexpr int T0 = TC >= 2 ? ((2 * i) & (TC - 1)) : 0, G0 = TC >= 2 ? (2 * i) / TC : 2 * i;
+              constexpr int Y0 = 2 * (G0 % C::GY), Z0 = G0 / C::GY;
+              const int t = T0 + (TC >= 2 ? hl : 0), gg = G0 + (TC >= 2 ? 0 : hl);
               if (t < T && ((gmask >> gg) & 1u)) {
                 const u64 val = lds64(tc_a + (unsigned)(L * TCS + cl * 8));
-                u64* a = fbase + (long long)t * g.nftot + ((long long)zz * nfy + yy + r) * nfx;
+                u64* a = fb_hl + ((long long)T0 * g.nftot + ((long long)Z0 * nfy + Y0 + r) * nfx);
                 if (!shared) __stcs(a, val);
                 else red_add_f32x2(reinterpret_cast<float2*>(a), val, 1);
               }
-            }
+            });
           }
           __syncwarp();
         }
@@ -780,16 +794,18 @@ k_rows(Geom g, int T, int nchunks, unsigned S, long long M, const uint4* __restr
         // keeps the halves where they landed and pays two moves per FFMA2 operand in the visit loops.
 #pragma unroll
         for (int r = 0; r < 2; ++r) {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
+          static_for<16>([&](auto I) {
+            constexpr int i = decltype(I)::value;
             const int L = 2 * i + hl;
-            const int t = L & (TC - 1), gg = L / TC, yy = 2 * (gg % C::GY), zz = gg / C::GY;
+            constexpr int T0 = TC >= 2 ? ((2 * i) & (TC - 1)) : 0, G0 = TC >= 2 ? (2 * i) / TC : 2 * i;
+            constexpr int Y0 = 2 * (G0 % C::GY), Z0 = G0 / C::GY;
+            const int t = T0 + (TC >= 2 ? hl : 0), gg = G0 + (TC >= 2 ? 0 : hl);
             const bool ok = cl < xlim && t < T && ((um >> gg) & 1u);
-            const u64* src = ok ? fbase + (long long)t * g.nftot + ((long long)zz * nfy + yy + r) * nfx : fw64;
+            const u64* src = ok ? fb_hl + ((long long)T0 * g.nftot + ((long long)Z0 * nfy + Y0 + r) * nfx) : fw64;
             const unsigned dst = tc_a + (unsigned)((L * TFS + cl) * 4);
             cp_async4_zfill(dst, src, ok ? 4 : 0);
             cp_async4_zfill(dst + 32u * TFS * 4u, reinterpret_cast<const char*>(src) + 4, ok ? 4 : 0);
-          }
+          });
           cp_async_commit();
           cp_async_wait<0>();
           __syncwarp();

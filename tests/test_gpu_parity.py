@@ -600,15 +600,66 @@ def test_large_sampled_ndft_and_linearity(mods, shape, M, C):
     assert abs(lhs - rhs) / abs(rhs) < 5e-6
 
 
+def _ndft_type2_at(torch, samples_d, img64, idx):
+    """Exact type-2 NDFT (float64, on the device, nothing of ours involved) of the images `img64` (C, *shape) at
+    the sample locations `idx`: y[c, j] = sum_n img[c, n] exp(-i k_j . (n - N/2)).  One phase vector per
+    location, shared by all coils."""
+    shape = img64.shape[1:]
+    axes = [torch.arange(n, device=img64.device, dtype=torch.float64) - n // 2 for n in shape]
+    out = torch.empty((img64.shape[0], len(idx)), dtype=torch.complex128, device=img64.device)
+    flat = img64.reshape(img64.shape[0], -1)
+    for j, i in enumerate(idx):
+        k = samples_d[int(i)].to(torch.float64)
+        ph = torch.polar(torch.ones_like(axes[0]), -k[0] * axes[0])
+        for a in range(1, len(shape)):
+            ph = (ph[..., None] * torch.polar(torch.ones_like(axes[a]), -k[a] * axes[a])).reshape(-1)
+        out[:, j] = flat @ ph.reshape(-1)
+    return out
+
+
+def _ndft_type1_at(torch, samples_d, ksp64, shape, vox):
+    """Exact type-1 NDFT (float64, on the device) of the k-space rows `ksp64` (C, M) at the voxels `vox`:
+    f[c, v] = sum_j ksp[c, j] exp(+i k_j . (n_v - N/2))."""
+    s64 = samples_d.to(torch.float64)
+    out = torch.empty((ksp64.shape[0], len(vox)), dtype=torch.complex128, device=ksp64.device)
+    for v, n in enumerate(vox):
+        r = torch.tensor([int(n[a]) - shape[a] // 2 for a in range(len(shape))], dtype=torch.float64, device=s64.device)
+        ph = torch.polar(torch.ones(s64.shape[0], dtype=torch.float64, device=s64.device), s64 @ r)
+        out[:, v] = ksp64 @ ph
+    return out
+
+
+def test_device_ndft_helpers_agree_with_the_cpu_oracle(mods):
+    """The float64 torch evaluations of the exact NDFT used at full size, pinned to the numpy oracle."""
+    from oracle import es_nufft as E
+
+    _, _, torch = mods
+    rng = np.random.default_rng(2)
+    shape, M = (12, 10, 14), 300
+    samples = rng.uniform(-np.pi, np.pi, (M, 3)).astype(np.float32)
+    img = rng.standard_normal((2, *shape)) + 1j * rng.standard_normal((2, *shape))
+    ksp = rng.standard_normal((2, M)) + 1j * rng.standard_normal((2, M))
+    idx = np.array([0, 7, 299])
+    vox = np.array([[0, 0, 0], [6, 5, 7], [11, 9, 13]])
+    sd = torch.from_numpy(samples).cuda()
+    y = _ndft_type2_at(torch, sd, torch.from_numpy(img).cuda(), idx).cpu().numpy()
+    x = _ndft_type1_at(torch, sd, torch.from_numpy(ksp).cuda(), shape, vox).cpu().numpy()
+    for c in range(2):
+        assert rel_l2(y[c], E.ndft_type2_sampled(samples, img[c], idx)) < 1e-12
+        assert rel_l2(x[c], E.ndft_type1_sampled(samples, ksp[c], shape, vox)) < 1e-12
+
+
 def test_baseline_config_at_its_full_size(mods):
     """BASELINE.json configs[2] exactly -- 3-D 256^3, 32 coils with smaps, M = 2^23 phyllotaxis-radial samples,
-    complex64 -- through properties that do not need a full-size reference: the exact NDFT at sampled k-space
-    locations, linearity, adjointness (which ties `adj_op` to the checked `op`), and the sort's invariants."""
+    complex64 -- against the exact NDFT (float64) at sampled locations, at the bar of this file (5e-6):
+    `op` at 64 k-space locations for ALL 32 coils, among them samples of the k = 0 crowd (16 384 coincident
+    points, whose tiles the spreader / interpolator split over many chunks and merge with atomics); `adj_op`
+    with density weights at 24 voxels (every voxel sums all 2^23 samples of all coils);
+    `data_consistency` == adj_op(op(x) - y); linearity, adjointness, and the invariants of the sort."""
     mrinufft, _, torch = mods
     if torch.cuda.mem_get_info()[0] < 80e9:
         pytest.skip("needs about 70 GB of device memory")
     from mrinufft.trajectories import initialize_3D_phyllotaxis_radial
-    from oracle import es_nufft as E
 
     shape, C, M = (256, 256, 256), 32, 1 << 23
     traj = initialize_3D_phyllotaxis_radial(16384, 512).astype(np.float32).reshape(-1, 3)
@@ -619,27 +670,50 @@ def test_baseline_config_at_its_full_size(mods):
 
     smaps = crandn(C, *shape)
     smaps /= torch.linalg.norm(smaps, dim=0, keepdim=True)
-    op = mrinufft.get_operator("b200")(traj, shape, n_coils=C, smaps=smaps, squeeze_dims=False)
+    dens = torch.rand(M, device="cuda", generator=gen) + 0.5
+    op = mrinufft.get_operator("b200")(traj, shape, n_coils=C, smaps=smaps, squeeze_dims=False, density=dens)
     assert op.n_samples == M and len(op._chunks()) == 1          # one library call for all 32 coils
+    assert op.raw_op.plan.rows_class(C)["class"] == 32
     img, img2, ksp = crandn(1, 1, *shape), crandn(1, 1, *shape), crandn(1, C, M)
+    samples_d = torch.from_numpy(op.samples).cuda()
     y = op.op(img)
-    # exact NDFT at 16 sampled locations, first and last coil (tolerance: the NDFT bar of this file)
+    # ---- type 2 against the exact NDFT: 64 locations, all coils
     rng = np.random.default_rng(0)
-    idx = np.sort(rng.choice(M, 16, replace=False))
-    img_h = img[0, 0].cpu().numpy().astype(np.complex128)
-    for c in (0, C - 1):
-        ref = E.ndft_type2_sampled(op.samples, img_h * smaps[c].cpu().numpy(), idx) / op.norm_factor
-        assert rel_l2(y[0, c, idx].cpu().numpy(), ref) <= 2 * TOL_NDFT
-    # linearity
+    centre = np.flatnonzero(np.linalg.norm(op.samples, axis=1) < 1e-6)
+    assert len(centre) >= 1000                                     # the k = 0 crowd of the radial trajectory
+    idx = np.sort(np.concatenate([rng.choice(centre, 8, replace=False), rng.choice(M, 56, replace=False)]))
+    coil_imgs = (img[0].to(torch.complex128) * smaps.to(torch.complex128))
+    ref = _ndft_type2_at(torch, samples_d, coil_imgs, idx) / op.norm_factor
+    del coil_imgs
+    got = y[0][:, torch.from_numpy(idx).cuda()].to(torch.complex128)
+    for c in range(C):
+        assert float(torch.linalg.norm(got[c] - ref[c]) / torch.linalg.norm(ref[c])) <= TOL_NDFT, c
+    # ---- type 1 (density weighted, SENSE combined) against the exact NDFT: 24 voxels
+    x = op.adj_op(ksp)
+    vox = np.stack([rng.integers(0, s, 24) for s in shape], -1)
+    vox[0], vox[1], vox[2] = (128, 128, 128), (0, 0, 0), (255, 255, 255)
+    f = _ndft_type1_at(torch, samples_d, ksp[0].to(torch.complex128) * dens.to(torch.float64), shape, vox)
+    vi = tuple(torch.from_numpy(vox[:, a]).cuda() for a in range(3))
+    ref1 = torch.sum(torch.conj(smaps.to(torch.complex128)[(slice(None), *vi)]) * f, dim=0) / op.norm_factor
+    got1 = x[0, 0][vi].to(torch.complex128)
+    assert float(torch.linalg.norm(got1 - ref1) / torch.linalg.norm(ref1)) <= TOL_NDFT
+    del f
+    # ---- data consistency: the fused call equals its definition
+    dc = op.data_consistency(img, ksp)
+    dc -= op.adj_op(y - ksp)
+    assert float(torch.linalg.norm(dc) / torch.linalg.norm(x)) < 2e-6
+    del dc
+    # ---- linearity
     y12 = op.op(img + 2j * img2)
     y12 -= y + 2j * op.op(img2)
     assert float(torch.linalg.norm(y12) / torch.linalg.norm(y)) < 3e-6
     del y12
-    # adjointness, inner products in float64 on the device
+    # ---- adjointness (density off), inner products in float64 on the device
+    op.density = None
     x = op.adj_op(ksp)
     lhs = torch.sum(torch.conj(y.to(torch.complex128)) * ksp.to(torch.complex128))
     rhs = torch.sum(torch.conj(img.to(torch.complex128)) * x.to(torch.complex128))
-    assert float(torch.abs(lhs - rhs) / torch.abs(rhs)) < 1e-5
+    assert float(torch.abs(lhs - rhs) / torch.abs(rhs)) < 5e-6
     # the sort (perm = stable argsort of the bin keys): keys ascending along perm, ties in caller order,
     # permutation complete
     _, _, key, perm = op.raw_op.sort_indices()
@@ -647,6 +721,123 @@ def test_baseline_config_at_its_full_size(mods):
     assert np.all(steps >= 0)
     assert np.all(np.diff(perm.astype(np.int64))[steps == 0] > 0)
     assert np.array_equal(np.sort(perm), np.arange(M, dtype=perm.dtype))
+
+
+@pytest.mark.parametrize("C", [16, 4])
+def test_strong_scaling_shards_of_the_baseline_config_at_full_size(mods, C):
+    """What one rank of a 2- / 8-GPU run of BASELINE configs[2] executes: the 256^3 / M = 2^23 transforms with
+    16 and 4 coils, i.e. coil classes 16 and 4 of the row kernels, against the exact NDFT at sampled locations
+    (all coils) and through adjointness."""
+    mrinufft, _, torch = mods
+    if torch.cuda.mem_get_info()[0] < 60e9:
+        pytest.skip("needs about 40 GB of device memory")
+    from mrinufft.trajectories import initialize_3D_phyllotaxis_radial
+
+    shape, M = (256, 256, 256), 1 << 23
+    traj = initialize_3D_phyllotaxis_radial(16384, 512).astype(np.float32).reshape(-1, 3)
+    gen = torch.Generator(device="cuda").manual_seed(C)
+
+    def crandn(*s):
+        return torch.view_as_complex(torch.randn(*s, 2, device="cuda", generator=gen))
+
+    smaps = crandn(C, *shape)
+    smaps /= torch.linalg.norm(smaps, dim=0, keepdim=True)
+    op = mrinufft.get_operator("b200")(traj, shape, n_coils=C, smaps=smaps, squeeze_dims=False)
+    assert op.raw_op.plan.rows_class(C)["class"] == C
+    img, ksp = crandn(1, 1, *shape), crandn(1, C, M)
+    samples_d = torch.from_numpy(op.samples).cuda()
+    rng = np.random.default_rng(C)
+    centre = np.flatnonzero(np.linalg.norm(op.samples, axis=1) < 1e-6)
+    idx = np.sort(np.concatenate([rng.choice(centre, 4, replace=False), rng.choice(M, 28, replace=False)]))
+    y = op.op(img)
+    ref = _ndft_type2_at(torch, samples_d, img[0].to(torch.complex128) * smaps.to(torch.complex128), idx) / op.norm_factor
+    got = y[0][:, torch.from_numpy(idx).cuda()].to(torch.complex128)
+    for c in range(C):
+        assert float(torch.linalg.norm(got[c] - ref[c]) / torch.linalg.norm(ref[c])) <= TOL_NDFT, c
+    x = op.adj_op(ksp)
+    vox = np.stack([rng.integers(0, s, 12) for s in shape], -1)
+    f = _ndft_type1_at(torch, samples_d, ksp[0].to(torch.complex128), shape, vox)
+    vi = tuple(torch.from_numpy(vox[:, a]).cuda() for a in range(3))
+    ref1 = torch.sum(torch.conj(smaps.to(torch.complex128)[(slice(None), *vi)]) * f, dim=0) / op.norm_factor
+    got1 = x[0, 0][vi].to(torch.complex128)
+    assert float(torch.linalg.norm(got1 - ref1) / torch.linalg.norm(ref1)) <= TOL_NDFT
+    lhs = torch.sum(torch.conj(y.to(torch.complex128)) * ksp.to(torch.complex128))
+    rhs = torch.sum(torch.conj(img.to(torch.complex128)) * x.to(torch.complex128))
+    assert float(torch.abs(lhs - rhs) / torch.abs(rhs)) < 5e-6
+
+
+def test_secondary_baseline_configs_at_their_sizes(mods):
+    """BASELINE configs[0] (README demo: 2-D radial 100 x 500, 512^2, one coil, density="voronoi" through the
+    constructor) and configs[1] (2-D spiral 64 x 2048, 320^2, 32 coils with smaps) at their stated sizes against
+    the exact NDFT at sampled locations."""
+    mrinufft, _, torch = mods
+    from mrinufft.trajectories import initialize_2D_radial, initialize_2D_spiral
+
+    rng = np.random.default_rng(5)
+    for name, traj, shape, C, kw in [
+        ("A", initialize_2D_radial(100, 500), (512, 512), 1, {"density": "voronoi"}),
+        ("B", initialize_2D_spiral(64, 2048, nb_revolutions=8), (320, 320), 32, {}),
+    ]:
+        traj = traj.astype(np.float32).reshape(-1, 2)
+        smaps = None
+        if C > 1:
+            smaps = (rng.standard_normal((C, *shape)) + 1j * rng.standard_normal((C, *shape))).astype(np.complex64)
+            smaps /= np.linalg.norm(smaps, axis=0)
+        op = mrinufft.get_operator("b200")(traj, shape, n_coils=C, smaps=smaps, squeeze_dims=False, **kw)
+        M = op.n_samples
+        if name == "A":
+            assert op.uses_density and op.density.shape == (M,)
+        img = (rng.standard_normal((1, 1, *shape)) + 1j * rng.standard_normal((1, 1, *shape))).astype(np.complex64)
+        ksp = (rng.standard_normal((1, C, M)) + 1j * rng.standard_normal((1, C, M))).astype(np.complex64)
+        sd = torch.from_numpy(op.samples).cuda()
+        idx = np.sort(rng.choice(M, 48, replace=False))
+        sm = torch.ones((1, *shape), dtype=torch.complex128, device="cuda") if smaps is None else \
+            torch.from_numpy(smaps).cuda().to(torch.complex128)
+        ref = (_ndft_type2_at(torch, sd, torch.from_numpy(img[0]).cuda().to(torch.complex128) * sm, idx)
+               / op.norm_factor).cpu().numpy()
+        y = op.op(img)
+        for c in range(C):
+            assert rel_l2(y[0, c, idx], ref[c]) <= TOL_NDFT, (name, c)
+        x = op.adj_op(ksp)
+        vox = np.stack([rng.integers(0, s, 16) for s in shape], -1)
+        k64 = torch.from_numpy(ksp[0]).cuda().to(torch.complex128)
+        if op.uses_density:
+            k64 = k64 * torch.from_numpy(np.asarray(op.density)).cuda().to(torch.float64)
+        f = _ndft_type1_at(torch, sd, k64, shape, vox)
+        vi = tuple(torch.from_numpy(vox[:, a]).cuda() for a in range(2))
+        ref1 = (torch.sum(torch.conj(sm[(slice(None), *vi)]) * f, dim=0) / op.norm_factor).cpu().numpy()
+        assert rel_l2(x[0, 0][tuple(vox.T)], ref1) <= TOL_NDFT, name
+
+
+def test_pipe_density_3d_at_128_matches_the_oracle_on_sampled_points(mods):
+    """3-D Pipe density at 128^3 (M = 2^19 radial samples): ten spread / interp-only iterations on the device
+    (single-coil calls: coil class 1 of the row kernels) against the C oracle's spread / interp, compared on
+    the whole weight vector (the iteration is global: every weight depends on all the others)."""
+    from oracle import es_nufft as E
+    from oracle.c_oracle import CpuNufft, fold
+
+    mrinufft, _, _ = mods
+    from mrinufft.trajectories import initialize_3D_phyllotaxis_radial
+
+    shape = (128, 128, 128)
+    traj = initialize_3D_phyllotaxis_radial(2048, 256).astype(np.float32).reshape(-1, 3)
+    d = mrinufft.get_operator("b200").pipe(traj, shape, max_iter=10, osf=2, normalize=False)
+    samples = (traj * 2 * np.pi).astype(np.float32)
+    cpu = CpuNufft(samples, (8, 8, 8), precision="f64")   # (tables only: the grid is replaced below)
+    cpu.nfs = shape
+    cpu.nf_arr = np.asarray(shape, np.int32)
+    cpu.origin = np.empty((3, len(samples)), np.int32)
+    cpu.x1 = np.empty((3, len(samples)), np.float32)
+    for a in range(3):
+        cpu.origin[a], cpu.x1[a] = fold(samples[:, a], shape[a], cpu.w)
+    cpu.perm = np.argsort(E.make_key(cpu.origin, shape, E.default_bins(3), cpu.w), kind="stable").astype(np.int32)
+    dd = np.ones(len(samples))
+    norm2 = np.prod(shape) * 8.0
+    for _ in range(10):
+        dd = dd / np.abs(cpu.interp(cpu.spread(dd.astype(np.complex128)))[0]) * norm2
+    assert np.all(np.isfinite(d)) and rel_l2(d, dd) < 5e-5
+    idx = np.random.default_rng(0).choice(len(d), 64, replace=False)
+    assert np.allclose(d[idx], dd[idx], rtol=2e-4)
 
 
 def test_empty_and_tiny_inputs(mods):
@@ -754,6 +945,37 @@ def test_pruned_fft_matches_cufft_path_and_oracle(mods, shape, C, sense):
         x_o = cpu.adj_op(ksp[0], smaps)
         assert rel_l2(res[2][0][0], y_o) <= 2e-6
         assert rel_l2(res[2][1][0, 0] if sense else res[2][1][0], x_o) <= 2e-6
+
+
+@pytest.mark.parametrize("shape,C", [((64, 64, 64), 3), ((256, 64, 128), 2), ((128, 128), 4), ((64, 256, 64), 1)])
+def test_tma_variant_of_the_fft_passes_equals_the_plain_loads(mods, shape, C):
+    """Option 2 = 3: the strided FFT passes bring their tiles in with cp.async.bulk.tensor + mbarrier instead of
+    per-thread global loads (boxes of zero padding / untouched tiles are not issued).  Same arithmetic in the
+    same order: results must agree with option 2 = 2 to rounding of the spreader's / interpolator's atomics
+    (tiles cut by chunk boundaries), for op, adj_op (incl. the spreader's untouched tiles: samples confined to
+    a ball) and the opposite sign."""
+    mrinufft, _, _ = mods
+    rng = np.random.default_rng(13)
+    d, M = len(shape), 30_000
+    v = rng.standard_normal((M, d))
+    v *= (rng.uniform(0, 1, (M, 1)) ** (1 / d)) * 2.0 / np.linalg.norm(v, axis=1, keepdims=True)
+    samples = v.astype(np.float32)
+    smaps = (rng.standard_normal((C, *shape)) + 1j * rng.standard_normal((C, *shape))).astype(np.complex64)
+    smaps /= np.linalg.norm(smaps, axis=0)
+    op = mrinufft.get_operator("b200")(samples, shape, n_coils=C, smaps=smaps, squeeze_dims=False)
+    plan = op.raw_op.plan
+    plan.set_option(4, 32)  # whole tiles are written without atomics: bit-reproducible spreading
+    img = (rng.standard_normal(op.img_full_shape) + 1j * rng.standard_normal(op.img_full_shape)).astype(np.complex64)
+    ksp = (rng.standard_normal(op.ksp_full_shape) + 1j * rng.standard_normal(op.ksp_full_shape)).astype(np.complex64)
+    res = {}
+    for method in (2, 3):
+        plan.set_option(2, method)
+        res[method] = [op.adj_op(ksp)]
+        with op.grad_traj_plan():
+            res[method].append(op.adj_op(ksp))
+        res[method].append(op.op(img))
+    for a, b in zip(res[2], res[3]):
+        assert np.all(np.isfinite(b)) and rel_l2(b, a) < 1e-6
 
 
 @pytest.mark.gpu

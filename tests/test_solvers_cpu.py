@@ -199,3 +199,56 @@ def test_committed_solver_goldens_are_what_the_reference_produces(tmp_path):
                     assert np.allclose(a[k], b[k], rtol=1e-4, atol=1e-6), (name, k)
                 else:
                     assert np.allclose(a[k], b[k], rtol=1e-6, atol=1e-8), (name, k)
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+def test_reference_cg_leaves_a_density_compensated_start_and_diverges_and_so_does_ours(dim):
+    """BASELINE configs[3] combines density="pipe" with pinv_solver(optim="cg").  The reference's `cg`
+    (extras/optim.py:839-862) takes its step size from the density-WEIGHTED operator and then iterates on the
+    un-weighted one.  Pipe's weights are normalised so that the weighted operator has a Lipschitz constant of a
+    few units, while the un-weighted operator of a radial trajectory (dense centre) has one that is many times
+    larger: the fixed step overshoots and the iteration diverges from the good density-compensated start it was
+    given -- on the reference's own exact NDFT, with the reference's own solver.  Ours mirrors the reference
+    statement by statement, so it follows the same path; handing `cg` the Lipschitz constant of the operator it
+    iterates on (`lipschitz_cst=`, an argument the reference does not have) gives the monotone reconstruction
+    that tools/bench_configs.py reports for that configuration."""
+    from mrinufft.density import voronoi
+    from mrinufft.trajectories import initialize_2D_radial, initialize_3D_phyllotaxis_radial
+
+    if dim == 3:
+        shape, traj = (12, 12, 12), initialize_3D_phyllotaxis_radial(96, 24).reshape(-1, 3).astype(np.float32)
+    else:
+        shape, traj = (32, 32), initialize_2D_radial(48, 64).reshape(-1, 2).astype(np.float32)
+    # weights on Pipe's scale: mean |A^H D A 1| = 1 (finufft.py:236-244)
+    dens = voronoi(traj, shape).astype(np.float32)
+    plain = ndft_full(traj, shape, n_coils=1, squeeze_dims=False)
+    dens /= np.mean(np.abs(plain.adj_op(plain.op(np.ones((1, 1, *shape), np.complex64)) * dens)))
+    grid = np.meshgrid(*[np.linspace(-1, 1, s) for s in shape], indexing="ij")
+    r2 = sum(g ** 2 for g in grid)
+    x_true = (np.exp(-3 * r2) + 0.5 * (r2 < 0.3)).astype(np.complex64).reshape(1, 1, *shape)
+    op = ndft_full(traj, shape, n_coils=1, density=dens, squeeze_dims=False)
+    y = op.op(x_true).astype(np.complex64)
+
+    def nrmse(x):
+        return float(np.linalg.norm(np.ravel(x) - x_true.ravel()) / np.linalg.norm(x_true))
+
+    np.random.seed(0)
+    lip_w = float(op.get_lipschitz_cst())
+    np.random.seed(0)
+    lip_u = float(plain.get_lipschitz_cst())
+    assert lip_u > 4 * lip_w                                  # the step 1 / lip_w is far too long
+    np.random.seed(0)
+    _, it_ref = ref_cg(op, y.copy(), max_iter=6, callback=_iterates, progressbar=False)
+    op.density = dens
+    err_ref = [nrmse(x) for x in it_ref]
+    assert err_ref[-1] > 10 * err_ref[0] or not np.isfinite(err_ref[-1])   # the reference diverges
+    np.random.seed(0)
+    _, it = solvers.cg(TorchFacade(op), y.copy(), max_iter=6, callback=_iterates)
+    op.density = dens
+    _close(it[:3], it_ref[:3], 1e-3)                          # ... and ours walks the same path
+    assert [nrmse(x) for x in it][-1] > 10 * err_ref[0] or not np.isfinite(nrmse(it[-1]))
+    # step size of the operator that is iterated on: monotone, better than the start
+    np.random.seed(0)
+    _, it_ok = solvers.cg(TorchFacade(op), y.copy(), max_iter=10, callback=_iterates, lipschitz_cst=lip_u)
+    err_ok = [nrmse(x) for x in it_ok]
+    assert all(b <= a * (1 + 1e-6) for a, b in zip(err_ok, err_ok[1:])) and err_ok[-1] < err_ok[0]
