@@ -35,9 +35,9 @@ for _p in (ROOT, ROOT / "baseline" / "_ref"):
 
 METRIC = "3D 32-coil NUFFT op+adj_op throughput"
 # DRAM bytes (read + write) of one launch of the row kernels at cfg-C, `ncu --set full`:
-# profiles/r01_k_rows_stream_full.txt
+# profiles/r02_rows_class32_full.txt
 FP32_PEAK_TFMA = 36.8  # measured: profiles/r01_ffma2_rate.jsonl (fp32_fma_per_s of FFMA2)
-NCU_TRAFFIC_GB = {"spread": 39.7, "interp": 42.5}
+NCU_TRAFFIC_GB = {"spread": 40.0, "interp": 42.5}  # profiles/r02_rows_class32_full.txt
 UNIT = "k-samples/s"
 
 

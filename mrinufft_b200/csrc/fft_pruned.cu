@@ -311,7 +311,9 @@ __device__ __forceinline__ RowInfo row_info(const RowArgs& A, int r) {
   return ri;
 }
 
-// type 2 x-pass: image row -> grid row.  grid (ceil(nrows / TX), 1, T)
+// type 2 x-pass: image row -> grid row.  grid (ceil(nrows / TX) * T): the coil index varies fastest, so that
+// the T CTAs that expand the same 16 image rows run together and share them through L2 (with the coil as the
+// slowest grid index the 134 MB image of cfg-C was re-read from HBM once per coil: 4.2 of 17 GB)
 // HALF: Nx == L / 2 (sigma = 2, Nx even): the non-zero inputs of a thread are its first and last
 // R1 / 4 points, at offsets known at compile time -- no per-element index arithmetic or predicates
 // (the generic path spends 70 % of its instructions there, ncu).
@@ -321,12 +323,12 @@ k_fft_rows_t2(RowArgs A, int nrows, const float2* __restrict__ tw) {
   constexpr int R1 = Split<L>::R1, R2 = Split<L>::R2, RS = R1 * (R2 + 1);
   extern __shared__ float2 S[];  // [TX][R1][R2 + 1]
   const int Nx = A.g.N[A.g.dim - 1];
-  const int t = blockIdx.z;
+  const int t = blockIdx.x % A.T, tile = blockIdx.x / A.T;
   const float2* img = A.smaps ? A.img_in : A.img_in + (long long)t * A.g.Ntot;
   const float2* sm = A.smaps ? A.smaps + (long long)t * A.g.Ntot : nullptr;
   for (int item = threadIdx.x; item < R2 * TX; item += FT) {
     const int row = item / R2, n2 = item % R2;
-    const int r = blockIdx.x * TX + row;
+    const int r = tile * TX + row;
     float2 a[R1];
     if (HALF && r < nrows) {
       const RowInfo ri = row_info(A, r);
@@ -426,7 +428,7 @@ k_fft_rows_t2(RowArgs A, int nrows, const float2* __restrict__ tw) {
   __syncthreads();
   for (int item = threadIdx.x; item < R1 * TX; item += FT) {
     const int row = item / R1, k1 = item % R1;
-    const int r = blockIdx.x * TX + row;
+    const int r = tile * TX + row;
     if (r >= nrows) continue;
     float2 b[R2];
     sfor<0, R2>([&](auto I) {
@@ -844,7 +846,7 @@ int launch_rows_t2_h(const RowArgs& A, int nrows, const float2* tw, cudaStream_t
     B200_TRY(set_smem(kern, smem));
     done = true;
   }
-  kern<<<dim3(ceil_div(nrows, TX), 1, A.T), FT, smem, st>>>(A, nrows, tw);
+  kern<<<dim3((unsigned)ceil_div(nrows, TX) * (unsigned)A.T, 1, 1), FT, smem, st>>>(A, nrows, tw);
   CHECK_LAUNCH();
   return B200_OK;
 }
@@ -925,7 +927,11 @@ int strided_pass(b200_plan* p, float2* fw, int T, int a, int dir, Keep in, Keep 
   const CUtensorMap* tmap = nullptr;
   A.tma_z = (g.dim == 3 && a == 0) ? 1 : 0;
   A.lookahead = p->fft_lookahead;
-  if (p->fft_method == 3 && L >= 128 && !mul && fw == p->d_fw) tmap = tma_map(p, fw, A.tma_z, L);
+  // (default: the passes whose tile lies inside one plane -- 3-D y-pass, 2-D pass -- take the bulk loads:
+  // 4.38 -> 4.13 ms and 4.47 -> 3.85 ms at 512^3 x 32 coils under ncu; the z-passes, 512 rows 2 MB apart,
+  // are unchanged by them: profiles/r02_fft_passes_full.txt)
+  const bool want_tma = p->fft_method == 3 || (p->fft_method == 0 && !A.tma_z);
+  if (want_tma && L >= 128 && !mul && fw == p->d_fw) tmap = tma_map(p, fw, A.tma_z, L);
   DISPATCH_L(L, dir, return (launch_strided<LL, DD>(A, nfx / TX, nouter, T, p->d_tw[a], st, tmap)));
   return B200_OK;
 }
