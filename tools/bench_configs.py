@@ -85,7 +85,7 @@ def smooth_phantom(n, dev):
     for (cz, cy, cx, rz, ry, rx, amp) in [(0, 0, 0, .8, .7, .6, 1.0), (.1, -.2, .15, .35, .3, .25, -.4),
                                           (-.25, .2, -.2, .2, .25, .15, .6), (.3, .3, .1, .12, .1, .15, .8)]:
         r = torch.sqrt(((z - cz) / rz) ** 2 + ((y - cy) / ry) ** 2 + ((x - cx) / rx) ** 2)
-        vol += amp * torch.sigmoid((1 - r) * 8)
+        vol += amp * torch.sigmoid((1 - r) * 5)
     phase = 0.6 * torch.sin(2.0 * x + 1.0) * torch.cos(1.5 * y) + 0.3 * z
     return (vol * torch.exp(1j * phase)).to(torch.complex64)
 
