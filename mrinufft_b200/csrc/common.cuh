@@ -190,3 +190,17 @@ int dbl_data_consistency(b200_plan* p, const void* img, const void* smaps, const
                          cudaStream_t st);
 
 static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// Function attributes (dynamic shared-memory limit) are per device: a launcher sets them on the first launch
+// on every device of the process, not once per process.
+struct PerDeviceOnce {
+  bool done[64] = {};
+  bool first() {
+    int d = 0;
+    cudaGetDevice(&d);
+    d &= 63;
+    const bool f = !done[d];
+    done[d] = true;
+    return f;
+  }
+};

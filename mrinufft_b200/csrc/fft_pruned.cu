@@ -793,22 +793,16 @@ int launch_strided_m(const StridedArgs& A, int ntx, int nouter, int T, const flo
   if constexpr (L >= 128 && !MUL) {
     if (tmap) {
       auto kern = k_fft_strided<L, DIR, MUL, EMODE, KIN, KOUT, true>;
-      static bool done = false;
-      if (!done) {
-        B200_TRY(set_smem(kern, smem));
-        done = true;
-      }
+      static PerDeviceOnce once;
+      if (once.first()) B200_TRY(set_smem(kern, smem));
       kern<<<grid, FT, smem, st>>>(A, tw, *tmap);
       CHECK_LAUNCH();
       return B200_OK;
     }
   }
   auto kern = k_fft_strided<L, DIR, MUL, EMODE, KIN, KOUT, false>;
-  static bool done = false;
-  if (!done) {
-    B200_TRY(set_smem(kern, smem));
-    done = true;
-  }
+  static PerDeviceOnce once;
+  if (once.first()) B200_TRY(set_smem(kern, smem));
   static const CUtensorMap none{};
   kern<<<grid, FT, smem, st>>>(A, tw, none);
   CHECK_LAUNCH();
@@ -841,11 +835,8 @@ template <int L, int DIR, bool HALF>
 int launch_rows_t2_h(const RowArgs& A, int nrows, const float2* tw, cudaStream_t st) {
   auto kern = k_fft_rows_t2<L, DIR, HALF>;
   const size_t smem = (size_t)TX * Split<L>::R1 * (Split<L>::R2 + 1) * sizeof(float2);
-  static bool done = false;
-  if (!done) {
-    B200_TRY(set_smem(kern, smem));
-    done = true;
-  }
+  static PerDeviceOnce once;
+  if (once.first()) B200_TRY(set_smem(kern, smem));
   kern<<<dim3((unsigned)ceil_div(nrows, TX) * (unsigned)A.T, 1, 1), FT, smem, st>>>(A, nrows, tw);
   CHECK_LAUNCH();
   return B200_OK;
@@ -862,11 +853,8 @@ template <int L, int DIR, bool HALF>
 int launch_rows_t1_h(const RowArgs& A, int nrows, const float2* tw, cudaStream_t st) {
   auto kern = k_fft_rows_t1<L, DIR, HALF>;
   const size_t smem = ((size_t)TXR1 * Split<L>::R1 * (Split<L>::R2 + 1) + 2 * (size_t)TXR1 * L) * sizeof(float2);
-  static bool done = false;
-  if (!done) {
-    B200_TRY(set_smem(kern, smem));
-    done = true;
-  }
+  static PerDeviceOnce once;
+  if (once.first()) B200_TRY(set_smem(kern, smem));
   kern<<<dim3(ceil_div(nrows, TXR1), 1, A.smaps ? 1 : A.T), Split<L>::R1 * TXR1, smem, st>>>(A, nrows, tw);
   CHECK_LAUNCH();
   return B200_OK;

@@ -1108,13 +1108,12 @@ int launch_rows_v(b200_plan* p, RowsState* ts, float2* fw, int T, const uint32_t
   StreamState* ss = &ts->cls[class_index(TC)];
   auto kern = k_rows<DIM, W, SPREAD, FIXED, TC>;
   const size_t smem = (size_t)WARPS * C::smem_per_warp(SPREAD);
-  static bool attr_done = false;
+  static PerDeviceOnce once;
   static int ctas_per_sm = 1;
-  if (!attr_done) {
+  if (once.first()) {
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, THREADS, smem));
     if (ctas_per_sm < 1) ctas_per_sm = 1;
-    attr_done = true;
   }
   if (SPREAD && ss->nsplit > 0) {
     k_zero_split_rows<DIM, TC><<<ceil_div(ss->nsplit * 32, 128), 128, 0, st>>>(p->g, T, ss->nsplit,

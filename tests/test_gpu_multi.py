@@ -31,3 +31,27 @@ def test_coil_sharded_operator_on_two_gpus_equals_one_gpu():
     out = json.loads(line)
     assert out["ok"] and out["world"] == 2 and out["worst_rel_err_over_ranks"] < 1e-4, out
     assert "adj_op_host_arrays" in out["sense"]
+
+
+def test_one_process_two_devices():
+    """Two operators on two devices of ONE process (`gpu_device_id`): per-device kernel attributes (dynamic
+    shared-memory limits) and workspaces; both must give the single-device result."""
+    import numpy as np
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    import mrinufft
+    import mrinufft_b200  # noqa: F401
+
+    rng = np.random.default_rng(0)
+    shape, M, C = (32, 32, 32), 20000, 4
+    samples = rng.uniform(-0.5, 0.5, (M, 3)).astype(np.float32)
+    img = (rng.standard_normal((1, C, *shape)) + 1j * rng.standard_normal((1, C, *shape))).astype(np.complex64)
+    outs = []
+    for dev in (0, 1):
+        op = mrinufft.get_operator("b200")(samples, shape, n_coils=C, squeeze_dims=False, gpu_device_id=dev)
+        y = op.op(img)
+        outs.append((y, op.adj_op(y)))
+    for a, b in zip(outs[0], outs[1]):
+        assert np.linalg.norm(a - b) <= 1e-6 * np.linalg.norm(a)

@@ -1,0 +1,48 @@
+#!/usr/bin/env python
+"""precision="double" against the single-precision path: 3-D 128^3, M = 2^21 radial, 8 coils with smaps
+(op / adj_op ms, device resident).  Round 2, one B200: single 3.0 / 2.8 ms, double 10.4 / 56 ms -- the double
+spreader runs at the L2's atomic rate (2 w^3 double atomics per point and coil, 2e11 / s).  Measured and not
+kept: points sorted by 4 x 4 x 16-cell bricks (61 ms: neighbouring lanes then collide on cells), lanes = coils
+(61 ms), brick tiles in shared memory with shared-memory double atomics, i.e. the classic sub-problem spreader
+(108 .. 220 ms: those atomics are compare-and-swap loops on sm_100a)."""
+import json
+import sys
+from pathlib import Path
+
+import numpy as np
+import torch
+
+ROOT = Path(__file__).resolve().parent.parent
+for p in (ROOT, ROOT / "baseline" / "_ref"):
+    if str(p) not in sys.path:
+        sys.path.insert(0, str(p))
+import mrinufft  # noqa: E402
+import mrinufft_b200  # noqa: E402,F401
+from mrinufft.trajectories import initialize_3D_phyllotaxis_radial  # noqa: E402
+
+
+def timed(fn, n=3):
+    fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / n
+
+
+n, C = 128, 8
+traj = initialize_3D_phyllotaxis_radial(4096, 512).reshape(-1, 3)
+for prec, dbg in (("single", 0), ("double", 0)):
+    cdt = torch.complex64 if prec == "single" else torch.complex128
+    smaps = torch.randn(C, n, n, n, dtype=cdt, device="cuda")
+    op = mrinufft.get_operator("b200")(traj.astype(np.float64 if prec == "double" else np.float32), (n,) * 3,
+                                       n_coils=C, smaps=smaps, squeeze_dims=False, precision=prec)
+    img = torch.randn(1, 1, n, n, n, dtype=cdt, device="cuda")
+    ksp = torch.randn(1, C, op.n_samples, dtype=cdt, device="cuda")
+    print(json.dumps({"precision": prec,  "op_ms": timed(lambda: op._op_device(img)),
+                      "adj_op_ms": timed(lambda: op._adj_device(ksp)), "M": op.n_samples, "coils": C, "n": n}), flush=True)
+    del op, smaps, img, ksp
+    torch.cuda.empty_cache()
