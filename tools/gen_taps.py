@@ -38,6 +38,7 @@ visit k + 1 is loaded before the taps of visit k execute.  See `gen_loop` for th
 import sys
 
 NJ = 8  # cell pairs per row
+DEFER_INTERP_TAIL = True  # see gen_loop
 
 
 def obuf_stride(TC):
@@ -125,8 +126,9 @@ def taps_spread(lay, W, X, c, slot=0):
     return L
 
 
-def taps_interp(lay, W, X, c, slot):
-    """kt[s] += sum of the taps of case c read from the tile registers, visit in register set X."""
+def taps_interp_sums(lay, W, X, c, S="S"):
+    """Partial sums of a visit: S0..S3 = sum over the tap pairs of case c of tile registers x x-weights
+    (S0 / S1: real / imaginary part of row 0, S2 / S3: row 1), visit in register set X."""
     jb0, _ = cases(W)
     NP = W // 2 + 1
     jb = c - jb0
@@ -143,17 +145,26 @@ def taps_interp(lay, W, X, c, slot):
                 o = r * 2 + ri
                 a = r * 16 + ri * 8 + j
                 if first[o]:
-                    L.append(f"mul.rn.f32x2 S{o}, %{a}, P{X}{q};")
+                    L.append(f"mul.rn.f32x2 {S}{o}, %{a}, P{X}{q};")
                     first[o] = False
                 else:
-                    L.append(f"fma.rn.f32x2 S{o}, %{a}, P{X}{q}, S{o};")
-    # row scales applied on the packed pairs, then one horizontal add per component
-    L += lane_scales(lay, X)
-    L += [f"mov.b64 A0, {{s{X}0, s{X}0}};", f"mov.b64 A1, {{s{X}1, s{X}1}};",
-          "mul.rn.f32x2 S0, S0, A0;", "mul.rn.f32x2 S1, S1, A0;",
-          "fma.rn.f32x2 S0, S2, A1, S0;", "fma.rn.f32x2 S1, S3, A1, S1;",
-          "mov.b64 {lo, hi}, S0;", "add.f32 t0, lo, hi;",
-          "mov.b64 {lo, hi}, S1;", "add.f32 t1, lo, hi;"]
+                    L.append(f"fma.rn.f32x2 {S}{o}, %{a}, P{X}{q}, {S}{o};")
+    return L
+
+
+def interp_tail(lay, s0, s1, z, n, slot, S="S"):
+    """Row scales applied on the packed pairs, one horizontal add per component, and the result on its way:
+    a red to k-space (class 32) or a store into the partial-sum buffer (smaller classes).  `s0, s1, z, n`:
+    registers that hold the visit's scales / z window entry / point index."""
+    L = []
+    if lay.generic:
+        L += [f"mul.f32 q0, {s0}, {z};", f"mul.f32 q1, {s1}, {z};"]
+        s0, s1 = "q0", "q1"
+    L += [f"mov.b64 A0, {{{s0}, {s0}}};", f"mov.b64 A1, {{{s1}, {s1}}};",
+          f"mul.rn.f32x2 {S}0, {S}0, A0;", f"mul.rn.f32x2 {S}1, {S}1, A0;",
+          f"fma.rn.f32x2 {S}0, {S}2, A1, {S}0;", f"fma.rn.f32x2 {S}1, {S}3, A1, {S}1;",
+          f"mov.b64 {{lo, hi}}, {S}0;", "add.f32 t0, lo, hi;",
+          f"mov.b64 {{lo, hi}}, {S}1;", "add.f32 t1, lo, hi;"]
     if lay.generic:
         # the G row groups of a coil each hold a partial sum: parked in shared memory ([visit][lane], rows of
         # `obuf_stride` bytes), summed and added to k-space by the kernel after the run (one compact loop
@@ -161,9 +172,14 @@ def taps_interp(lay, W, X, c, slot):
         # enough for the instruction cache)
         L += [f"st.shared.v2.f32 [ob+{slot * lay.obs}], {{t0, t1}};"]
     else:
-        L += [f"mad.wide.u32 addr, n{X}, 256, ktl;",
+        L += [f"mad.wide.u32 addr, {n}, 256, ktl;",
               "red.global.add.v2.f32 [addr], {t0, t1};"]
     return L
+
+
+def taps_interp(lay, W, X, c, slot):
+    """kt[s] += sum of the taps of case c read from the tile registers, visit in register set X."""
+    return taps_interp_sums(lay, W, X, c) + interp_tail(lay, f"s{X}0", f"s{X}1", f"z{X}", f"n{X}", slot)
 
 
 def gen_loop(W, spread, dim=3, TC=32):
@@ -192,8 +208,8 @@ def gen_loop(W, spread, dim=3, TC=32):
         return s
 
     body = ["{",
-            ".reg .b64 PA<4>, PB<4>, vA, vB, A<4>, S<4>, addr, ktl;",
-            ".reg .b32 sA<2>, sB<2>, iA, iB, nA, nB, zA, zB, vx, vy, lo, hi, t<4>, pk, pky, pkz, vb, ob, n;",
+            ".reg .b64 PA<4>, PB<4>, vA, vB, A<4>, S<4>, U<4>, addr, ktl;",
+            ".reg .b32 sA<2>, sB<2>, iA, iB, nA, nB, zA, zB, vx, vy, lo, hi, t<4>, q<2>, e<4>, pk, pky, pkz, vb, ob, n;",
             ".reg .pred p1, p2, p3, p4, p5;",
             "mov.u32 pk, %32;", "mov.u32 n, %33;"]
     if spread:
@@ -219,15 +235,32 @@ def gen_loop(W, spread, dim=3, TC=32):
     body += ["DA:", "setp.lt.s32 p5, n, 1;", "@p5 bra.uni DONE;",
              "tblA: .branchtargets " + ", ".join(f"RA{i}" for i in range(ncase)) + ";",
              "brx.idx.uni iA, tblA;"]
+    # (class 32 only: 21.2 -> 20.5 ms at cfg-C; in the smaller classes the extra live registers spill)
+    defer = (not spread) and DEFER_INTERP_TAIL and not lay.generic
     for c in range(ncase):
         body += [f"RA{c}:", "setp.lt.s32 p1, n, 2;"]
         body += load_set(lay, Y, 1, "p1", spread)
-        body += taps(lay, W, X, c, 0)
-        body += [f"setp.ne.u32 p2, i{Y}, {c};", "@p2 bra.uni XA;", "setp.lt.s32 p3, n, 3;"]
-        body += load_set(lay, X, 2, "p3", spread)
-        body += taps(lay, W, Y, c, 1)
+        if defer:
+            # The tail of visit A (scales -> horizontal add -> red / store: a chain of dependent fixed-latency
+            # instructions) is emitted BEHIND the branch that ends A's basic block, in the block of visit B's
+            # taps, so that ptxas can interleave the two; the values it needs are copied out of set A first,
+            # because the block also reloads that set for the visit after next.
+            body += taps_interp_sums(lay, W, X, c, "S")
+            body += [f"setp.ne.u32 p2, i{Y}, {c};", "@p2 bra.uni TA;", "setp.lt.s32 p3, n, 3;",
+                     "mov.b32 e0, sA0;", "mov.b32 e1, sA1;", "mov.b32 e2, nA;"] + (["mov.b32 e3, zA;"] if lay.generic else [])
+            body += load_set(lay, X, 2, "p3", spread)
+            body += interp_tail(lay, "e0", "e1", "e3", "e2", 0, "S")
+            body += taps_interp_sums(lay, W, Y, c, "U")
+            body += interp_tail(lay, f"s{Y}0", f"s{Y}1", f"z{Y}", f"n{Y}", 1, "U")
+        else:
+            body += taps(lay, W, X, c, 0)
+            body += [f"setp.ne.u32 p2, i{Y}, {c};", "@p2 bra.uni XA;", "setp.lt.s32 p3, n, 3;"]
+            body += load_set(lay, X, 2, "p3", spread)
+            body += taps(lay, W, Y, c, 1)
         body += step(2)
         body += [f"setp.eq.u32 p4, i{X}, {c};", f"@p4 bra.uni RA{c};", "bra.uni DA;"]
+    if defer:
+        body += ["TA:"] + interp_tail(lay, "sA0", "sA1", "zA", "nA", 0, "S")
     body += ["XA:"] + step(1) + moves + ["bra.uni DA;"]
     body += ["DONE:", "}"]
     args = "unsigned vb" if spread else ("unsigned ob" if lay.generic else "const void* ktl")
