@@ -219,3 +219,35 @@ def test_one_plan_serves_calls_of_different_coil_counts(mods):
     np.random.seed(0)
     assert abs(op.get_lipschitz_cst(max_iter=5) - lip1) <= 1e-5 * lip1
     assert lip0 > 0
+
+
+@pytest.mark.parametrize("eps,w", [(1e-3, 4), (1e-4, 5), (1e-5, 6)])
+@pytest.mark.parametrize("shape,C,classes", [((24, 32, 20), 2, (2, 4, 8, 16, 32)), ((24, 32, 20), 1, (1,)),
+                                             ((48, 40), 2, (8, 16, 32))])
+def test_narrower_kernels_in_every_class(mods, eps, w, shape, C, classes):
+    """Kernel widths 4, 5, 6 (eps = 1e-3 .. 1e-5) have their own generated visit loops in every coil class:
+    against the float64 oracle run with the same eps (same kernel, same grid: only float rounding differs)
+    and against the exact NDFT at the accuracy the width promises."""
+    from oracle import es_nufft as E
+    from oracle.c_oracle import CpuNufft
+
+    mrinufft, _, _ = mods
+    rng = np.random.default_rng(int(-np.log10(eps)))
+    d, M = len(shape), 2500
+    samples = rng.uniform(-np.pi, np.pi, (M, d)).astype(np.float32)
+    op = mrinufft.get_operator("b200")(samples, shape, n_coils=C, squeeze_dims=False, eps=eps)
+    plan = op.raw_op.plan
+    assert plan.w == w
+    plan.set_option(0, 2)
+    plan.set_option(1, 2)
+    img, ksp = _c(rng, 1, C, *shape), _c(rng, 1, C, M)
+    cpu = CpuNufft(samples, shape, eps=eps, precision="f64")
+    y_o, x_o = cpu.op(img[0]), cpu.adj_op(ksp[0])
+    A = E.ndft_matrix(samples, shape) / op.norm_factor
+    y_n = np.stack([A @ img[0, c].ravel() for c in range(C)])
+    for cls in classes:
+        plan.set_option(4, cls)
+        assert plan.rows_class(C)["class"] == cls
+        y, x = op.op(img)[0], op.adj_op(ksp)[0]
+        assert rel_l2(y, y_o) <= 3e-6 and rel_l2(x, x_o) <= 3e-6, cls
+        assert rel_l2(y, y_n) <= 5 * eps, cls
