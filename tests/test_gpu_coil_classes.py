@@ -226,7 +226,8 @@ def test_one_plan_serves_calls_of_different_coil_counts(mods):
                                              ((48, 40), 2, (8, 16, 32))])
 def test_narrower_kernels_in_every_class(mods, eps, w, shape, C, classes):
     """Kernel widths 4, 5, 6 (eps = 1e-3 .. 1e-5) have their own generated visit loops in every coil class:
-    against the float64 oracle run with the same eps (same kernel, same grid: only float rounding differs)
+    against the float64 oracle run with the same eps (same kernel, same grid: float rounding and the device's
+    polynomial fit of the kernel differ)
     and against the exact NDFT at the accuracy the width promises."""
     from oracle import es_nufft as E
     from oracle.c_oracle import CpuNufft
@@ -249,5 +250,7 @@ def test_narrower_kernels_in_every_class(mods, eps, w, shape, C, classes):
         plan.set_option(4, cls)
         assert plan.rows_class(C)["class"] == cls
         y, x = op.op(img)[0], op.adj_op(ksp)[0]
-        assert rel_l2(y, y_o) <= 3e-6 and rel_l2(x, x_o) <= 3e-6, cls
+        # (the device evaluates the kernel with a polynomial fitted to 0.1 eps, the oracle exactly)
+        tol = 3e-6 + 0.05 * eps
+        assert rel_l2(y, y_o) <= tol and rel_l2(x, x_o) <= tol, cls
         assert rel_l2(y, y_n) <= 5 * eps, cls
