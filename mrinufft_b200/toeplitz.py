@@ -1,64 +1,54 @@
 """Toeplitz embedding of the Gram operator ``A^H W A`` -- kernel assembly (plan time).
 
-Host-side mirror of ``compute_toeplitz_kernel`` / ``_compute_toep_2d`` / ``_compute_toep_3d``
-(``src/mrinufft/operators/toeplitz.py:35-200``): the point-spread function of the trajectory is
-needed on the ``2N - 1`` lags of every axis; ``2^(d-1)`` raw adjoints of phase-modulated weights
-give the lag windows ``[-N/2, N/2)`` shifted onto the outer lags, Hermitian symmetry (real weights)
-gives the other half, and one real inverse FFT turns the lag array into the real spectrum of the
-circulant embedding on the ``2N`` grid.  The adjoints are the expensive part and run in
-``libb200nufft.so``; what is here is index bookkeeping on torch tensors (any device).
+Role of ``compute_toeplitz_kernel`` (``src/mrinufft/operators/toeplitz.py:35-200``).  The Gram operator of a
+NUFFT is a convolution with the point-spread function of the trajectory,
 
-The spectrum is applied by ``b200_toeplitz_apply`` (``include/b200nufft.h``).
+    c[l] = sum_j w_j exp(i omega_j . l),      l in [-(N-1), N-1]^d,
+
+and applying it to an image of ``N`` voxels per axis only ever needs those ``2N - 1`` lags per axis: zero-padded
+to ``2N`` it is a circular convolution, i.e. a multiply by the (real, because ``c[-l] = conj(c[l])`` for real
+weights) DFT of the lag array.  A raw adjoint NUFFT of the weights gives ``c`` on the ``N`` lags
+``[-N/2, N/2)``; modulating the weights by ``exp(i omega . s N/2)``, ``s = +-1`` per axis, shifts that window to
+``[0, N)`` or ``[-N, 0)``.  The ``2^d`` sign combinations tile ``[-N, N)^d``: every adjoint result is dropped
+into its octant of the lag array (lag ``l`` at index ``l mod 2N``), the lag ``-N`` of every axis -- which a
+zero-padded convolution never reads -- is cleared, and one FFT gives the spectrum.  (The reference halves the
+number of adjoints with the Hermitian symmetry and a real inverse FFT of a half array; with single-coil
+adjoints at 3 ms apiece -- coil class 1 of the row kernels -- the plain tiling is not worth complicating.)
+
+The adjoints are the expensive part and run in ``libb200nufft.so``; what is here is bookkeeping on torch
+tensors (any device, any dimension).  The spectrum is applied by ``b200_toeplitz_apply``
+(``include/b200nufft.h``).
 """
 
 from __future__ import annotations
 
+import itertools
+import math
+
 import torch
 
 
-def _rev(t: torch.Tensor) -> torch.Tensor:
-    """``t[N-1:0:-1]`` along every axis (drop index 0, reverse the rest)."""
-    idx = tuple(slice(1, None) for _ in range(t.ndim))
-    return torch.flip(t[idx], dims=tuple(range(t.ndim)))
-
-
 def assemble_toeplitz_kernel(adj, shape, scale: float) -> torch.Tensor:
-    """Real spectrum ``(2N0, 2N1[, 2N2])`` of the Toeplitz embedding.
+    """Real spectrum, of shape ``2N``, of the Toeplitz embedding.
 
-    ``adj(signs)`` must return the raw (un-normalised, no smaps) adjoint NUFFT, a complex tensor
-    of ``shape``, of the weights modulated by ``exp(i omega . (signs * N/2))``
-    (``_modulated_weights``, toeplitz.py:98-111).  ``scale`` is ``1 / norm_factor``.
+    ``adj(signs)`` must return the raw (un-normalised, no smaps) adjoint NUFFT, a complex tensor of ``shape``,
+    of the weights modulated by ``exp(i omega . (signs * N/2))`` (``modulated_weights``).  ``scale`` is
+    ``1 / norm_factor``; the result carries ``scale / sqrt(prod(2N))``, the convention of the reference's
+    ``irfftn(..., norm="ortho")`` kernel (toeplitz.py:89-93).
     """
-    shape = tuple(int(s) for s in shape)
-    if any(s % 2 for s in shape):
+    shape = tuple(int(n) for n in shape)
+    if any(n % 2 for n in shape):
         raise ValueError(f"Toeplitz kernel computation only supports even grid sizes, got {shape}.")
-    if len(shape) == 2:
-        N0, N1 = shape
-        A = adj((1, 1))
-        kernel = torch.zeros((2 * N0, N1 + 1), dtype=A.dtype, device=A.device)
-        kernel[:N0, :N1] = A
-        B = adj((1, -1))
-        kernel[N0 + 1:, 0] = torch.conj(_rev(A[:, 0]))
-        kernel[N0 + 1:, 1:N1] = torch.conj(_rev(B))
-    elif len(shape) == 3:
-        N0, N1, N2 = shape
-        A = adj((1, 1, 1))
-        kernel = torch.zeros((2 * N0, 2 * N1, N2 + 1), dtype=A.dtype, device=A.device)
-        kernel[:N0, :N1, :N2] = A
-        C = adj((1, -1, 1))
-        kernel[:N0, N1 + 1:, :N2] = C[:, 1:, :]
-        B = adj((1, 1, -1))
-        D = adj((1, -1, -1))
-        kernel[N0 + 1:, 0, 0] = torch.conj(_rev(A[:, 0, 0]))
-        kernel[N0 + 1:, 0, 1:N2] = torch.conj(_rev(B[:, 0, :]))
-        kernel[N0 + 1:, 1:N1, 0] = torch.conj(_rev(C[:, :, 0]))
-        kernel[N0 + 1:, 1:N1, 1:N2] = torch.conj(_rev(D))
-        kernel[N0 + 1:, N1 + 1:, 0] = torch.conj(_rev(A[:, :, 0]))
-        kernel[N0 + 1:, N1 + 1:, 1:N2] = torch.conj(_rev(B))
-    else:
-        raise ValueError(f"Toeplitz kernel calculation not implemented for ndim={len(shape)}")
-    full_shape = tuple(2 * s for s in shape)
-    return torch.fft.irfftn(torch.conj(kernel) * scale, s=full_shape, norm="ortho")
+    full = tuple(2 * n for n in shape)
+    lags = None
+    for signs in itertools.product((1, -1), repeat=len(shape)):
+        window = adj(signs)  # c[n + (s - 1) N / 2]: lags [0, N) for s = +1, [-N, 0) for s = -1
+        if lags is None:
+            lags = torch.zeros(full, dtype=window.dtype, device=window.device)
+        lags[tuple(slice(0, n) if s > 0 else slice(n, 2 * n) for s, n in zip(signs, shape))] = window
+    for axis, n in enumerate(shape):
+        lags.select(axis, n).zero_()
+    return torch.fft.fftn(lags).real * (scale / math.sqrt(math.prod(full)))
 
 
 def modulated_weights(weights: torch.Tensor, omega: torch.Tensor, signs, shape) -> torch.Tensor:
