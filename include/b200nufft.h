@@ -216,6 +216,8 @@ int b200_plan_set_option(b200_plan* plan, int key, int64_t value);
  *   out[0] = class (1, 2, 4, 8, 16, 32; 0 if the tiled kernels do not serve this plan)
  *   out[1] = (point, tile) visits of that class's visit stream, out[2] = stream entries
  *            (both 0 until a transform has built the stream), out[3] = 1 if the stream does not fit
+ * B200_DOUBLE plans: out[0] = 16 (coils per launch of the complex128 spreader's row kernel) once setpts has
+ * built its visit stream, 0 when the point-driven spreader serves the plan.
  */
 int b200_plan_rows_class(b200_plan* plan, int T, int64_t out[4]);
 

@@ -428,7 +428,11 @@ int b200_plan_rows_class(b200_plan* p, int T, int64_t out[4]) {
     return B200_EINVAL;
   }
   out[0] = out[1] = out[2] = out[3] = 0;
-  if (p->dbl || !tiled_supported(p, T)) return B200_OK;
+  if (p->dbl) {
+    drows_info(p, out);
+    return B200_OK;
+  }
+  if (!tiled_supported(p, T)) return B200_OK;
   tiled_class_info(p, T, out);
   return B200_OK;
 }

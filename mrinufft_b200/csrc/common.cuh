@@ -121,6 +121,7 @@ struct b200_plan {
   void* tiled = nullptr;
   // complex128 path (double_path.cu): non-null for plans created with B200_DOUBLE
   void* dbl = nullptr;
+  void* drows = nullptr;  // state of its tile-owned spreader (double_rows.cu)
   // tensor maps of the TMA variant of the FFT passes (fft_pruned.cu)
   void* tma = nullptr;
   // spreading into a grid that the fused FFT passes consume next: tiles without visitors are neither
@@ -156,6 +157,8 @@ void es_deapod_vector(int n, int nf, int w, double beta, std::vector<float>* out
 
 // ---------------------------------------------------------------- kernels (implemented in the .cu files)
 int k1_setpts(b200_plan* p, const float* xyz, cudaStream_t st);
+int k1_reserve_points(b200_plan* p, long long M);       // point arrays of the plan for M points
+int k1_sort_origins(b200_plan* p, cudaStream_t st);     // sort by bin key from p->d_org_u (complex128 path)
 int k2_spread(b200_plan* p, const float2* ksp, const float* density, float2* fw, int T,
               cudaStream_t st);
 int k3_interp(b200_plan* p, const float2* fw, float2* ksp, int T, float scale,
@@ -188,6 +191,12 @@ int dbl_type1(b200_plan* p, const void* ksp, const void* density, const void* sm
 int dbl_data_consistency(b200_plan* p, const void* img, const void* smaps, const void* obs,
                          const void* density, void* grad, int T, int accumulate, double scale,
                          cudaStream_t st);
+// tile-owned spread / interp in double (double_rows.cu); both return 1 when they cannot serve the plan
+bool drows_supported(const b200_plan* p);
+int drows_setpts(b200_plan* p, const double* const* x1_unsorted, cudaStream_t st);
+int drows_spread(b200_plan* p, const double2* ksp, const double* density, double2* fw, int T, cudaStream_t st);
+void drows_free(b200_plan* p);
+void drows_info(const b200_plan* p, int64_t out[4]);  // b200_plan_rows_class of a complex128 plan
 
 static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 

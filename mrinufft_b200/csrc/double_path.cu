@@ -6,8 +6,9 @@
 // tuned kernel (row kernels, fused FFT passes) is float -- and offers double as an opt-in,
 // correctness-first path: the same algorithm (fold, exponential-of-semicircle kernel of width
 // w = ceil(log10(10 / eps)) <= 16, sigma = 2, deapodisation by quadrature) with the kernel evaluated
-// directly (exp / sqrt in double, no polynomial), point-driven spreading with native double atomics,
-// point-driven interpolation, cuFFT Z2Z and separate pad / crop passes.  Same C entry points, data
+// directly (exp / sqrt in double, no polynomial), tile-owned spreading (double_rows.cu; point-driven
+// with native double atomics for the geometries that file does not take, and in 1-D), point-driven
+// interpolation, cuFFT Z2Z and separate pad / crop passes.  Same C entry points, data
 // pointers are complex128 / float64.  Not supported in double: B200_SPREAD_ONLY plans, the sort
 // read-back and the Toeplitz entry point.
 #include <cmath>
@@ -24,6 +25,7 @@ struct DblState {
   double2* d_res = nullptr;  // k-space residual of data_consistency
   size_t res_cap = 0;
   long long Mcap = 0;
+  bool rows = false;  // the current points have a visit stream (double_rows.cu)
   cufftHandle fft = 0;
   bool fft_ok = false;
 };
@@ -362,8 +364,15 @@ int type1_d(b200_plan* p, const double2* ksp, const double* density, const doubl
             int T, int accumulate, int isign, double scale, int conj_smaps, cudaStream_t st) {
   DblState* ds = dstate(p);
   const Geom& g = p->g;
-  CUDA_TRY(cudaMemsetAsync(ds->d_fw, 0, (size_t)T * g.nftot * sizeof(double2), st));
-  if (p->M > 0) {
+  // the row kernels write every cell of the grid themselves
+  bool rows = false;
+  if (ds->rows && p->M > 0) {
+    const int rc = drows_spread(p, ksp, density, ds->d_fw, T, st);
+    if (rc < 0) return rc;
+    rows = rc == B200_OK;
+  }
+  if (!rows) CUDA_TRY(cudaMemsetAsync(ds->d_fw, 0, (size_t)T * g.nftot * sizeof(double2), st));
+  if (p->M > 0 && !rows) {
     const PtArgs P = pt_args(ds);
     const int nb = ceil_div(p->M, 128);
     if (g.dim == 1) kd_spread<1><<<nb, 128, 0, st>>>(g, p->beta, p->M, T, P, ksp, density, ds->d_fw);
@@ -391,6 +400,10 @@ int dbl_init(b200_plan* p) {
     CUDA_TRY(cudaMalloc(&ds->d_deapod[a], dv.size() * sizeof(double)));
     CUDA_TRY(cudaMemcpy(ds->d_deapod[a], dv.data(), dv.size() * sizeof(double), cudaMemcpyHostToDevice));
   }
+  if (g.dim >= 2) {
+    CUDA_TRY(cudaMalloc(&p->d_bin_start, (size_t)(p->nbins_tot + 1) * sizeof(int32_t)));
+    p->ws_bytes += (size_t)(p->nbins_tot + 1) * sizeof(int32_t);
+  }
   const size_t fwb = (size_t)p->ntrans_max * g.nftot * sizeof(double2);
   if (cudaMalloc(&ds->d_fw, fwb) != cudaSuccess) {
     cudaGetLastError();
@@ -413,6 +426,7 @@ int dbl_init(b200_plan* p) {
 }
 
 void dbl_free(b200_plan* p) {
+  drows_free(p);
   DblState* ds = dstate(p);
   if (!ds) return;
   auto fr = [](void* q) {
@@ -446,10 +460,20 @@ int dbl_setpts(b200_plan* p, const double* xyz, cudaStream_t st) {
     }
     ds->Mcap = M;
   }
+  ds->rows = false;
   if (M == 0) return B200_OK;
   kd_fold<<<ceil_div(M, 256), 256, 0, st>>>(xyz, M, p->g, ds->d_org[0], ds->d_org[1], ds->d_org[2],
                                            ds->d_x1[0], ds->d_x1[1], ds->d_x1[2]);
   CHECK_LAUNCH();
+  if (drows_supported(p)) {
+    // bin sort on the origins + visit stream of the tile-owned spreader
+    B200_TRY(k1_reserve_points(p, M));
+    for (int a = 0; a < p->g.dim; ++a)
+      CUDA_TRY(cudaMemcpyAsync(p->d_org_u[a], ds->d_org[a], (size_t)M * 4, cudaMemcpyDeviceToDevice, st));
+    const int rc = drows_setpts(p, ds->d_x1, st);
+    if (rc < 0) return rc;  // rc > 0: this trajectory is left to the point-driven kernel
+    ds->rows = rc == B200_OK;
+  }
   return B200_OK;
 }
 

@@ -183,3 +183,44 @@ int k1_setpts(b200_plan* p, const float* xyz, cudaStream_t st) {
   CHECK_LAUNCH();
   return B200_OK;
 }
+
+// ---------------------------------------------------------------- sort of points whose origins are known
+// The complex128 path folds its points in double (double_path.cu) and hands the footprint origins over in
+// p->d_org_u[]: bin key, stable sort, sorted origins and bin offsets as above (the float offsets are not
+// used by that path).
+__global__ void __launch_bounds__(256)
+k_key_from_origins(long long M, Geom g, const int32_t* __restrict__ o0, const int32_t* __restrict__ o1,
+                   const int32_t* __restrict__ o2, int32_t* __restrict__ key, int32_t* __restrict__ iota) {
+  const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= M) return;
+  int o[3] = {o0[j], g.dim > 1 ? o1[j] : 0, g.dim > 2 ? o2[j] : 0};
+  key[j] = make_key(g, o);
+  iota[j] = (int32_t)j;
+}
+
+int k1_reserve_points(b200_plan* p, long long M) { return ensure_point_capacity(p, M); }
+
+int k1_sort_origins(b200_plan* p, cudaStream_t st) {
+  const long long M = p->M;
+  if (M == 0) {
+    CUDA_TRY(cudaMemsetAsync(p->d_bin_start, 0, (size_t)(p->nbins_tot + 1) * 4, st));
+    return B200_OK;
+  }
+  const int nb = ceil_div(M, 256);
+  k_key_from_origins<<<nb, 256, 0, st>>>(M, p->g, p->d_org_u[0], p->d_org_u[1], p->d_org_u[2], p->d_key_u,
+                                         p->d_iota);
+  CHECK_LAUNCH();
+  int bits = 1;
+  while (bits < 31 && (1LL << bits) < p->nbins_tot) ++bits;
+  size_t tmp = p->sort_tmp_bytes;
+  CUDA_TRY(cub::DeviceRadixSort::SortPairs(p->d_sort_tmp, tmp, p->d_key_u, p->d_key_s, p->d_iota, p->d_perm,
+                                           (int)M, 0, bits, st));
+  g_kernel_launches += 3;
+  k_gather_sorted<<<nb, 256, 0, st>>>(M, p->g.dim, p->d_perm, p->d_org_u[0], p->d_org_u[1], p->d_org_u[2],
+                                      p->d_x1_u[0], p->d_x1_u[1], p->d_x1_u[2], p->d_org_s[0], p->d_org_s[1],
+                                      p->d_org_s[2], p->d_x1_s[0], p->d_x1_s[1], p->d_x1_s[2]);
+  CHECK_LAUNCH();
+  k_bin_start<<<ceil_div(M + 1, 256), 256, 0, st>>>(M, p->d_key_s, p->d_bin_start, p->nbins_tot);
+  CHECK_LAUNCH();
+  return B200_OK;
+}

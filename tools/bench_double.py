@@ -7,6 +7,7 @@ kept: points sorted by 4 x 4 x 16-cell bricks (61 ms: neighbouring lanes then co
 (108 .. 220 ms: those atomics are compare-and-swap loops on sm_100a)."""
 import json
 import sys
+import time
 from pathlib import Path
 
 import numpy as np
@@ -33,16 +34,23 @@ def timed(fn, n=3):
     return e0.elapsed_time(e1) / n
 
 
-n, C = 128, 8
+n = 128
 traj = initialize_3D_phyllotaxis_radial(4096, 512).reshape(-1, 3)
-for prec, dbg in (("single", 0), ("double", 0)):
+for prec, dbg, C in (("single", 0, 8), ("double", 32, 8), ("double", 0, 8), ("double", 0, 16), ("double", 0, 4)):
     cdt = torch.complex64 if prec == "single" else torch.complex128
     smaps = torch.randn(C, n, n, n, dtype=cdt, device="cuda")
     op = mrinufft.get_operator("b200")(traj.astype(np.float64 if prec == "double" else np.float32), (n,) * 3,
                                        n_coils=C, smaps=smaps, squeeze_dims=False, precision=prec)
+    if dbg:  # option 3, bit 5: point-driven double spreader (atomics)
+        op.raw_op.plan.set_option(3, dbg)
     img = torch.randn(1, 1, n, n, n, dtype=cdt, device="cuda")
     ksp = torch.randn(1, C, op.n_samples, dtype=cdt, device="cuda")
-    print(json.dumps({"precision": prec,  "op_ms": timed(lambda: op._op_device(img)),
-                      "adj_op_ms": timed(lambda: op._adj_device(ksp)), "M": op.n_samples, "coils": C, "n": n}), flush=True)
+    t0 = time.perf_counter()
+    op.raw_op._set_pts(op.samples)
+    torch.cuda.synchronize()
+    setpts_ms = (time.perf_counter() - t0) * 1e3
+    print(json.dumps({"precision": prec, "spreader": "points" if dbg else "rows",
+                      "op_ms": timed(lambda: op._op_device(img)), "adj_op_ms": timed(lambda: op._adj_device(ksp)),
+                      "setpts_ms": setpts_ms, "M": op.n_samples, "coils": C, "n": n}), flush=True)
     del op, smaps, img, ksp
     torch.cuda.empty_cache()
