@@ -252,15 +252,17 @@ __device__ __forceinline__ void cp_async16_zfill(unsigned smem_dst, const void* 
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(smem_dst), "l"(gsrc), "r"(n) : "memory");
 }
 
-// per-warp shared memory: two buffers of 32 staged visits
-constexpr int DSM_E = 32 * 16 * 8;      // cell weights: [visit][16 cells]
-constexpr int DSM_V = 32 * DTC * 16;    // coil values: [visit][DTC] complex128
-constexpr int DSM_R = 32 * 32;          // [visit] {wy[dy], wy[dy + 1], wz[dz], -} -> row scales (s0, s1)
+// per-warp shared memory: two buffers of NB staged visits
+constexpr int NB = 16;                  // visits per staged block
+constexpr int DCTAS = 3;                // CTAs per SM the row kernel is compiled for
+constexpr int DSM_E = NB * 16 * 8;      // cell weights: [visit][16 cells]
+constexpr int DSM_V = NB * DTC * 16;    // coil values: [visit][DTC] complex128
+constexpr int DSM_R = NB * 32;          // [visit] {wy[dy], wy[dy + 1], wz[dz], -} -> row scales (s0, s1)
 constexpr int DSM_BUF = DSM_E + DSM_V + DSM_R;
 constexpr int DSM_WARP = 2 * DSM_BUF;
 
 template <int DIM>
-__global__ void __launch_bounds__(THREADS, 2)
+__global__ void __launch_bounds__(THREADS, DCTAS)
 kd_rows(Geom g, int T, int nchunks, unsigned S, const uint4* __restrict__ ent, const int32_t* __restrict__ chunk_row,
         const double* __restrict__ wtab, const double2* __restrict__ kt, double2* __restrict__ fw,
         int* __restrict__ counter, int lch_log2) {
@@ -291,7 +293,7 @@ kd_rows(Geom g, int T, int nchunks, unsigned S, const uint4* __restrict__ ent, c
     const unsigned base = (unsigned)ch << lch_log2;
     const uint4* v = ent + base;
     const int nw = (int)min(1u << lch_log2, S - base);
-    const int nblk = (nw + 31) >> 5;
+    const int nblk = (nw + NB - 1) / NB;
     const bool tail_whole = __ldg(reinterpret_cast<const unsigned*>(v + nw) + 2) == DHDR;
 
     double2* tbase = nullptr;  // this lane's first cell of row 0 of the tile
@@ -339,10 +341,10 @@ kd_rows(Geom g, int T, int nchunks, unsigned S, const uint4* __restrict__ ent, c
           if (c < xlim) __stcs(tbase + (long long)r * nfx + c, make_double2(0.0, 0.0));
     };
     auto load_entries = [&](int blk) -> uint4 {
-      const int i = blk * 32 + lane;
-      return i < nw ? __ldg(v + i) : pad;
+      const int i = blk * NB + lane;
+      return (lane < NB && i < nw) ? __ldg(v + i) : pad;
     };
-    // Stage a block of 32 entries, all copies asynchronous.  A lane fetches the y / z weights of its own entry;
+    // Stage a block of NB entries, all copies asynchronous.  A lane fetches the y / z weights of its own entry;
     // the 16 cell weights (the x weights laid over the tile's cells, zero outside the footprint) and the 16
     // coil values of a visit are fetched by a half-warp, two visits per step (coalesced, conflict-free).
     auto issue = [&](int buf, const uint4& e) {
@@ -351,19 +353,22 @@ kd_rows(Geom g, int T, int nchunks, unsigned S, const uint4* __restrict__ ent, c
       const double* wt = wtab + (hdr ? 0LL : (long long)e.w * (3 * WT));
       const int dy = (int)e.y;
       const bool ok0 = !hdr && dy >= 0 && dy < w, ok1 = !hdr && dy + 1 < w;
-      cp_async8_zfill(sR + lane * 32, wt + WT + (ok0 ? dy : 0), ok0 ? 8 : 0);
-      cp_async8_zfill(sR + lane * 32 + 8, wt + WT + (ok1 ? dy + 1 : 0), ok1 ? 8 : 0);
-      if (DIM == 3) cp_async8_zfill(sR + lane * 32 + 16, wt + 2 * WT + (hdr ? 0 : (int)e.z), hdr ? 0 : 8);
+      if (lane < NB) {
+        cp_async8_zfill(sR + lane * 32, wt + WT + (ok0 ? dy : 0), ok0 ? 8 : 0);
+        cp_async8_zfill(sR + lane * 32 + 8, wt + WT + (ok1 ? dy + 1 : 0), ok1 ? 8 : 0);
+        if (DIM == 3) cp_async8_zfill(sR + lane * 32 + 16, wt + 2 * WT + (hdr ? 0 : (int)e.z), hdr ? 0 : 8);
+      }
 #pragma unroll 4
-      for (int q = 0; q < 16; ++q) {
+      for (int q = 0; q < NB / 2; ++q) {
         const int vi = 2 * q + xh;
         const unsigned pw = __shfl_sync(FULL, e.w, vi);
         const int pxo = (int)__shfl_sync(FULL, e.x, vi);
         const bool ph = __shfl_sync(FULL, e.z, vi) == DHDR;
         const int k = t - pxo;
         const bool ok = !ph && k >= 0 && k < w;
-        cp_async8_zfill(sE + (vi * 16 + t) * 8, wtab + (ok ? (long long)pw * (3 * WT) + k : 0LL), ok ? 8 : 0);
-        cp_async16_zfill(sV + (vi * DTC + t) * 16, kt + (ph ? 0LL : (long long)pw * DTC + t), ph ? 0 : 16);
+        // 32-bit element indices: M * 48 < 2^32 is a condition of `build`
+        cp_async8_zfill(sE + (vi * 16 + t) * 8, wtab + (ok ? pw * (3u * WT) + (unsigned)k : 0u), ok ? 8 : 0);
+        cp_async16_zfill(sV + (vi * DTC + t) * 16, kt + (ph ? 0u : pw * (unsigned)DTC + (unsigned)t), ph ? 0 : 16);
       }
       cp_async_commit();
     };
@@ -386,12 +391,14 @@ kd_rows(Geom g, int T, int nchunks, unsigned S, const uint4* __restrict__ ent, c
       const double2* sV = reinterpret_cast<const double2*>(bp + DSM_E);
       double2* sR = reinterpret_cast<double2*>(const_cast<unsigned char*>(bp) + DSM_E + DSM_V);
       if (DIM == 3) {  // row scales of this lane's entry: wy[dy] wz[dz], wy[dy + 1] wz[dz]
-        const double2 wy = sR[lane * 2];
-        const double wz = sR[lane * 2 + 1].x;
-        sR[lane * 2] = make_double2(wy.x * wz, wy.y * wz);
+        if (lane < NB) {
+          const double2 wy = sR[lane * 2];
+          const double wz = sR[lane * 2 + 1].x;
+          sR[lane * 2] = make_double2(wy.x * wz, wy.y * wz);
+        }
         __syncwarp();
       }
-      const int n = min(32, nw - blk * 32);
+      const int n = min(NB, nw - blk * NB);
       // ---- consume: runs of visits separated by header entries
       unsigned hm = __ballot_sync(FULL, e0.z == DHDR && e0.w != 0xffffffffu);
       int k0 = 0;
@@ -480,7 +487,7 @@ int build(b200_plan* p, DRowsState* ds, const double* const* x1u, cudaStream_t s
     CHECK_LAUNCH();
   }
   const long long nrows = num_tiles<DIM, 32>(g);
-  if (nrows >= (1LL << 30)) {
+  if (nrows >= (1LL << 30) || M >= (1LL << 32) / (3 * WT)) {
     ds->unsupported = true;
     return 1;
   }

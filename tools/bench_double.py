@@ -1,10 +1,12 @@
 #!/usr/bin/env python
-"""precision="double" against the single-precision path: 3-D 128^3, M = 2^21 radial, 8 coils with smaps
-(op / adj_op ms, device resident).  Round 2, one B200: single 3.0 / 2.8 ms, double 10.4 / 56 ms -- the double
-spreader runs at the L2's atomic rate (2 w^3 double atomics per point and coil, 2e11 / s).  Measured and not
-kept: points sorted by 4 x 4 x 16-cell bricks (61 ms: neighbouring lanes then collide on cells), lanes = coils
-(61 ms), brick tiles in shared memory with shared-memory double atomics, i.e. the classic sub-problem spreader
-(108 .. 220 ms: those atomics are compare-and-swap loops on sm_100a)."""
+"""precision="double" against the single-precision path: 3-D 128^3, M = 2^21 radial, C coils with smaps
+(op / adj_op ms, device resident), with the point-driven atomic spreader (option 3, bit 5) and the tile-owned row
+spreader (csrc/double_rows.cu).  Round 2, one B200, 8 coils: single 3.0 / 2.8 ms; double 10.8 / 51.8 ms with
+atomics (2 w^3 double atomics per point and coil, 2e11 / s at the L2), 10.8 / 12.6 ms with the row spreader.
+Measured on the way and not kept: points sorted by 4 x 4 x 16-cell bricks under the atomic spreader (61 ms:
+neighbouring lanes then collide on cells), lanes = coils (61 ms), brick tiles in shared memory with shared-memory
+double atomics, i.e. the classic sub-problem spreader (108 .. 220 ms: those atomics are compare-and-swap loops on
+sm_100a)."""
 import json
 import sys
 import time
