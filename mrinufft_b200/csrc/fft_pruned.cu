@@ -113,7 +113,7 @@ __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, i
 // point visits are not written (type 2, last pass: the row interpolator never reads them)
 // KIN / KOUT = 1: the non-zero inputs / wanted outputs are the modes of an N = L / 2 image (sigma = 2), a
 // pattern known at compile time: inputs n1 < R1/4 or n1 >= 3 R1/4, outputs k2 < R2/4 or k2 >= 3 R2/4 --
-// no per-element predicates.  0: generic (run-time `Keep`, all-kept included).
+// no per-element predicates.  2: all of them, no predicates either.  0: generic (run-time `Keep`).
 // TMA = true: the tile is brought into shared memory with bulk tensor copies (cp.async.bulk.tensor, boxes of
 // 16 columns x BZ = 32 grid rows / planes = 4 KB, issued by one thread, completion on an mbarrier) instead of R1
 // global loads per thread; step A then works in place on the tile.  Boxes that hold only zero padding, or
@@ -132,10 +132,25 @@ k_fft_strided(StridedArgs A, const float2* __restrict__ tw, const __grid_constan
   float2* g = A.base + (long long)bt * A.coil_stride + goff;
   // the bit string of this CTA's column of spreader tiles (16 columns = one tile width)
   __shared__ uint32_t ebits[EMPTY ? L / 32 : 1];
+  // the same bits regrouped by thread: tmask[j] bit i = plane i * NJ + j, where a thread of step A (EMODE 1:
+  // j = n2, i = n1, NJ = R2) or step B (EMODE 2: j = k1, i = k2, NJ = R1) owns one j -- one word per thread
+  // and compile-time bit positions instead of a shared-memory load and a run-time shift per element
+  constexpr int NJ = EMODE == 1 ? R2 : R1, NI = L / NJ;
+  __shared__ uint32_t tmask[EMPTY ? NJ : 1];
   if (EMPTY) {
     constexpr int wpc = L / 32;  // 3-D only: one bit per grid plane
     const long long col = (long long)(lo >> 1) * A.nbx + bx;
     if (threadIdx.x < wpc) ebits[threadIdx.x] = __ldg(A.empty + col * wpc + threadIdx.x);
+    if (threadIdx.x >= 32 && threadIdx.x < 32 + NJ) {
+      const int j = threadIdx.x - 32;
+      uint32_t m = 0;
+#pragma unroll
+      for (int i = 0; i < NI; ++i) {
+        const int n = i * NJ + j;
+        m |= ((__ldg(A.empty + col * wpc + (n >> 5)) >> (n & 31)) & 1u) << i;
+      }
+      tmask[j] = m;
+    }
     __syncthreads();
     // a column without any visited tile (outside the trajectory's support): the transform of zeros
     bool all_empty = true;
@@ -144,7 +159,7 @@ k_fft_strided(StridedArgs A, const float2* __restrict__ tw, const __grid_constan
     if (all_empty) {
       for (int item = threadIdx.x; item < L * TX; item += FT) {
         const int k = item / TX, tx = item % TX;
-        if (kept(k, L, A.out)) __stcs(g + (long long)k * A.stride_n + tx, make_float2(0.f, 0.f));
+        if (KOUT == 2 || kept(k, L, A.out)) __stcs(g + (long long)k * A.stride_n + tx, make_float2(0.f, 0.f));
       }
       return;
     }
@@ -161,7 +176,7 @@ k_fft_strided(StridedArgs A, const float2* __restrict__ tw, const __grid_constan
       const char* pg = reinterpret_cast<const char*>(A.base + (long long)pbt * A.coil_stride +
                                                      (long long)plo * A.outer_stride + (long long)pbx * TX);
       for (int n = threadIdx.x; n < L; n += FT) {
-        bool live = KIN == 1 ? (n < L / 4 || n >= 3 * L / 4) : kept(n, L, A.in);
+        bool live = KIN == 1 ? (n < L / 4 || n >= 3 * L / 4) : (KIN == 2 || kept(n, L, A.in));
         if (EMODE == 1 && live) {
           const long long col = (long long)(plo >> 1) * A.nbx + pbx;
           live = !((__ldg(A.empty + col * (L / 32) + (n >> 5)) >> (n & 31)) & 1u);
@@ -184,7 +199,7 @@ k_fft_strided(StridedArgs A, const float2* __restrict__ tw, const __grid_constan
 #pragma unroll
       for (int b = 0; b < NB; ++b) {
         bool want = KIN == 1 ? (b * BZ < L / 4 || b * BZ >= 3 * L / 4)
-                             : (b * BZ < A.in.np || (b + 1) * BZ > L - A.in.nm);
+                             : (KIN == 2 || b * BZ < A.in.np || (b + 1) * BZ > L - A.in.nm);
         if (EMODE == 1) want = want && ebits[b] != 0xffffffffu;
         need |= want ? (1u << b) : 0u;
       }
@@ -200,25 +215,21 @@ k_fft_strided(StridedArgs A, const float2* __restrict__ tw, const __grid_constan
   for (int item = threadIdx.x; item < R2 * TX; item += FT) {
     const int n2 = item / TX, tx = item % TX;
     float2 a[R1];
+    const uint32_t im = EMODE == 1 ? tmask[EMODE == 1 ? n2 : 0] : 0u;
     const float2* gin = TMA ? S + n2 * TX + tx : g + (long long)n2 * A.stride_n + tx;
     const long long sR2 = TMA ? (long long)TX * R2 : A.stride_n * R2;
     sfor<0, R1>([&](auto I) {
       constexpr int n1 = decltype(I)::value;
       constexpr bool static_zero = KIN == 1 && n1 >= R1 / 4 && n1 < 3 * R1 / 4;
-      if constexpr (static_zero) {
-        a[n1] = make_float2(0.f, 0.f);
-      } else {
+      if constexpr (!static_zero) {  // (the zero middle of a sigma = 2 pad is never materialised)
         const int n = n1 * R2 + n2;
-        bool live = KIN == 1 ? true : kept(n, L, A.in);
-        if (EMODE == 1) {
-          // tile of grid plane n (3-D only): word n >> 5, bit n & 31 -- static word index when R2 = 16
-          if constexpr (R2 == 16) live = live && !((ebits[n1 >> 1] >> ((n1 & 1) * 16 + n2)) & 1u);
-          else live = live && !((ebits[n >> 5] >> (n & 31)) & 1u);
-        }
+        bool live = KIN != 0 ? true : kept(n, L, A.in);
+        if (EMODE == 1) live = live && !((im >> n1) & 1u);  // the tile of grid plane n (3-D only)
         a[n1] = live ? gin[n1 * sR2] : make_float2(0.f, 0.f);
       }
     });
-    fftreg::fft<R1, DIR>(a);
+    if constexpr (KIN == 1) fftreg::fft_zero_middle<R1, DIR>(a);
+    else fftreg::fft<R1, DIR>(a);
     sfor<0, R1>([&](auto I) {
       constexpr int k1 = decltype(I)::value;
       float2 v = a[brev(k1, R1)];
@@ -242,6 +253,7 @@ k_fft_strided(StridedArgs A, const float2* __restrict__ tw, const __grid_constan
     // Toeplitz factor of this thread's outputs: requested before the FFT so that the loads are in
     // flight while it runs
     float mf[MUL ? R2 : 1];
+    const uint32_t om = EMODE == 2 ? tmask[EMODE == 2 ? k1 : 0] : 0u;
     float2* gout = g + (long long)k1 * A.stride_n + tx;
     const long long sR1 = A.stride_n * R1;
     if (MUL) {
@@ -257,11 +269,8 @@ k_fft_strided(StridedArgs A, const float2* __restrict__ tw, const __grid_constan
       constexpr bool static_drop = KOUT == 1 && k2 >= R2 / 4 && k2 < 3 * R2 / 4;
       if constexpr (!static_drop) {
         const int k = k1 + R1 * k2;
-        bool wanted = KOUT == 1 ? true : kept(k, L, A.out);
-        if (EMODE == 2) {
-          if constexpr (R1 == 32) wanted = wanted && !((ebits[k2] >> k1) & 1u);
-          else wanted = wanted && !((ebits[k >> 5] >> (k & 31)) & 1u);
-        }
+        bool wanted = KOUT != 0 ? true : kept(k, L, A.out);
+        if (EMODE == 2) wanted = wanted && !((om >> k2) & 1u);
         if (wanted) {
           float2 v = b[brev(k2, R2)];
           if (MUL) v = cscale(v, mf[MUL ? k2 : 0]);
@@ -413,7 +422,8 @@ k_fft_rows_t2(RowArgs A, int nrows, const float2* __restrict__ tw) {
     } else {
       sfor<0, R1>([&](auto I) { a[decltype(I)::value] = make_float2(0.f, 0.f); });
     }
-    fftreg::fft<R1, DIR>(a);
+    if constexpr (HALF) fftreg::fft_zero_middle<R1, DIR>(a);
+    else fftreg::fft<R1, DIR>(a);
     sfor<0, R1>([&](auto I) {
       constexpr int k1 = decltype(I)::value;
       float2 v = a[brev(k1, R1)];
@@ -810,21 +820,34 @@ int launch_strided_m(const StridedArgs& A, int ntx, int nouter, int T, const flo
 }
 
 // (32-column tiles -- 256-byte segments per grid row, 512 threads, one CTA per SM -- were measured at
-// cfg-C: 50.0 ms for the six passes against 42.4 ms with 16-column tiles; not kept.)
+// cfg-C: 50.0 ms for the six passes against 42.4 ms with 16-column tiles; not kept.  Neither were, in round 2
+// (six passes at 30.1 ms):
+//  - a three-step radix-8 version of the pass for L = 512 (8 x 8 x 8 like k_fft_rows_t1_512: 40 registers, 512
+//    threads, 48 warps per SM instead of 24, two more shared-memory trips and 14 instead of 31/4 twiddles per 8
+//    points): correct to 1.5e-7 and 8 % slower on z- and y-passes alike -- the passes are bound by instruction
+//    issue, not by latency that more warps would hide;
+//  - persistent CTAs that fetch the empty-tile strings of their next tile while they work (the string ->
+//    barrier -> loads round trip at the start of a CTA is 21 % of the z-passes' stall samples): 34.0 ms, and
+//    32.8 ms for the same code with one tile per CTA -- the tile loop and its index arithmetic cost more than
+//    the round trip;
+//  - per-row strings that let the 3-D y-passes skip the rows of columns the z-pass skips (21 % of their
+//    traffic at cfg-C): 30.3 ms -- not bound by bytes;
+//  - type-2 z-pass: the loads of step A issued before the strings are waited for (the strings concern its
+//    outputs only): 30.2 against 29.9 ms.)
 template <int L, int DIR>
 int launch_strided(const StridedArgs& A, int ntx, int nouter, int T, const float2* tw, cudaStream_t st,
                    const CUtensorMap* tmap) {
-  // sigma = 2 patterns: modes of an N = L / 2 image <-> Keep{L / 4, L / 4}; everything <-> Keep{L, 0}
+  // sigma = 2 patterns: modes of an N = L / 2 image <-> Keep{L / 4, L / 4} (KIN / KOUT 1); everything <-> Keep{L, 0} (2)
   const bool in_half = A.in.np == L / 4 && A.in.nm == L / 4, in_all = A.in.np == L && A.in.nm == 0;
   const bool out_half = A.out.np == L / 4 && A.out.nm == L / 4, out_all = A.out.np == L && A.out.nm == 0;
   if (A.mul) return launch_strided_m<L, DIR, true, 0, 0, 0>(A, ntx, nouter, T, tw, st, nullptr);
   if (in_half && out_all) {  // type 2
-    if (A.empty && A.empty_out) return launch_strided_m<L, DIR, false, 2, 1, 0>(A, ntx, nouter, T, tw, st, tmap);
-    if (!A.empty) return launch_strided_m<L, DIR, false, 0, 1, 0>(A, ntx, nouter, T, tw, st, tmap);
+    if (A.empty && A.empty_out) return launch_strided_m<L, DIR, false, 2, 1, 2>(A, ntx, nouter, T, tw, st, tmap);
+    if (!A.empty) return launch_strided_m<L, DIR, false, 0, 1, 2>(A, ntx, nouter, T, tw, st, tmap);
   }
   if (in_all && out_half) {  // type 1
-    if (A.empty && !A.empty_out) return launch_strided_m<L, DIR, false, 1, 0, 1>(A, ntx, nouter, T, tw, st, tmap);
-    if (!A.empty) return launch_strided_m<L, DIR, false, 0, 0, 1>(A, ntx, nouter, T, tw, st, tmap);
+    if (A.empty && !A.empty_out) return launch_strided_m<L, DIR, false, 1, 2, 1>(A, ntx, nouter, T, tw, st, tmap);
+    if (!A.empty) return launch_strided_m<L, DIR, false, 0, 2, 1>(A, ntx, nouter, T, tw, st, tmap);
   }
   if (A.empty && A.empty_out) return launch_strided_m<L, DIR, false, 2, 0, 0>(A, ntx, nouter, T, tw, st, tmap);
   if (A.empty) return launch_strided_m<L, DIR, false, 1, 0, 0>(A, ntx, nouter, T, tw, st, tmap);

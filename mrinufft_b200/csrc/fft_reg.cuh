@@ -88,4 +88,38 @@ __device__ __forceinline__ void fft(float2 (&a)[R]) {
   Stage<R, R / 2, DIR>::run(a);
 }
 
+// -d * exp(DIR * 2 pi i K / 32), K in [0, 16)
+template <int K, int DIR>
+__device__ __forceinline__ float2 mul_tw32_neg(float2 d) {
+  if constexpr (K == 0) {
+    return make_float2(-d.x, -d.y);
+  } else if constexpr (K == 8) {
+    return DIR > 0 ? make_float2(d.y, -d.x) : make_float2(-d.y, d.x);
+  } else {
+    return cmul_cs(d, -cos32(K), DIR > 0 ? -sin32(K) : sin32(K));
+  }
+}
+
+// The same transform for inputs whose middle half is zero, a[n] = 0 for R/4 <= n < 3R/4 (a zero-padded
+// signal in FFT order, sigma = 2): every butterfly of the first stage has one zero input, so the stage is R/2
+// twiddle multiplies and no additions, and the zeros are never materialised.  a[R/4 .. 3R/4) need not be
+// initialised.
+template <int R, int DIR>
+__device__ __forceinline__ void fft_zero_middle(float2 (&a)[R]) {
+  static_assert(R >= 4 && R <= 32 && (R & (R - 1)) == 0, "R must be a power of two in [4, 32]");
+  constexpr int H = R / 2;
+  sfor<0, H>([&](auto I) {
+    constexpr int j = decltype(I)::value;
+    constexpr int k32 = j * (16 / H);
+    if constexpr (j < R / 4) {
+      a[j + H] = mul_tw32<k32, DIR>(a[j]);  // u + 0, (u - 0) w
+    } else {
+      const float2 v = a[j + H];
+      a[j] = v;  // 0 + v, (0 - v) w
+      a[j + H] = mul_tw32_neg<k32, DIR>(v);
+    }
+  });
+  Stage<R, H / 2, DIR>::run(a);
+}
+
 }  // namespace fftreg
