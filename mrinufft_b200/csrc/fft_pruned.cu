@@ -217,7 +217,9 @@ k_fft_strided(StridedArgs A, const float2* __restrict__ tw, const __grid_constan
     float2 a[R1];
     const uint32_t im = EMODE == 1 ? tmask[EMODE == 1 ? n2 : 0] : 0u;
     const float2* gin = TMA ? S + n2 * TX + tx : g + (long long)n2 * A.stride_n + tx;
-    const long long sR2 = TMA ? (long long)TX * R2 : A.stride_n * R2;
+    // (32-bit element strides: L stride_n < 2^31 for every grid the plan accepts, so an address is one
+    // IMAD.WIDE of a compile-time multiple of the stride)
+    const unsigned sR2 = TMA ? (unsigned)(TX * R2) : (unsigned)(A.stride_n * R2);
     sfor<0, R1>([&](auto I) {
       constexpr int n1 = decltype(I)::value;
       constexpr bool static_zero = KIN == 1 && n1 >= R1 / 4 && n1 < 3 * R1 / 4;
@@ -225,7 +227,7 @@ k_fft_strided(StridedArgs A, const float2* __restrict__ tw, const __grid_constan
         const int n = n1 * R2 + n2;
         bool live = KIN != 0 ? true : kept(n, L, A.in);
         if (EMODE == 1) live = live && !((im >> n1) & 1u);  // the tile of grid plane n (3-D only)
-        a[n1] = live ? gin[n1 * sR2] : make_float2(0.f, 0.f);
+        a[n1] = live ? gin[(unsigned)n1 * sR2] : make_float2(0.f, 0.f);
       }
     });
     if constexpr (KIN == 1) fftreg::fft_zero_middle<R1, DIR>(a);
@@ -255,7 +257,7 @@ k_fft_strided(StridedArgs A, const float2* __restrict__ tw, const __grid_constan
     float mf[MUL ? R2 : 1];
     const uint32_t om = EMODE == 2 ? tmask[EMODE == 2 ? k1 : 0] : 0u;
     float2* gout = g + (long long)k1 * A.stride_n + tx;
-    const long long sR1 = A.stride_n * R1;
+    const unsigned sR1 = (unsigned)(A.stride_n * R1);
     if (MUL) {
       sfor<0, R2>([&](auto I) {
         constexpr int k2 = decltype(I)::value;
@@ -274,7 +276,7 @@ k_fft_strided(StridedArgs A, const float2* __restrict__ tw, const __grid_constan
         if (wanted) {
           float2 v = b[brev(k2, R2)];
           if (MUL) v = cscale(v, mf[MUL ? k2 : 0]);
-          __stcs(gout + k2 * sR1, v);
+          __stcs(gout + (unsigned)k2 * sR1, v);
         }
       }
     });
