@@ -133,9 +133,13 @@ kd_spread(Geom g, double beta, long long M, int T, PtArgs P, const double2* __re
 template <int DIM>
 __global__ void __launch_bounds__(128)
 kd_interp(Geom g, double beta, long long M, int T, PtArgs P, const double2* __restrict__ fw,
-          double2* __restrict__ ksp, double scale, const double2* __restrict__ obs) {
-  const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= M) return;
+          double2* __restrict__ ksp, double scale, const double2* __restrict__ obs,
+          const int32_t* __restrict__ perm) {
+  const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= M) return;
+  // with a bin sort at hand (double_rows.cu) the threads of a warp take neighbouring points: their loads
+  // fall on the same few lines
+  const long long j = perm ? perm[s] : s;
   int o[3] = {0, 0, 0};
   double wt[3][B200_MAX_W];
   point_weights<DIM>(g, beta, j, P.org, P.x1, o, wt);
@@ -353,9 +357,10 @@ int type2_d(b200_plan* p, const double2* img, const double2* smaps, double2* ksp
   if (p->M == 0) return B200_OK;
   const PtArgs P = pt_args(ds);
   const int nb = ceil_div(p->M, 128);
-  if (g.dim == 1) kd_interp<1><<<nb, 128, 0, st>>>(g, p->beta, p->M, T, P, ds->d_fw, ksp, scale, obs);
-  else if (g.dim == 2) kd_interp<2><<<nb, 128, 0, st>>>(g, p->beta, p->M, T, P, ds->d_fw, ksp, scale, obs);
-  else kd_interp<3><<<nb, 128, 0, st>>>(g, p->beta, p->M, T, P, ds->d_fw, ksp, scale, obs);
+  const int32_t* perm = (ds->rows && !(p->rows_dbg & 64)) ? p->d_perm : nullptr;
+  if (g.dim == 1) kd_interp<1><<<nb, 128, 0, st>>>(g, p->beta, p->M, T, P, ds->d_fw, ksp, scale, obs, perm);
+  else if (g.dim == 2) kd_interp<2><<<nb, 128, 0, st>>>(g, p->beta, p->M, T, P, ds->d_fw, ksp, scale, obs, perm);
+  else kd_interp<3><<<nb, 128, 0, st>>>(g, p->beta, p->M, T, P, ds->d_fw, ksp, scale, obs, perm);
   CHECK_LAUNCH();
   return B200_OK;
 }
