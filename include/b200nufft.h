@@ -187,6 +187,23 @@ int b200_interp(b200_plan* plan, const void* grid, void* ksp, int T, void* strea
 int b200_pipe_iteration(b200_plan* plan, float* d, void* stream);
 
 /*
+ * z transform of the stacked (2.5-D) operator, fused with the sensitivity-map multiply, both centring
+ * shifts, the kz-plane selection and the (coil, stack)-major plane layout of the 2-D operator's coil axis:
+ * replaces `MRIStackedNUFFT._fftz` / `_ifftz` and the array shuffling around them
+ * (src/mrinufft/operators/stacked.py:178-195, 203-240, 254-300).  No plan is needed; any length Z.
+ *   forward: planes[c NZ + j, x, y] = scale * fftshift(fft(ifftshift(img[c | 0, x, y, :] * smaps[c, x, y, :])))[zsel[j]]
+ *   adjoint: out[c | 0, x, y, :]    = (sum over c) conj(smaps[c]) * scale * fftshift(ifft_unnormalised(ifftshift(K_c)))
+ *            with K_c[x, y, zsel[j]] = planes[c NZ + j, x, y], zero elsewhere (zsel without repeats)
+ *   img / out  complex64 (C, X, Y, Z), or (X, Y, Z) when smaps is given;  smaps NULL or complex64 (C, X, Y, Z)
+ *   planes     complex64 (C * NZ, X, Y);  zsel int32 (NZ) on the device, values in [0, Z)
+ *   scale      multiplied into the result (the reference's 1 / sqrt(2 Z))
+ */
+int b200_stack_fftz_forward(const void* img, const void* smaps, void* planes, const int32_t* zsel,
+                            int C, int X, int Y, int Z, int NZ, float scale, void* stream);
+int b200_stack_fftz_adjoint(const void* planes, const void* smaps, void* out, const int32_t* zsel,
+                            int C, int X, int Y, int Z, int NZ, float scale, void* stream);
+
+/*
  * Counters for bench.py: number of kernels this library launched and number of cuFFT
  * executions since the last reset (process wide).
  */

@@ -63,6 +63,16 @@ _SIGNATURES = {
     "b200_plan_rows_class": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int64)]),
     "b200_plan_last_timings": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
     "b200_plan_enable_timing": (C.c_int, [C.c_void_p, C.c_int]),
+    "b200_stack_fftz_forward": (
+        C.c_int,
+        [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+         C.c_float, C.c_void_p],
+    ),
+    "b200_stack_fftz_adjoint": (
+        C.c_int,
+        [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+         C.c_float, C.c_void_p],
+    ),
 }
 
 _lib = None
@@ -222,6 +232,13 @@ class Plan:
         check(self._lib.b200_plan_last_timings(self._h, out), "b200_plan_last_timings")
         return {"spread_ms": out[0], "interp_ms": out[1], "fft_ms": out[2], "grid_ms": out[3],
                 "rows_ms": out[4]}
+
+
+def stack_fftz(adjoint, src, smaps, dst, zsel, C_, X, Y, Z, NZ, scale, stream=0):
+    """z transform of the stacked operator (raw device pointers; see include/b200nufft.h)."""
+    fn = load().b200_stack_fftz_adjoint if adjoint else load().b200_stack_fftz_forward
+    check(fn(src, smaps, dst, zsel, int(C_), int(X), int(Y), int(Z), int(NZ), float(scale), stream),
+          "b200_stack_fftz_adjoint" if adjoint else "b200_stack_fftz_forward")
 
 
 def header_symbols(header: Path | None = None):

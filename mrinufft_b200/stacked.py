@@ -4,8 +4,9 @@ Mirror of ``MRIStackedNUFFT`` / ``MRIStackedNUFFTGPU`` (``src/mrinufft/operators
 360-837``): a 3-D acquisition that repeats one 2-D trajectory on a set of Cartesian kz planes is
 ``FFT along z`` followed by one 2-D NUFFT per plane.  The planes of all coils are "virtual coils" of one
 2-D b200 operator (``n_coils = C * len(z_index)``), so a single library call transforms up to 32
-planes; the z transform (``torch.fft``: cuFFT, a plain library FFT over contiguous rows), the
-sensitivity-map multiply and the plane selection stay on the device.  The reference's generic class does the
+planes.  The z transform is the library's own kernel (``csrc/stack_fftz.cu``, any length Z): sensitivity-map
+multiply, both centring shifts, the FFT, the kz-plane selection and the (coil, stack)-major plane layout are
+one pass per direction, the SENSE coil sum of the adjoint included.  The reference's generic class does the
 same arithmetic through host numpy arrays (``get_operator("stacked-<x>")``, ``base.py:151-158``).
 """
 
@@ -16,6 +17,7 @@ import torch
 
 from mrinufft.operators.stacked import MRIStackedNUFFT
 
+from . import _lib
 from ._arrays import to_device
 from .operator import MRIB200NUFFT, _copy_into
 
@@ -33,6 +35,7 @@ class MRIB200StackedNUFFT(MRIStackedNUFFT):
         super().__init__(samples, shape, "b200", smaps, z_index=z_index, n_coils=n_coils,
                          n_batchs=n_batchs, squeeze_dims=squeeze_dims, **kwargs)
         self._smaps_dev = None
+        self._zsel_dev = None
 
     # ------------------------------------------------------------------ helpers
     @property
@@ -47,32 +50,34 @@ class MRIB200StackedNUFFT(MRIStackedNUFFT):
                                .reshape(self.n_coils, *self.shape))
         return self._smaps_dev[1]
 
-    @staticmethod
-    def _fftz_d(x):  # stacked.py:177-185 (`_fftz`): centred, orthonormal, and the reference's 1/sqrt(2)
-        y = torch.fft.fftshift(torch.fft.fft(torch.fft.ifftshift(x, dim=-1), dim=-1, norm="ortho"), dim=-1)
-        return y * float(1.0 / np.sqrt(2.0))
-
-    @staticmethod
-    def _ifftz_d(x):  # stacked.py:187-195
-        y = torch.fft.fftshift(torch.fft.ifft(torch.fft.ifftshift(x, dim=-1), dim=-1, norm="ortho"), dim=-1)
-        return y * float(1.0 / np.sqrt(2.0))
-
     def _zsel(self):
-        return torch.as_tensor(np.asarray(self.z_index), device=self._dev, dtype=torch.long)
+        zi = np.asarray(self.z_index)
+        if self._zsel_dev is None or self._zsel_dev[0] is not self.z_index:
+            if zi.ndim != 1 or zi.min() < 0 or zi.max() >= self.shape[-1] or len(np.unique(zi)) != len(zi):
+                raise ValueError("z_index must hold distinct plane indices in [0, shape[-1])")
+            self._zsel_dev = (self.z_index, torch.as_tensor(zi.astype(np.int32), device=self._dev))
+        return self._zsel_dev[1]
+
+    def _fftz_call(self, adjoint, src, dst):
+        """One launch of the fused z transform (`b200_stack_fftz_forward` / `_adjoint`): `_fftz` / `_ifftz` of
+        stacked.py:178-195 (centred, orthonormal, and the reference's 1/sqrt(2)) with everything around them."""
+        X, Y, Z = self.shape
+        sm = self._smaps_d()
+        with torch.cuda.device(self._dev):
+            _lib.stack_fftz(adjoint, src.data_ptr(), sm.data_ptr() if sm is not None else None, dst.data_ptr(),
+                            self._zsel().data_ptr(), self.n_coils, X, Y, Z, len(self.z_index),
+                            1.0 / np.sqrt(2.0 * Z), torch.cuda.current_stream(self._dev).cuda_stream)
 
     # ------------------------------------------------------------------ device transforms
     def _op_device(self, img: torch.Tensor) -> torch.Tensor:
         """(B, 1|C, X, Y, Z) -> (B, C, NZ * NS)   (stacked.py:197-240)."""
         B, C, XYZ = self.n_batchs, self.n_coils, self.shape
         NS, NZ = len(self._samples2d), len(self.z_index)
-        zsel = self._zsel()
         ksp = torch.empty((B, C * NZ, NS), dtype=self.operator._cdt, device=self._dev)
-        sm = self._smaps_d()
-        img = img.reshape(B, 1 if sm is not None else C, *XYZ)
+        img = img.reshape(B, 1 if self.smaps is not None else C, *XYZ).contiguous()
+        planes = torch.empty((1, C * NZ, *XYZ[:2]), dtype=self.operator._cdt, device=self._dev)
         for b in range(B):
-            coil = img[b] * sm if sm is not None else img[b]            # (C, X, Y, Z)
-            kz = self._fftz_d(coil).index_select(-1, zsel)               # (C, X, Y, NZ)
-            planes = kz.permute(0, 3, 1, 2).reshape(1, C * NZ, *XYZ[:2]).contiguous()
+            self._fftz_call(False, img[b], planes)
             ksp[b] = self.operator._op_device(planes)[0]
         return ksp.reshape(B, C, NZ * NS)
 
@@ -80,16 +85,12 @@ class MRIB200StackedNUFFT(MRIStackedNUFFT):
         """(B, C, NZ * NS) -> (B, 1|C, X, Y, Z)   (stacked.py:254-305)."""
         B, C, XYZ = self.n_batchs, self.n_coils, self.shape
         NS, NZ = len(self._samples2d), len(self.z_index)
-        zsel = self._zsel()
-        sm = self._smaps_d()
         ksp = ksp.reshape(B, C * NZ, NS)
-        out = torch.empty((B, 1 if sm is not None else C, *XYZ), dtype=self.operator._cdt, device=self._dev)
+        out = torch.empty((B, 1 if self.smaps is not None else C, *XYZ), dtype=self.operator._cdt,
+                          device=self._dev)
         for b in range(B):
-            planes = self.operator._adj_device(ksp[b:b + 1].contiguous())  # (1, C*NZ, X, Y)
-            imgz = torch.zeros((C, *XYZ), dtype=self.operator._cdt, device=self._dev)
-            imgz.index_copy_(-1, zsel, planes.reshape(C, NZ, *XYZ[:2]).permute(0, 2, 3, 1))
-            imgc = self._ifftz_d(imgz)
-            out[b] = torch.sum(imgc * torch.conj(sm), dim=0, keepdim=True) if sm is not None else imgc
+            planes = self.operator._adj_device(ksp[b:b + 1].contiguous()).contiguous()  # (1, C*NZ, X, Y)
+            self._fftz_call(True, planes, out[b])
         return out
 
     # ------------------------------------------------------------------ public API

@@ -1145,6 +1145,58 @@ def test_field_map_autograd_through_the_batched_orc_operator(mods, C, sense):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("Z,Y,C", [(1, 5, 2), (2, 16, 1), (12, 24, 3), (15, 17, 2), (22, 40, 2), (49, 16, 1),
+                                    (64, 33, 4), (97, 8, 1), (176, 20, 2), (256, 32, 2), (512, 16, 1)])
+def test_stack_fftz_kernel_against_numpy(mods, Z, Y, C):
+    """`b200_stack_fftz_forward` / `_adjoint` (csrc/stack_fftz.cu) for lengths with every kind of factor
+    (powers of 4 and 2, 3, 5, 7, the direct-DFT primes 11 and 97, Z = 1), ragged y tiles, with and without
+    sensitivity maps, against `_fftz` / `_ifftz` of the reference (stacked.py:178-195) on float64 numpy."""
+    _, mb, torch = mods
+    from mrinufft_b200 import _lib
+
+    rng = np.random.default_rng(Z * 131 + Y)
+    X = 3
+    zsel = np.sort(rng.choice(Z, size=max(1, (2 * Z) // 3), replace=False)).astype(np.int32)
+    NZ = len(zsel)
+    cplx = lambda *sh: (rng.standard_normal(sh) + 1j * rng.standard_normal(sh)).astype(np.complex64)
+    fz = lambda a: np.fft.fftshift(np.fft.fft(np.fft.ifftshift(a, axes=-1), axis=-1, norm="ortho"), axes=-1) / np.sqrt(2)
+    ifz = lambda a: np.fft.fftshift(np.fft.ifft(np.fft.ifftshift(a, axes=-1), axis=-1, norm="ortho"), axes=-1) / np.sqrt(2)
+    smaps = cplx(C, X, Y, Z)
+    zs_d = torch.from_numpy(zsel).cuda()
+    scale = 1.0 / np.sqrt(2.0 * Z)
+    for sense in (False, True):
+        img = cplx(1 if sense else C, X, Y, Z)
+        sm_d = torch.from_numpy(smaps).cuda() if sense else None
+        planes_d = torch.full((C * NZ, X, Y), float("nan"), dtype=torch.complex64, device="cuda")
+        _lib.stack_fftz(False, torch.from_numpy(img).cuda().data_ptr(), sm_d.data_ptr() if sense else None,
+                        planes_d.data_ptr(), zs_d.data_ptr(), C, X, Y, Z, NZ, scale,
+                        torch.cuda.current_stream().cuda_stream)
+        coil = img.astype(np.complex128) * smaps if sense else img.astype(np.complex128)
+        want = np.moveaxis(fz(coil)[..., zsel], -1, 1).reshape(C * NZ, X, Y)
+        assert rel_l2(planes_d.cpu().numpy(), want) <= 1e-6
+        planes = cplx(C * NZ, X, Y)
+        out_d = torch.full((1 if sense else C, X, Y, Z), float("nan"), dtype=torch.complex64, device="cuda")
+        _lib.stack_fftz(True, torch.from_numpy(planes).cuda().data_ptr(), sm_d.data_ptr() if sense else None,
+                        out_d.data_ptr(), zs_d.data_ptr(), C, X, Y, Z, NZ, scale,
+                        torch.cuda.current_stream().cuda_stream)
+        kz = np.zeros((C, X, Y, Z), np.complex128)
+        kz[..., zsel] = np.moveaxis(planes.reshape(C, NZ, X, Y), 1, -1)
+        want = ifz(kz)
+        if sense:
+            want = np.sum(want * smaps.conj(), axis=0, keepdims=True)
+        assert rel_l2(out_d.cpu().numpy(), want) <= 1e-6
+
+
+@pytest.mark.gpu
+def test_stacked_b200_rejects_repeated_planes(mods):
+    mrinufft, _, _ = mods
+    traj2d = np.random.default_rng(0).uniform(-0.5, 0.5, (50, 2)).astype(np.float32)
+    op = mrinufft.get_operator("stacked-b200")(traj2d, (16, 16, 8), z_index=np.array([1, 1, 3]), n_coils=1)
+    with pytest.raises(ValueError, match="distinct"):
+        op.op(np.zeros((1, 1, 16, 16, 8), np.complex64))
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("sense", [False, True])
 def test_native_stacked_matches_generic_stacked(mods, sense):
     """`MRIB200StackedNUFFT` (device resident) against the reference's generic `MRIStackedNUFFT` driving the
