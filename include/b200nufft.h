@@ -204,6 +204,30 @@ int b200_stack_fftz_adjoint(const void* planes, const void* smaps, void* out, co
                             int C, int X, int Y, int Z, int NZ, float scale, void* stream);
 
 /*
+ * Vector updates of the iterative solvers, one pass over memory each: replace the array expressions of
+ * `lsqr` / `lsmr` / `cg` (src/mrinufft/extras/optim.py:402-446, 669-724, 866-883).  Vectors are device arrays
+ * of B x n complex64 (dbl = 0) or complex128 (dbl = 1) elements, batch-major; scalars are HOST arrays of B
+ * complex doubles (re, im interleaved; the imaginary part is ignored where the update is real); sums are
+ * DEVICE arrays of doubles, overwritten.  `out` may alias an input.
+ *   axpby      out = a x + b y  (y NULL: out = a x);  sumsq (NULL or [B]) = ||out_b||^2
+ *   cg_dots    out5 [B][5] = { ||gnew||^2, Re, Im sum gnew (gnew - gold), Re, Im sum gold gold }  (no conjugates,
+ *              like `xp.dot`, optim.py:872-878)
+ *   cg_step    v = g + beta v ;  x = x + minus_inv_l v
+ *   lsqr_step  sumsq_w [B] = ||w_b||^2 of the incoming w ;  x += t1 w ;  w = v + t2 w
+ *   lsmr_step  hbar = h + a hbar ;  x += b hbar ;  h = v + c h ;  sumsq_x [B] = ||x_b||^2 of the new x
+ */
+int b200_vec_axpby(void* out, const void* x, const void* y, const double* a, const double* b, int B,
+                   int64_t n, double* sumsq, int dbl, void* stream);
+int b200_vec_cg_dots(const void* gnew, const void* gold, int B, int64_t n, double* out5, int dbl,
+                     void* stream);
+int b200_vec_cg_step(void* x, void* v, const void* g, const double* beta, const double* minus_inv_l,
+                     int B, int64_t n, int dbl, void* stream);
+int b200_vec_lsqr_step(void* x, void* w, const void* v, const double* t1, const double* t2, int B,
+                       int64_t n, double* sumsq_w, int dbl, void* stream);
+int b200_vec_lsmr_step(void* x, void* hbar, void* h, const void* v, const double* a, const double* b,
+                       const double* c, int B, int64_t n, double* sumsq_x, int dbl, void* stream);
+
+/*
  * Counters for bench.py: number of kernels this library launched and number of cuFFT
  * executions since the last reset (process wide).
  */

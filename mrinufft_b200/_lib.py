@@ -63,6 +63,26 @@ _SIGNATURES = {
     "b200_plan_rows_class": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int64)]),
     "b200_plan_last_timings": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
     "b200_plan_enable_timing": (C.c_int, [C.c_void_p, C.c_int]),
+    "b200_vec_axpby": (
+        C.c_int,
+        [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_int,
+         C.c_void_p],
+    ),
+    "b200_vec_cg_dots": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_int, C.c_void_p]),
+    "b200_vec_cg_step": (
+        C.c_int,
+        [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_void_p],
+    ),
+    "b200_vec_lsqr_step": (
+        C.c_int,
+        [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_int,
+         C.c_void_p],
+    ),
+    "b200_vec_lsmr_step": (
+        C.c_int,
+        [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int64,
+         C.c_void_p, C.c_int, C.c_void_p],
+    ),
     "b200_stack_fftz_forward": (
         C.c_int,
         [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,

@@ -4,7 +4,10 @@ The reference's solvers (``src/mrinufft/extras/optim.py``: ``lsqr`` 249-495, ``l
 801-902) run through ``with_numpy_cupy``: without cupy every ``op`` / ``adj_op`` of every iteration is
 a host round trip of the whole k-space batch.  Here the iterates, the k-space data and all vector
 updates stay on the device; only the per-batch scalars (a handful of floats per iteration) come to
-the host, where the Givens-rotation recurrences run in numpy exactly as in the reference.
+the host, where the Givens-rotation recurrences run in numpy exactly as in the reference.  The vector
+updates of an iteration are the library's fused kernels (``csrc/vecops.cu``: one pass over memory per group
+of updates that read the same vectors, the norms / dot products accumulated in double on the way) -- e.g. the
+whole image-domain update of an ``lsqr`` iteration, ``||w||``, ``x += t1 w``, ``w = v + t2 w``, is one launch.
 
 Iterate-level parity is the contract (tests/test_solvers_cpu.py compares iterate by iterate against
 the reference on its exact-NDFT backend), so the reference's quirks are kept:
@@ -32,6 +35,7 @@ import contextlib
 import numpy as np
 import torch
 
+from . import _lib
 from ._arrays import describe, from_device, to_device
 
 
@@ -74,16 +78,99 @@ class _Ctx:
     def out(self, x):
         return from_device(x, self.kind, self.kdev)
 
+    # ---- vector updates: the library's fused kernels on the device (csrc/vecops.cu).  CPU tensors only occur
+    # with the stand-in operators of the host-logic tests (tests/test_solvers_cpu.py, test_dist_cpu.py), which
+    # have no CUDA device: there the same updates are written with torch.
+    def _scal(self, v, B):
+        """(B,) complex scalars as interleaved doubles for the C ABI."""
+        a = np.ascontiguousarray(np.broadcast_to(np.asarray(v, dtype=np.complex128), (B,)))
+        return a, a.ctypes.data
+
+    def _launch(self, fn, vecs, scalars, nred, red_arg=True):
+        t0 = vecs[0]
+        B, n = t0.shape[0], t0[0].numel()
+        for t in vecs:
+            assert t is None or (t.is_contiguous() and t.dtype == self.cdt and t.numel() == B * n)
+        red = torch.empty((B, nred), dtype=torch.float64, device=t0.device) if nred else None
+        keep = [self._scal(v, B) for v in scalars]
+        args = [t.data_ptr() if t is not None else None for t in vecs] + [k[1] for k in keep] + [B, n]
+        if red_arg:
+            args.append(red.data_ptr() if nred else None)
+        args += [int(self.cdt == torch.complex128), torch.cuda.current_stream(t0.device).cuda_stream]
+        with torch.cuda.device(t0.device):
+            _lib.check(getattr(_lib.load(), fn)(*args), fn)
+        return red
+
+    def _host_norm(self, sq, reduce):
+        return np.sqrt(reduce(sq).cpu().numpy().astype(self.rnp))
+
     # per-batch 2-norms (optim.py:57-58) as a host (B,) array of the operator's real precision
     def _norm(self, t, reduce):
+        if t.is_cuda:
+            t = t.reshape(t.shape[0], -1)
+            return self._host_norm(self._launch("b200_vec_cg_dots", [t, t], [], 5)[:, 0], reduce)
         sq = torch.sum(t.real.reshape(t.shape[0], -1) ** 2 + t.imag.reshape(t.shape[0], -1) ** 2, dim=1)
-        return np.sqrt(reduce(sq).cpu().numpy().astype(self.rnp))
+        return self._host_norm(sq, reduce)
 
     def knorm(self, t):
         return self._norm(t, self.reduce_ksp)
 
     def inorm(self, t):
         return self._norm(t, self.reduce_img)
+
+    def axpby(self, out, a, x, b=None, y=None, norm=None):
+        """``out = a x + b y`` with per-batch real scalars (``out`` may be ``x`` or ``y``); with ``norm`` =
+        "ksp" / "img" the per-batch 2-norms of the result come back as a host array."""
+        reduce = {None: None, "ksp": self.reduce_ksp, "img": self.reduce_img}[norm]
+        if out.is_cuda:
+            sq = self._launch("b200_vec_axpby", [out, x, y], [a, 0.0 if b is None else b], 1 if norm else 0)
+            return self._host_norm(sq[:, 0], reduce) if norm else None
+        r = self.bc(a, x) * x
+        if y is not None:
+            r = r + self.bc(b, y) * y
+        out.copy_(r)
+        return self._norm(out, reduce) if norm else None
+
+    def cg_dots(self, gn, g):
+        """``(||gn||^2, sum gn (gn - g), sum g g)`` over the whole batch, un-conjugated products as ``xp.dot``
+        (optim.py:866-880), summed over ranks where the image is sharded."""
+        if gn.is_cuda:
+            d = self.reduce_img(self._launch("b200_vec_cg_dots", [gn, g], [], 5).sum(dim=0)).cpu().numpy()
+            return float(d[0]), complex(d[1], d[2]), complex(d[3], d[4])
+        a, b = gn.flatten(), g.flatten()
+        _sum = self.reduce_img
+        return (float(_sum(torch.sum(a.real ** 2 + a.imag ** 2))), complex(_sum(torch.sum(a * (a - b))).item()),
+                complex(_sum(torch.sum(b * b)).item()))
+
+    def cg_step(self, x, v, g, beta, lipschitz):
+        """``v = g + beta v ; x = x - v / L`` in place (optim.py:881-883)."""
+        if x.is_cuda:
+            self._launch("b200_vec_cg_step", [x, v, g], [beta, -1.0 / lipschitz], 0, red_arg=False)
+            return
+        v.copy_(g + beta * v)
+        x.sub_(v / lipschitz)
+
+    def lsqr_step(self, x, w, v, t1, t2):
+        """``||w||`` (of the incoming ``w``), then ``x += t1 w ; w = v + t2 w`` in place (optim.py:441-446)."""
+        if x.is_cuda:
+            return self._host_norm(self._launch("b200_vec_lsqr_step", [x, w, v], [t1, t2], 1)[:, 0], self.reduce_img)
+        nw = self.inorm(w)
+        x += self.bc(t1, w) * w
+        w *= self.bc(t2, w)
+        w += v
+        return nw
+
+    def lsmr_step(self, x, hbar, h, v, a, b, c):
+        """``hbar = h + a hbar ; x += b hbar ; h = v + c h`` in place, returns ``||x||`` (optim.py:716-724, 760)."""
+        if x.is_cuda:
+            return self._host_norm(self._launch("b200_vec_lsmr_step", [x, hbar, h, v], [a, b, c], 1)[:, 0],
+                                   self.reduce_img)
+        hbar *= self.bc(a, hbar)
+        hbar += h
+        x += self.bc(b, hbar) * hbar
+        h *= self.bc(c, h)
+        h += v
+        return self.inorm(x)
 
     # host (B,) scalars -> device tensor that broadcasts from the left (``_bc_left``, optim.py:68-86)
     def bc(self, s, like):
@@ -142,20 +229,19 @@ class _Bidiag:
 
     def __init__(self, ctx: _Ctx, x0_d):
         self.c = ctx
-        self.u = ctx.y.clone()
+        self.u = ctx.y.clone(memory_format=torch.contiguous_format)
         self.bnorm = ctx.knorm(self.u)
         self.beta = self.bnorm.copy()
         if x0_d is not None:
-            self.u -= ctx.A(x0_d)
-            self.beta = ctx.knorm(self.u)
+            self.beta = ctx.axpby(self.u, 1.0, self.u, -1.0, ctx.A(x0_d).contiguous(), norm="ksp")
         self.v = None
         self.alpha = None
 
     def start(self, x):
         c = self.c
         if np.all(self.beta) > 0:
-            self.u /= c.bc(self.beta, self.u)
-            self.v = c.AH(self.u)
+            c.axpby(self.u, 1 / self.beta, self.u)
+            self.v = c.AH(self.u).contiguous()
             self.alpha = c.inorm(self.v)
         else:
             self.v = x.clone()
@@ -163,36 +249,32 @@ class _Bidiag:
         if np.any((self.alpha * self.beta) == 0):
             return False
         if np.all(self.alpha) > 0:
-            self.v /= c.bc(self.alpha, self.v)
+            c.axpby(self.v, 1 / self.alpha, self.v)
         return True
 
     def step(self):
         """Next pair of Lanczos vectors.  Returns True when the ``beta > 0`` branch ran."""
         c = self.c
-        self.u *= -c.bc(self.alpha, self.u)
-        self.u += c.A(self.v)
-        self.beta = c.knorm(self.u)
+        self.beta = c.axpby(self.u, 1.0, c.A(self.v).contiguous(), -self.alpha, self.u, norm="ksp")
         if not (np.all(self.beta) > 0):
             return False
-        self.u /= c.bc(self.beta, self.u)
+        c.axpby(self.u, 1 / self.beta, self.u)
         return True
 
     def step_v(self):
         c = self.c
-        self.v *= -c.bc(self.beta, self.v)
-        self.v += c.AH(self.u)
-        self.alpha = c.inorm(self.v)
+        self.alpha = c.axpby(self.v, 1.0, c.AH(self.u).contiguous(), -self.beta, self.v, norm="img")
         if np.all(self.alpha) > 0:
-            self.v /= c.bc(self.alpha, self.v)
+            c.axpby(self.v, 1 / self.alpha, self.v)
 
 
 def _initial_iterate(ctx: _Ctx, x0, x_init):
     """(x, x0_d): the starting image (a fresh device tensor) and the regularisation centre."""
     x0_d = None if x0 is None else ctx.image(x0)
     if x_init is not None:
-        x = ctx.image(x_init).clone()
+        x = ctx.image(x_init).clone(memory_format=torch.contiguous_format)
     elif x0_d is not None:
-        x = x0_d.clone()
+        x = x0_d.clone(memory_format=torch.contiguous_format)
     else:
         x = torch.zeros(ctx.full_img, dtype=ctx.cdt, device=ctx.dev)
     return x, x0_d
@@ -291,10 +373,7 @@ def lsqr(
             t2 = -theta / rho
 
             # x += (phi / rho) w ;  ||w / rho||^2 feeds the condition estimate ;  w = v - (theta / rho) w
-            ddnorm = ddnorm + (ctx.inorm(w) / np.abs(rho)) ** 2
-            x += ctx.bc(t1, w) * w
-            w *= ctx.bc(t2, w)
-            w += gk.v
+            ddnorm = ddnorm + (ctx.lsqr_step(x, w, gk.v, t1, t2) / np.abs(rho)) ** 2
 
             # rotation on the right: estimate of ||x||
             delta = sn2 * rho
@@ -397,11 +476,8 @@ def lsmr(
 
             # hbar = h - (thetabar rho / (rhoold rhobarold)) hbar ;  x += (zeta / (rho rhobar)) hbar ;
             # h = v - (thetanew / rho) h
-            hbar *= ctx.bc(-(thetabar * rho / (rhoold * rhobarold)), hbar)
-            hbar += h
-            x += ctx.bc(zeta / (rho * rhobar), hbar) * hbar
-            h *= ctx.bc(-(thetanew / rho), h)
-            h += gk.v
+            normx = ctx.lsmr_step(x, hbar, h, gk.v, -(thetabar * rho / (rhoold * rhobarold)), zeta / (rho * rhobar),
+                                  -(thetanew / rho))
 
             # estimate of ||r||: rotations Qhat_{k,2k+1}, Q_{k,k+1}, Qtilde_{k-1}
             betaacute = chat * betadd
@@ -428,7 +504,6 @@ def lsmr(
             condA = np.mean(np.maximum(maxrbar, rhotemp) / rhotemp)
 
             normar = np.abs(zetabar)
-            normx = ctx.inorm(x)
             test1 = normr / normb
             test2 = normar / (normA * normr) if np.all((normA * normr) != 0) else np.inf
             test3 = 1 / condA
@@ -466,8 +541,6 @@ def cg(
     y, cdt, dev = ctx.y, ctx.cdt, ctx.dev
     if lipschitz_cst is None:
         lipschitz_cst = float(operator.get_lipschitz_cst())
-    _sum = ctx.reduce_img
-
     xi = None if x_init is None else ctx.image(x_init)
     with contextlib.ExitStack() as stack:
         if operator.uses_density:
@@ -485,24 +558,21 @@ def cg(
                 g = g + damp * (img - x0_d) if x0_d is not None else g + damp * img
             return g
 
-        grad = _grad(image)
-        velocity = tol * velocity + grad / lipschitz_cst
-        image = image - velocity
+        grad = _grad(image).contiguous()
+        velocity = (tol * velocity + grad / lipschitz_cst).contiguous()
+        image = (image - velocity).contiguous()
         callbacks_results = []
         for _ in range(max_iter):
-            grad_new = _grad(image)
-            gnorm = torch.sqrt(_sum(torch.sum(grad_new.real**2 + grad_new.imag**2)))
-            if float(gnorm) <= tol:
+            grad_new = _grad(image).contiguous()
+            gsq, num, den = ctx.cg_dots(grad_new, grad)
+            if np.sqrt(gsq) <= tol:
                 break
-            gn, g = grad_new.flatten(), grad.flatten()
-            num = _sum(torch.sum(gn * (gn - g)))  # un-conjugated dot, as xp.dot
-            den = _sum(torch.sum(g * g))
-            beta = _lex_max0(complex((num / den).item()))
-            velocity = grad_new + beta * velocity
-            image = image - velocity / lipschitz_cst
+            with np.errstate(all="ignore"):
+                beta = _lex_max0(complex(np.complex128(num) / np.complex128(den)))
+            ctx.cg_step(image, velocity, grad_new, beta, lipschitz_cst)
             grad = grad_new
             if callback:
-                callbacks_results.append(callback(ctx.out(image), operator, kspace_data, damp=damp, x0=x0))
+                callbacks_results.append(callback(ctx.out(image.clone()), operator, kspace_data, damp=damp, x0=x0))
     return _finish(ctx, image, callbacks_results)
 
 

@@ -407,6 +407,63 @@ def test_host_arrays_in_several_chunks_are_pipelined_and_equal_the_device_path(m
     assert op1.op(xs).shape == (C, M) and op1.adj_op(y0[0]).shape == (shape if sense else (C, *shape))
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,n,dbl", [(1, 1, False), (3, 1001, False), (40, 777, False), (2, 300001, True)])
+def test_solver_vector_kernels_against_numpy(mods, B, n, dbl):
+    """`b200_vec_*` (csrc/vecops.cu) through the solver context's wrappers against the array expressions of
+    optim.py they replace, in float64 numpy: results and the accumulated norms / dot products; more batches
+    than one launch carries scalars for (40 > 32), a length that is not a multiple of anything."""
+    _, mb, torch = mods
+    from mrinufft_b200.solvers import _Ctx
+
+    rng = np.random.default_rng(B * 7 + n)
+    cdt, npc = (torch.complex128, np.complex128) if dbl else (torch.complex64, np.complex64)
+    ctx = _Ctx.__new__(_Ctx)
+    ctx.cdt, ctx.rnp = cdt, (np.float64 if dbl else np.float32)
+    ctx.reduce_ksp = ctx.reduce_img = lambda v: v
+    vec = lambda: (rng.standard_normal((B, n)) + 1j * rng.standard_normal((B, n))).astype(npc)
+    dev = lambda a: torch.from_numpy(a.copy()).cuda()
+    sc = lambda: rng.standard_normal(B)
+    tol = 1e-12 if dbl else 2e-6
+    col = lambda a: np.asarray(a)[:, None]
+    nrm = lambda a: np.linalg.norm(a.astype(np.complex128), axis=1)
+
+    x, y, a, b = vec(), vec(), sc(), sc()
+    out = dev(x)
+    got = ctx.axpby(out, a, out, b, dev(y), norm="ksp")
+    want = col(a) * x.astype(np.complex128) + col(b) * y
+    assert rel_l2(out.cpu().numpy(), want) <= tol and np.allclose(got, nrm(want), rtol=tol * 10)
+    out = dev(x)
+    assert ctx.axpby(out, 1 / a, out) is None and rel_l2(out.cpu().numpy(), x / col(a)) <= tol
+    assert np.allclose(ctx.inorm(dev(x)), nrm(x), rtol=tol * 10)
+
+    gsq, num, den = ctx.cg_dots(dev(x), dev(y))
+    xd, yd = x.astype(np.complex128).ravel(), y.astype(np.complex128).ravel()
+    assert np.isclose(gsq, np.vdot(xd, xd).real, rtol=1e-10)
+    assert np.isclose(num, np.dot(xd, xd - yd), rtol=1e-9, atol=1e-9 * n * B)
+    assert np.isclose(den, np.dot(yd, yd), rtol=1e-9, atol=1e-9 * n * B)
+
+    xi, v, g, beta, L = vec(), vec(), vec(), complex(0.3, -0.2), 1.7
+    xt, vt = dev(xi), dev(v)
+    ctx.cg_step(xt, vt, dev(g), beta, L)
+    vn = g.astype(np.complex128) + beta * v
+    assert rel_l2(vt.cpu().numpy(), vn) <= tol and rel_l2(xt.cpu().numpy(), xi - vn / L) <= tol
+
+    xi, w, v, t1, t2 = vec(), vec(), vec(), sc(), sc()
+    xt, wt = dev(xi), dev(w)
+    got = ctx.lsqr_step(xt, wt, dev(v), t1, t2)
+    assert np.allclose(got, nrm(w), rtol=tol * 10)
+    assert rel_l2(xt.cpu().numpy(), xi + col(t1) * w) <= tol and rel_l2(wt.cpu().numpy(), v + col(t2) * w) <= tol
+
+    xi, hb, h, v, a, b, c = vec(), vec(), vec(), vec(), sc(), sc(), sc()
+    xt, hbt, ht = dev(xi), dev(hb), dev(h)
+    got = ctx.lsmr_step(xt, hbt, ht, dev(v), a, b, c)
+    hbn = h.astype(np.complex128) + col(a) * hb
+    xn = xi + col(b) * hbn
+    assert rel_l2(hbt.cpu().numpy(), hbn) <= tol and rel_l2(xt.cpu().numpy(), xn) <= tol
+    assert rel_l2(ht.cpu().numpy(), v + col(c) * h) <= tol and np.allclose(got, nrm(xn), rtol=tol * 10)
+
+
 # ------------------------------------------------------------------ solvers
 def test_cg_matches_reference_golden(mods):
     mrinufft, _, _ = mods
