@@ -91,6 +91,10 @@ struct Cls {
   static constexpr int EU = ESZ / 16;                                                // ... in uint4 units
   static constexpr int IS_OFF = GENERIC ? 0 : 8;                                     // byte offset of {idx, s}
   static constexpr int PKT = 32 + ESZ;                                               // staged packet: P0..P3 | entry
+  // PROD: the entry has room for the 2 G row scales wy[2 gy + r] wz[gz] themselves (3-D class 16, the 2-D
+  // classes, whose z weight is 1): a lane loads its pair instead of forming it (one load and two multiplies
+  // less per visit); entry = {idx, s, p[gz GY + gy][r]}
+  static constexpr bool PROD = GENERIC && 8 + 8 * G <= ESZ;
   static constexpr int WY_OFF = 32 + 8;                                              // packet offsets of the windows
   static constexpr int WZ_OFF = 32 + 8 + 4 * TY;
   static constexpr int SB = TC >= 16 ? 16 : 32;      // visits per value block of the spreader (cp.async granularity)
@@ -301,21 +305,34 @@ __device__ __forceinline__ void write_entry(const Geom& g, const TileCoord& rc, 
     for (int i = 0; i < C::EU * 4; ++i) wd[i] = 0u;
     wd[0] = idx;
     wd[1] = (unsigned)s;
+    float wyk[C::TY], wzk[C::GZ];
 #pragma unroll
     for (int k = 0; k < C::TY; ++k) {
       const int d = dy + k;
       const bool in = d >= 0 && d < W && rc.y + k < nfy;
-      wd[2 + k] = in ? __float_as_uint(r[R_WY + 1 + (in ? d : 0)]) : 0u;
+      wyk[k] = in ? r[R_WY + 1 + (in ? d : 0)] : 0.f;
     }
 #pragma unroll
     for (int k = 0; k < C::GZ; ++k) {
       if (DIM == 3) {
         const int d = zs - (C::GZ - 1) + k;
         const bool in = d >= 0 && d < W && rc.z + k < g.nf[0];
-        wd[2 + C::TY + k] = in ? __float_as_uint(r[R_WZ + (in ? d : 0)]) : 0u;
+        wzk[k] = in ? r[R_WZ + (in ? d : 0)] : 0.f;
       } else {
-        wd[2 + C::TY + k] = __float_as_uint(1.f);
+        wzk[k] = 1.f;
       }
+    }
+    if constexpr (C::PROD) {
+#pragma unroll
+      for (int q = 0; q < C::G; ++q) {
+        wd[2 + 2 * q] = __float_as_uint(wyk[2 * (q % C::GY)] * wzk[q / C::GY]);   // q = row group of a lane
+        wd[3 + 2 * q] = __float_as_uint(wyk[2 * (q % C::GY) + 1] * wzk[q / C::GY]);
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < C::TY; ++k) wd[2 + k] = __float_as_uint(wyk[k]);
+#pragma unroll
+      for (int k = 0; k < C::GZ; ++k) wd[2 + C::TY + k] = __float_as_uint(wzk[k]);
     }
 #pragma unroll
     for (int q = 0; q < C::EU; ++q) dst[q] = make_uint4(wd[4 * q], wd[4 * q + 1], wd[4 * q + 2], wd[4 * q + 3]);
@@ -594,7 +611,7 @@ k_rows(Geom g, int T, int nchunks, unsigned S, long long M, const uint4* __restr
   asm volatile("" : "+l"(ktl));
   // class < 32: this lane's row group and the packet offsets of its window entries
   const int grp = lane / TC, gyi = grp % C::GY, gzi = grp / C::GY;
-  const unsigned yo = (unsigned)(C::WY_OFF + 8 * gyi), zo = (unsigned)(C::WZ_OFF + 4 * gzi);
+  const unsigned yo = (unsigned)(C::WY_OFF + 8 * (C::PROD ? grp : gyi)), zo = (unsigned)(C::WZ_OFF + 4 * gzi);
 
   const int nfx = g.nf[DIM - 1];
   const int nfy = g.nf[DIM - 2];

@@ -20,6 +20,8 @@ GZ planes of a larger tile, so a point visits fewer tiles and no lane idles for 
 A visit is staged in shared memory as a packet (read with warp-broadcast loads)
     TC = 32 (48 bytes):  P_0..P_3 | s0, s1, idx, s
     TC < 32 (32 + ESZ):  P_0..P_3 | idx, s | wy[2 GY] | wz[GZ] | padding
+    (TC < 32 with room in the entry -- 3-D class 16, the 2-D classes: the 2 G products wy[2 gy + r] wz[gz]
+     take the place of the windows and a lane loads its pair s_0, s_1 directly)
         P_q      pair-packed x weights, P_q = (w[2q - par], w[2q + 1 - par]), par = x offset & 1
         s0, s1   row scales wy[dy] wz[dz], wy[dy + 1] wz[dz]; for TC < 32 a lane forms its own pair from
                  the windows: s_r = wy[2 gy + r] * wz[gz]  (zero outside the point's footprint)
@@ -74,6 +76,8 @@ class Layout:
         self.pkt = 32 + self.esz
         self.vstride = TC * 8
         self.generic = TC != 32
+        # the entry holds the lanes' row scales themselves (mirrors `Cls::PROD` in rows_common.cuh)
+        self.prod = self.generic and 8 + 8 * (32 // TC) <= self.esz
         self.obs = obuf_stride(TC)
 
 
@@ -89,8 +93,9 @@ def load_set(lay, X, k, pred, spread):
           f"{p}ld.shared.v2.b64 {{P{X}2, P{X}3}}, [pk+{off_pk + 16}];"]
     if lay.generic:
         L += [f"{p}ld.shared.v2.b32 {{i{X}, n{X}}}, [pk+{off_pk + 32}];",
-              f"{p}ld.shared.v2.b32 {{s{X}0, s{X}1}}, [pky+{off_pk}];",
-              f"{p}ld.shared.b32 z{X}, [pkz+{off_pk}];"]
+              f"{p}ld.shared.v2.b32 {{s{X}0, s{X}1}}, [pky+{off_pk}];"]
+        if not lay.prod:
+            L.append(f"{p}ld.shared.b32 z{X}, [pkz+{off_pk}];")
     else:
         L.append(f"{p}ld.shared.v4.b32 {{s{X}0, s{X}1, i{X}, n{X}}}, [pk+{off_pk + 32}];")
     if spread:
@@ -100,7 +105,7 @@ def load_set(lay, X, k, pred, spread):
 
 def lane_scales(lay, X):
     """TC < 32: the lane's two row scales from its window entries."""
-    if not lay.generic:
+    if not lay.generic or lay.prod:
         return []
     return [f"mul.f32 s{X}0, s{X}0, z{X};", f"mul.f32 s{X}1, s{X}1, z{X};"]
 
@@ -157,7 +162,7 @@ def interp_tail(lay, s0, s1, z, n, slot, S="S"):
     a red to k-space (class 32) or a store into the partial-sum buffer (smaller classes).  `s0, s1, z, n`:
     registers that hold the visit's scales / z window entry / point index."""
     L = []
-    if lay.generic:
+    if lay.generic and not lay.prod:
         L += [f"mul.f32 q0, {s0}, {z};", f"mul.f32 q1, {s1}, {z};"]
         s0, s1 = "q0", "q1"
     L += [f"mov.b64 A0, {{{s0}, {s0}}};", f"mov.b64 A1, {{{s1}, {s1}}};",
@@ -227,7 +232,7 @@ def gen_loop(W, spread, dim=3, TC=32):
     # -- the visit loops are half the size, which the instruction cache (32 KB) rewards.
     moves = [f"mov.b64 PA{q}, PB{q};" for q in range(4)] + ["mov.b32 sA0, sB0;", "mov.b32 sA1, sB1;",
                                                              "mov.b32 iA, iB;", "mov.b32 nA, nB;"]
-    if lay.generic:
+    if lay.generic and not lay.prod:
         moves.append("mov.b32 zA, zB;")
     if spread:
         moves.append("mov.b64 vA, vB;")
@@ -247,7 +252,7 @@ def gen_loop(W, spread, dim=3, TC=32):
             # because the block also reloads that set for the visit after next.
             body += taps_interp_sums(lay, W, X, c, "S")
             body += [f"setp.ne.u32 p2, i{Y}, {c};", "@p2 bra.uni TA;", "setp.lt.s32 p3, n, 3;",
-                     "mov.b32 e0, sA0;", "mov.b32 e1, sA1;", "mov.b32 e2, nA;"] + (["mov.b32 e3, zA;"] if lay.generic else [])
+                     "mov.b32 e0, sA0;", "mov.b32 e1, sA1;", "mov.b32 e2, nA;"] + (["mov.b32 e3, zA;"] if lay.generic and not lay.prod else [])
             body += load_set(lay, X, 2, "p3", spread)
             body += interp_tail(lay, "e0", "e1", "e3", "e2", 0, "S")
             body += taps_interp_sums(lay, W, Y, c, "U")
