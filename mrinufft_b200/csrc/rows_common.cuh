@@ -95,6 +95,10 @@ struct Cls {
   // classes, whose z weight is 1): a lane loads its pair instead of forming it (one load and two multiplies
   // less per visit); entry = {idx, s, p[gz GY + gy][r]}
   static constexpr bool PROD = GENERIC && 8 + 8 * G <= ESZ;
+  // DIRECT: every lane sends its partial sum to k-space itself (one red per lane and visit, like class 32)
+  // instead of parking it for a reduction over the row groups: with only two groups the second red is cheaper
+  // than the store, the re-reads and the extra pass (class 16: 15.5 -> see DESIGN 3.3)
+  static constexpr bool DIRECT = GENERIC && TC == 16;
   static constexpr int WY_OFF = 32 + 8;                                              // packet offsets of the windows
   static constexpr int WZ_OFF = 32 + 8 + 4 * TY;
   static constexpr int SB = TC >= 16 ? 16 : 32;      // visits per value block of the spreader (cp.async granularity)
@@ -946,7 +950,7 @@ k_rows(Geom g, int T, int nchunks, unsigned S, long long M, const uint4* __restr
           dirty = true;
           if (SPREAD) {
             rows_loop_spread<W, DIM, TC>(acc, pk_a + (unsigned)(k0 * PKT), k1 - k0, vb_a + (unsigned)(k0 * TC * 8), yo, zo);
-          } else if constexpr (!GEN) {
+          } else if constexpr (!GEN || C::DIRECT) {
             rows_loop_interp<W, DIM, TC>(acc, pk_a + (unsigned)(k0 * PKT), k1 - k0, ktl, 0u, yo, zo);
           } else {
             // class < 32: pieces of OBV visits; every lane parks its partial sums (this lane's coil, its

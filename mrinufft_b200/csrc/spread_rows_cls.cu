@@ -32,13 +32,21 @@ __device__ __forceinline__ void rows_loop_spread(u64 (&acc)[NACC], unsigned pk, 
   else ROWS_LOOP(spread, 4)(acc, pk, n, vb, yo, zo);
 }
 template <int W, int DIM, int TC>
-__device__ __forceinline__ void rows_loop_interp(u64 (&acc)[NACC], unsigned pk, int n, const void*, unsigned ob,
+__device__ __forceinline__ void rows_loop_interp(u64 (&acc)[NACC], unsigned pk, int n, const void* ktl, unsigned ob,
                                                  unsigned yo, unsigned zo) {
   static_assert(DIM == ROWS_DIM && TC == ROWS_TC, "one coil class per translation unit");
-  if (W == 7) ROWS_LOOP(interp, 7)(acc, pk, n, ob, yo, zo);
-  else if (W == 6) ROWS_LOOP(interp, 6)(acc, pk, n, ob, yo, zo);
-  else if (W == 5) ROWS_LOOP(interp, 5)(acc, pk, n, ob, yo, zo);
-  else ROWS_LOOP(interp, 4)(acc, pk, n, ob, yo, zo);
+  // class 16 adds to k-space through `ktl` like class 32 (Cls::DIRECT), the others park partial sums at `ob`
+#if ROWS_TC == 16
+#define ROWS_SINK ktl
+#else
+#define ROWS_SINK ob
+#endif
+  if (W == 7) ROWS_LOOP(interp, 7)(acc, pk, n, ROWS_SINK, yo, zo);
+  else if (W == 6) ROWS_LOOP(interp, 6)(acc, pk, n, ROWS_SINK, yo, zo);
+  else if (W == 5) ROWS_LOOP(interp, 5)(acc, pk, n, ROWS_SINK, yo, zo);
+  else ROWS_LOOP(interp, 4)(acc, pk, n, ROWS_SINK, yo, zo);
+  (void)ktl;
+  (void)ob;
 }
 }  // namespace rows
 

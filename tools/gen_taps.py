@@ -79,6 +79,10 @@ class Layout:
         # the entry holds the lanes' row scales themselves (mirrors `Cls::PROD` in rows_common.cuh)
         self.prod = self.generic and 8 + 8 * (32 // TC) <= self.esz
         self.obs = obuf_stride(TC)
+        # the row groups' partial sums go to k-space directly, one red per lane and visit like class 32
+        # (mirrors `Cls::DIRECT`): with two groups parking and re-reading them costs more than the second red
+        self.direct = self.generic and TC == 16
+        self.parked = self.generic and not self.direct
 
 
 def load_set(lay, X, k, pred, spread):
@@ -170,14 +174,14 @@ def interp_tail(lay, s0, s1, z, n, slot, S="S"):
           f"fma.rn.f32x2 {S}0, {S}2, A1, {S}0;", f"fma.rn.f32x2 {S}1, {S}3, A1, {S}1;",
           f"mov.b64 {{lo, hi}}, {S}0;", "add.f32 t0, lo, hi;",
           f"mov.b64 {{lo, hi}}, {S}1;", "add.f32 t1, lo, hi;"]
-    if lay.generic:
+    if lay.parked:
         # the G row groups of a coil each hold a partial sum: parked in shared memory ([visit][lane], rows of
         # `obuf_stride` bytes), summed and added to k-space by the kernel after the run (one compact loop
         # instead of shuffles + a predicated red in every tap-kernel case: the visit loops stay small
         # enough for the instruction cache)
         L += [f"st.shared.v2.f32 [ob+{slot * lay.obs}], {{t0, t1}};"]
     else:
-        L += [f"mad.wide.u32 addr, {n}, 256, ktl;",
+        L += [f"mad.wide.u32 addr, {n}, {lay.TC * 8}, ktl;",
               "red.global.add.v2.f32 [addr], {t0, t1};"]
     return L
 
@@ -207,7 +211,7 @@ def gen_loop(W, spread, dim=3, TC=32):
             s += [f"add.u32 pky, pky, {k * lay.pkt};", f"add.u32 pkz, pkz, {k * lay.pkt};"]
         if spread:
             s.append(f"add.u32 vb, vb, {k * lay.vstride};")
-        elif lay.generic:
+        elif lay.parked:
             s.append(f"add.u32 ob, ob, {k * lay.obs};")
         s.append(f"add.s32 n, n, -{k};")
         return s
@@ -219,7 +223,7 @@ def gen_loop(W, spread, dim=3, TC=32):
             "mov.u32 pk, %32;", "mov.u32 n, %33;"]
     if spread:
         body.append("mov.u32 vb, %34;")
-    elif lay.generic:
+    elif lay.parked:
         body.append("mov.u32 ob, %34;")
     else:
         body.append("mov.u64 ktl, %34;")
@@ -268,7 +272,7 @@ def gen_loop(W, spread, dim=3, TC=32):
         body += ["TA:"] + interp_tail(lay, "sA0", "sA1", "zA", "nA", 0, "S")
     body += ["XA:"] + step(1) + moves + ["bra.uni DA;"]
     body += ["DONE:", "}"]
-    args = "unsigned vb" if spread else ("unsigned ob" if lay.generic else "const void* ktl")
+    args = "unsigned vb" if spread else ("unsigned ob" if lay.parked else "const void* ktl")
     if lay.generic:
         args += ", unsigned yo, unsigned zo"
     L = [f"__device__ __forceinline__ void {name}(",
@@ -276,7 +280,7 @@ def gen_loop(W, spread, dim=3, TC=32):
          "  asm volatile("]
     L += [f'      "{b}\\n"' for b in body]
     L.append("      : " + ", ".join(f'"+l"(acc[{i}])' for i in range(32)))
-    ins = '"r"(pk), "r"(n), ' + ('"r"(vb)' if spread else ('"r"(ob)' if lay.generic else '"l"(ktl)'))
+    ins = '"r"(pk), "r"(n), ' + ('"r"(vb)' if spread else ('"r"(ob)' if lay.parked else '"l"(ktl)'))
     if lay.generic:
         ins += ', "r"(yo), "r"(zo)'
     L.append("      : " + ins)
