@@ -97,7 +97,8 @@ struct Cls {
   static constexpr bool PROD = GENERIC && 8 + 8 * G <= ESZ;
   // DIRECT: every lane sends its partial sum to k-space itself (one red per lane and visit, like class 32)
   // instead of parking it for a reduction over the row groups: with only two groups the second red is cheaper
-  // than the store, the re-reads and the extra pass (class 16: 15.5 -> see DESIGN 3.3)
+  // than the store, the re-reads and the extra pass (15.5 -> 13.3 ms at cfg-C geometry; with the four groups of
+  // class 8 the two ways cost the same, 8.9 ms, and parking keeps the L2 reduction traffic at a quarter)
   static constexpr bool DIRECT = GENERIC && TC == 16;
   static constexpr int WY_OFF = 32 + 8;                                              // packet offsets of the windows
   static constexpr int WZ_OFF = 32 + 8 + 4 * TY;

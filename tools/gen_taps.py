@@ -245,7 +245,7 @@ def gen_loop(W, spread, dim=3, TC=32):
              "tblA: .branchtargets " + ", ".join(f"RA{i}" for i in range(ncase)) + ";",
              "brx.idx.uni iA, tblA;"]
     # (class 32 only: 21.2 -> 20.5 ms at cfg-C; in the smaller classes the extra live registers spill)
-    defer = (not spread) and DEFER_INTERP_TAIL and not lay.generic
+    defer = (not spread) and DEFER_INTERP_TAIL and (not lay.generic or lay.TC == 16)
     for c in range(ncase):
         body += [f"RA{c}:", "setp.lt.s32 p1, n, 2;"]
         body += load_set(lay, Y, 1, "p1", spread)
