@@ -238,7 +238,9 @@ int b200_launch_count(int64_t* kernels, int64_t* ffts, int reset);
  *   key 0: spread method   (0 auto, 1 global-atomic point driven, 2 tiled)
  *   key 1: interp method   (0 auto, 1 point driven, 2 tiled)
  *   key 2: FFT method      (0 auto, 1 cuFFT + pad/crop kernels, 2 fused zero-padding-aware passes,
- *          3 the same with the tiles of the strided passes loaded by TMA bulk tensor copies)
+ *          3 the same with the tiles of the strided passes loaded by TMA bulk tensor copies,
+ *          4 pad/crop kernels + the library's own any-length FFT passes instead of cuFFT: every grid size,
+ *          complex64 and complex128)
  *   key 3: timing experiments on the tiled spreader (bit 0: skip the tile flush, bit 1: skip the
  *          coil-value copies; results are then wrong -- never set outside a profiling session;
  *          bit 3: pretend the visit stream does not fit 32-bit indices, which exercises the

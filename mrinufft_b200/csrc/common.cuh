@@ -73,6 +73,10 @@ struct Geom {
   long long Ntot;  // prod N
 };
 
+// fft_any.cu: unnormalised in-place FFT (sign < 0: exp(-i ...)) of T oversampled grids, any axis lengths
+int fft_any_c64(float2* fw, int T, const Geom& g, int sign, cudaStream_t st);
+int fft_any_c128(double2* fw, int T, const Geom& g, int sign, cudaStream_t st);
+
 // ---------------------------------------------------------------- the plan
 struct b200_plan {
   Geom g;

@@ -13,6 +13,8 @@
 // read-back and the Toeplitz entry point.
 #include <cmath>
 
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace {
@@ -336,6 +338,7 @@ PtArgs pt_args(DblState* ds) {
 }
 
 int fft_d(b200_plan* p, DblState* ds, int T, int sign, cudaStream_t st) {
+  if (p->fft_method == 4) return fft_any_c128(ds->d_fw, T, p->g, sign, st);  // own any-length passes (A/B, see api.cu)
   CUFFT_TRY(cufftSetStream(ds->fft, st));
   for (int t = 0; t < T; ++t) {
     cufftDoubleComplex* q = (cufftDoubleComplex*)(ds->d_fw + (long long)t * p->g.nftot);

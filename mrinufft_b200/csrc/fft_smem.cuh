@@ -1,0 +1,201 @@
+// fft_smem.cuh -- Stockham autosort FFT of ANY length on rows held in shared memory (complex64 or complex128).
+// Shared by stack_fftz.cu (z transform of the stacked operator) and fft_any.cu (grids that are not powers of
+// two, complex128 grids).  Radix 4 / 2 / 3 / 5 / 7 butterflies in registers, any other prime factor p as a direct
+// p-point DFT (O(p^2) per butterfly: only what the factorisation leaves); twiddles from one table
+// exp(-2 pi i t / L) computed in double on the host, once per (device, L, precision).
+#pragma once
+#include <cmath>
+#include <map>
+#include <mutex>
+#include <tuple>
+
+#include "common.cuh"
+
+namespace fftsm {
+
+constexpr int ZT = 256;      // threads per CTA
+constexpr int MAXRAD = 24;   // radices of a length < 2^24
+
+struct Radices {
+  int n;
+  int r[MAXRAD];
+};
+
+// what the stage loop needs to know about the rows
+struct Rows {
+  int Z;      // length
+  int rows;   // rows in the tile
+  int zp;     // row stride in elements (odd: row-fastest accesses spread over the banks)
+  Radices rad;
+};
+
+template <class V>
+struct RealOf;
+template <>
+struct RealOf<float2> {
+  typedef float type;
+};
+template <>
+struct RealOf<double2> {
+  typedef double type;
+};
+template <class V>
+__device__ __forceinline__ V mkc(typename RealOf<V>::type x, typename RealOf<V>::type y) {
+  V v;
+  v.x = x;
+  v.y = y;
+  return v;
+}
+template <class V>
+__device__ __forceinline__ V cmulf(V a, V b) {
+  return mkc<V>(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+template <class V>
+__device__ __forceinline__ V caddf(V a, V b) {
+  return mkc<V>(a.x + b.x, a.y + b.y);
+}
+template <class V>
+__device__ __forceinline__ V csubf(V a, V b) {
+  return mkc<V>(a.x - b.x, a.y - b.y);
+}
+// multiply by exp(-+ i pi / 2): -i forward, +i inverse
+template <bool INV, class V>
+__device__ __forceinline__ V rot90(V a) {
+  return INV ? mkc<V>(-a.y, a.x) : mkc<V>(a.y, -a.x);
+}
+
+// One Stockham stage of radix R on one row: butterfly (p, q), sub-length n = R m, stride s (s n = Z).
+//   y[q + s (R p + k)] = w_n^(p k) sum_j x[q + s (p + j m)] w_R^(j k),   w_L = tw[Z / L]
+template <int R, bool INV, class V>
+__device__ __forceinline__ void butterfly(const V* __restrict__ src, V* __restrict__ dst, const V* __restrict__ tw,
+                                          int p, int q, int s, int m, int Z) {
+  V a[R];
+#pragma unroll
+  for (int j = 0; j < R; ++j) a[j] = src[q + s * (p + j * m)];
+  V o[R];
+  if constexpr (R == 2) {
+    o[0] = caddf(a[0], a[1]);
+    o[1] = csubf(a[0], a[1]);
+  } else if constexpr (R == 4) {
+    const V t0 = caddf(a[0], a[2]), t1 = csubf(a[0], a[2]);
+    const V t2 = caddf(a[1], a[3]), t3 = rot90<INV>(csubf(a[1], a[3]));
+    o[0] = caddf(t0, t2);
+    o[1] = caddf(t1, t3);
+    o[2] = csubf(t0, t2);
+    o[3] = csubf(t1, t3);
+  } else {
+    V w[R];
+#pragma unroll
+    for (int j = 1; j < R; ++j) w[j] = tw[j * (Z / R)];
+#pragma unroll
+    for (int k = 0; k < R; ++k) {
+      V acc = a[0];
+#pragma unroll
+      for (int j = 1; j < R; ++j) {
+        const int e = (j * k) % R;  // compile time
+        if (e == 0) acc = caddf(acc, a[j]);
+        else acc = caddf(acc, cmulf(a[j], w[e]));
+      }
+      o[k] = acc;
+    }
+  }
+  const int t1 = p * s;  // p k s < Z for every k < R
+  V* d = dst + q + s * (R * p);
+  d[0] = o[0];
+#pragma unroll
+  for (int k = 1; k < R; ++k) d[s * k] = t1 ? cmulf(o[k], tw[t1 * k]) : o[k];
+}
+
+// any other (prime) radix: direct r-point DFT, inputs re-read from shared memory
+template <class V>
+__device__ __forceinline__ void butterfly_any(const V* __restrict__ src, V* __restrict__ dst, const V* __restrict__ tw,
+                                              int r, int p, int q, int s, int m, int Z) {
+  const int zr = Z / r;
+  for (int k = 0; k < r; ++k) {
+    V acc = src[q + s * p];
+    int e = 0;
+    for (int j = 1; j < r; ++j) {
+      e += k;
+      if (e >= r) e -= r;
+      acc = caddf(acc, cmulf(src[q + s * (p + j * m)], tw[e * zr]));
+    }
+    dst[q + s * (r * p + k)] = cmulf(acc, tw[p * k * s]);
+  }
+}
+
+// all stages on the rows of the tile (`tw` in shared memory, already conjugated for the inverse); returns the
+// buffer that holds the result (natural order).  Ends with a __syncthreads().
+template <bool INV, class V>
+__device__ __forceinline__ V* fft_rows(V* a, V* b, const V* tw, const Rows& g) {
+  int s = 1, n = g.Z;
+  for (int st = 0; st < g.rad.n; ++st) {
+    const int r = g.rad.r[st], m = n / r, nb = g.Z / r;
+    for (int i = threadIdx.x; i < g.rows * nb; i += ZT) {
+      const int row = i / nb, bf = i - row * nb, p = bf / s, q = bf - p * s;
+      const V* x = a + row * g.zp;
+      V* y = b + row * g.zp;
+      switch (r) {
+        case 2: butterfly<2, INV>(x, y, tw, p, q, s, m, g.Z); break;
+        case 3: butterfly<3, INV>(x, y, tw, p, q, s, m, g.Z); break;
+        case 4: butterfly<4, INV>(x, y, tw, p, q, s, m, g.Z); break;
+        case 5: butterfly<5, INV>(x, y, tw, p, q, s, m, g.Z); break;
+        case 7: butterfly<7, INV>(x, y, tw, p, q, s, m, g.Z); break;
+        default: butterfly_any(x, y, tw, r, p, q, s, m, g.Z); break;
+      }
+    }
+    __syncthreads();
+    V* t = a;
+    a = b;
+    b = t;
+    n = m;
+    s *= r;
+  }
+  return a;
+}
+
+// ---------------------------------------------------------------- host side
+// table exp(-2 pi i t / Z), t < Z, on the current device (cached per device, length and precision)
+template <class V>
+inline int twiddles(int Z, const V** out) {
+  static std::mutex mu;
+  static std::map<std::tuple<int, int>, V*> cache;
+  int dev = 0;
+  CUDA_TRY(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lock(mu);
+  auto it = cache.find(std::make_tuple(dev, Z));
+  if (it == cache.end()) {
+    std::vector<V> h(Z);
+    const double pi = 3.14159265358979323846;
+    for (int t = 0; t < Z; ++t) {
+      const double a = -2.0 * pi * (double)t / (double)Z;
+      h[t].x = (typename RealOf<V>::type)cos(a);
+      h[t].y = (typename RealOf<V>::type)sin(a);
+    }
+    V* d = nullptr;
+    CUDA_TRY(cudaMalloc(&d, (size_t)Z * sizeof(V)));
+    CUDA_TRY(cudaMemcpy(d, h.data(), (size_t)Z * sizeof(V), cudaMemcpyHostToDevice));
+    it = cache.emplace(std::make_tuple(dev, Z), d).first;
+  }
+  *out = it->second;
+  return B200_OK;
+}
+
+inline int factorise(int Z, Radices* rad) {
+  rad->n = 0;
+  auto push = [&](int r) {
+    if (rad->n < MAXRAD) rad->r[rad->n] = r;
+    ++rad->n;
+  };
+  while (Z % 4 == 0) { push(4); Z /= 4; }
+  for (int p : {2, 3, 5, 7})
+    while (Z % p == 0) { push(p); Z /= p; }
+  for (int p = 11; Z > 1; p += 2)
+    while (Z % p == 0) { push(p); Z /= p; }
+  if (rad->n > MAXRAD) {
+    b200_set_error("FFT length has too many prime factors");
+    return B200_EINVAL;
+  }
+  return B200_OK;
+}
+
+}  // namespace fftsm

@@ -1202,6 +1202,33 @@ def test_field_map_autograd_through_the_batched_orc_operator(mods, C, sense):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("shape,precision", [((30,), "single"), ((40, 36), "single"), ((64, 32), "single"),
+                                             ((20, 24, 28), "single"), ((33, 14, 22), "single"),
+                                             ((40, 36), "double"), ((20, 24, 28), "double")])
+def test_own_any_length_fft_matches_the_library_fft(mods, shape, precision):
+    """Option key 2 = 4: the library's own any-length FFT passes (csrc/fft_any.cu: Stockham in shared memory,
+    radix 4 / 2 / 3 / 5 / 7 / direct-DFT primes, fastest axis and strided axes) in place of the cuFFT execution
+    of grids that are not powers of two and of complex128 plans: same results, both signs, several coils."""
+    mrinufft, _, _ = mods
+    rng = np.random.default_rng(11)
+    d, C, M = len(shape), 3, 3000
+    dbl = precision == "double"
+    samples = rng.uniform(-np.pi, np.pi, (M, d)).astype(np.float64 if dbl else np.float32)
+    op = mrinufft.get_operator("b200")(samples, shape, n_coils=C, squeeze_dims=False, precision=precision)
+    cdt = np.complex128 if dbl else np.complex64
+    img = (rng.standard_normal(op.img_full_shape) + 1j * rng.standard_normal(op.img_full_shape)).astype(cdt)
+    ksp = (rng.standard_normal(op.ksp_full_shape) + 1j * rng.standard_normal(op.ksp_full_shape)).astype(cdt)
+    res = {}
+    for method in (0, 4):
+        op.raw_op.plan.set_option(2, method)
+        res[method] = (op.op(img), op.adj_op(ksp))
+        with op.grad_traj_plan():
+            res[method] += (op.op(img), op.adj_op(ksp))
+    for a, b in zip(res[0], res[4]):
+        assert rel_l2(b, a) < (1e-13 if dbl else 1e-6)
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("Z,Y,C", [(1, 5, 2), (2, 16, 1), (12, 24, 3), (15, 17, 2), (22, 40, 2), (49, 16, 1),
                                     (64, 33, 4), (97, 8, 1), (176, 20, 2), (256, 32, 2), (512, 16, 1)])
 def test_stack_fftz_kernel_against_numpy(mods, Z, Y, C):
