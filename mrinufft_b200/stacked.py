@@ -39,6 +39,22 @@ class MRIB200StackedNUFFT(MRIStackedNUFFT):
 
     # ------------------------------------------------------------------ helpers
     @property
+    def smaps(self):
+        return self._smaps
+
+    @smaps.setter
+    def smaps(self, new_smaps):
+        # numpy, torch (cpu / cuda) and cupy arrays; the base setter only takes numpy (base.py:759-760)
+        if new_smaps is not None:
+            if tuple(new_smaps.shape[1:]) != tuple(self.shape):
+                raise ValueError("Smaps should match image shape.")
+            if new_smaps.shape[0] != self._n_coils:
+                self._n_coils = int(new_smaps.shape[0])
+                self.log.warning("updating number of coils via Smaps.")
+        self._smaps = new_smaps
+        self._smaps_dev = None
+
+    @property
     def _dev(self):
         return self.operator.device
 

@@ -1313,6 +1313,10 @@ def test_native_stacked_matches_generic_stacked(mods, sense):
     assert nat.op(xt).is_cuda and rel_l2(nat.op(xt).cpu().numpy(), ax) <= 1e-6
     dc = nat.data_consistency(x, y)
     assert rel_l2(dc, nat.adj_op(nat.op(x) - y)) <= 1e-5
+    if sense:  # device-resident maps (the base setter only takes numpy, base.py:759-760)
+        nat_d = mrinufft.get_operator("stacked-b200")(traj2d, shape, smaps=torch.from_numpy(smaps).cuda(),
+                                                      z_index=z_index, n_coils=C)
+        assert rel_l2(nat_d.op(x), ax) <= 1e-6 and rel_l2(nat_d.adj_op(y), ahy) <= 1e-6
 
 
 @pytest.mark.gpu
