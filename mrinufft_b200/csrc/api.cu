@@ -56,7 +56,7 @@ struct Timed {
 int exec_fft(b200_plan* p, float2* fw, int T, int sign, cudaStream_t st) {
   Timed tm(p, EV_FFT, st);
   // option 2 = 4: the library's own any-length passes (fft_any.cu) instead of cuFFT -- correct for every grid,
-  // measured at 2.5x cuFFT's time on grids with factors 3 / 5, so cuFFT stays the default here
+  // measured at 1.5 - 1.8x cuFFT's time on grids with factors 3 / 5, so cuFFT stays the default here
   if (p->fft_method == 4) return fft_any_c64(fw, T, p->g, sign, st);
   CUFFT_TRY(cufftSetStream(p->fft, st));
   const int dir = sign < 0 ? CUFFT_FORWARD : CUFFT_INVERSE;

@@ -2,8 +2,8 @@
 // complex128: an own replacement of the cuFFT C2C / Z2Z executions that serve the plans where the
 // zero-padding-aware power-of-two passes of fft_pruned.cu do not apply (grids with factors 3, 5, 7, ...; 1-D;
 // complex128 plans).  Selected with option key 2 = 4.  Correct on every grid of the test suite, but measured at
-// ~2.5x cuFFT's time (five radix-4/2/3/5 stages through shared memory per axis against cuFFT's two or three
-// in registers), so cuFFT remains the default for those grids; the stacked operator's z transform, where the
+// 1.5 - 1.8x cuFFT's time (three or four stages through shared memory per axis against cuFFT's two in
+// registers), so cuFFT remains the default for those grids; the stacked operator's z transform, where the
 // fusion with its neighbours pays, uses the same shared-memory FFT (stack_fftz.cu).
 //
 // One pass per axis.  The T grids (n0, n1, n2), C order, are seen as [outer][L][S] for the axis of length L
@@ -46,18 +46,18 @@ __global__ void __launch_bounds__(ZT) k_fft_axis(const AxisArgs<V> g) {
     const int nrow = (int)min((long long)rows, g.outer - o0);
     V* base = g.data + o0 * L;
     for (int i = threadIdx.x; i < nrow * L; i += ZT) {
-      const int row = i / L, k = i - row * L;
+      const int row = fdiv(i, g.r.zmagic), k = i - row * L;
       bufa[row * zp + k] = base[i];
     }
     if (nrow < rows)
       for (int i = threadIdx.x + nrow * L; i < rows * L; i += ZT) {
-        const int row = i / L, k = i - row * L;
+        const int row = fdiv(i, g.r.zmagic), k = i - row * L;
         bufa[row * zp + k] = mkc<V>(0, 0);
       }
     __syncthreads();
     const V* res = fft_rows<INV>(bufa, bufb, tw, g.r);
     for (int i = threadIdx.x; i < nrow * L; i += ZT) {
-      const int row = i / L, k = i - row * L;
+      const int row = fdiv(i, g.r.zmagic), k = i - row * L;
       base[i] = res[row * zp + k];
     }
   } else {
@@ -66,13 +66,13 @@ __global__ void __launch_bounds__(ZT) k_fft_axis(const AxisArgs<V> g) {
     const int ncol = (int)min((long long)rows, g.S - c0);
     V* base = g.data + o * L * g.S + c0;
     for (int i = threadIdx.x; i < rows * L; i += ZT) {
-      const int k = i / rows, c = i - k * rows;
+      const int k = i >> g.r.rshift, c = i & (rows - 1);
       bufa[c * zp + k] = c < ncol ? base[(long long)k * g.S + c] : mkc<V>(0, 0);
     }
     __syncthreads();
     const V* res = fft_rows<INV>(bufa, bufb, tw, g.r);
     for (int i = threadIdx.x; i < rows * L; i += ZT) {
-      const int k = i / rows, c = i - k * rows;
+      const int k = i >> g.r.rshift, c = i & (rows - 1);
       if (c < ncol) base[(long long)k * g.S + c] = res[c * zp + k];
     }
   }
@@ -87,18 +87,18 @@ int axis_pass(V* data, long long outer, int L, long long S, int sign, cudaStream
   g.S = S;
   g.r.Z = L;
   g.r.zp = L | 1;
-  B200_TRY(factorise(L, &g.r.rad));
   B200_TRY(twiddles<V>(L, &g.tw));
   auto bytes = [&](int r) { return ((size_t)2 * r * g.r.zp + L) * sizeof(V); };
-  // 16 lines per tile when three CTAs still fit an SM, fewer for long lines
+  // 16 lines per tile when two CTAs still fit an SM, fewer for long lines
   int rows = 16;
-  while (rows > 4 && bytes(rows) > 72 * 1024) rows >>= 1;
+  while (rows > 4 && bytes(rows) > 110 * 1024) rows >>= 1;
   while (rows > 1 && bytes(rows) > 216 * 1024) rows >>= 1;
   if (bytes(rows) > 216 * 1024) {
     b200_set_error("FFT axis of length %d does not fit one CTA's shared memory", L);
     return B200_EINVAL;
   }
   g.r.rows = rows;
+  B200_TRY(prepare(&g.r));
   long long tiles;
   if (S == 1) {
     g.tiles_per_outer = 1;

@@ -24,10 +24,18 @@ struct Radices {
 // what the stage loop needs to know about the rows
 struct Rows {
   int Z;      // length
-  int rows;   // rows in the tile
+  int rows;   // rows in the tile (a power of two <= 16)
   int zp;     // row stride in elements (odd: row-fastest accesses spread over the banks)
+  int rshift; // log2(rows)
   Radices rad;
+  unsigned zmagic;          // fdiv magic of Z (tile loads / stores: element index -> (row, position))
+  unsigned smagic[MAXRAD];  // per stage: floor(2^32 / s) + 1 for the stage's stride s (0 for s = 1), see fdiv
 };
+
+// n / d for n d < 2^32 through the precomputed magic = floor(2^32 / d) + 1 (0 stands for d = 1): one IMAD.HI
+// instead of the ~25 instructions of a run-time 32-bit division
+__host__ __device__ inline unsigned fdiv_magic(unsigned d) { return d <= 1 ? 0u : (unsigned)(0x100000000ull / d) + 1u; }
+__device__ __forceinline__ int fdiv(int n, unsigned magic) { return magic ? (int)__umulhi((unsigned)n, magic) : n; }
 
 template <class V>
 struct RealOf;
@@ -83,6 +91,30 @@ __device__ __forceinline__ void butterfly(const V* __restrict__ src, V* __restri
     o[1] = caddf(t1, t3);
     o[2] = csubf(t0, t2);
     o[3] = csubf(t1, t3);
+  } else if constexpr (R == 8) {
+    // two 4-point transforms of the even / odd inputs, joined by the eighth roots of unity
+    typedef typename RealOf<V>::type T;
+    const T h = (T)0.70710678118654752440;
+    V e[4], d[4];
+    {
+      const V t0 = caddf(a[0], a[4]), t1 = csubf(a[0], a[4]);
+      const V t2 = caddf(a[2], a[6]), t3 = rot90<INV>(csubf(a[2], a[6]));
+      e[0] = caddf(t0, t2); e[1] = caddf(t1, t3); e[2] = csubf(t0, t2); e[3] = csubf(t1, t3);
+    }
+    {
+      const V t0 = caddf(a[1], a[5]), t1 = csubf(a[1], a[5]);
+      const V t2 = caddf(a[3], a[7]), t3 = rot90<INV>(csubf(a[3], a[7]));
+      d[0] = caddf(t0, t2); d[1] = caddf(t1, t3); d[2] = csubf(t0, t2); d[3] = csubf(t1, t3);
+    }
+    // d[k] *= w8^k: w8 = (1 -+ i) / sqrt 2, w8^2 = -+ i, w8^3 = (-1 -+ i) / sqrt 2
+    d[1] = INV ? mkc<V>((d[1].x - d[1].y) * h, (d[1].x + d[1].y) * h) : mkc<V>((d[1].x + d[1].y) * h, (d[1].y - d[1].x) * h);
+    d[2] = rot90<INV>(d[2]);
+    d[3] = INV ? mkc<V>((-d[3].x - d[3].y) * h, (d[3].x - d[3].y) * h) : mkc<V>((d[3].y - d[3].x) * h, (-d[3].x - d[3].y) * h);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      o[k] = caddf(e[k], d[k]);
+      o[k + 4] = csubf(e[k], d[k]);
+    }
   } else {
     V w[R];
 #pragma unroll
@@ -130,11 +162,16 @@ __device__ __forceinline__ V* fft_rows(V* a, V* b, const V* tw, const Rows& g) {
   int s = 1, n = g.Z;
   for (int st = 0; st < g.rad.n; ++st) {
     const int r = g.rad.r[st], m = n / r, nb = g.Z / r;
-    for (int i = threadIdx.x; i < g.rows * nb; i += ZT) {
-      const int row = i / nb, bf = i - row * nb, p = bf / s, q = bf - p * s;
-      const V* x = a + row * g.zp;
-      V* y = b + row * g.zp;
+    const unsigned magic = g.smagic[st];
+    // lane = row (rows vary fastest: odd row stride -> distinct banks), the butterflies of a row are strided
+    // over the rest of the CTA
+    const int row = threadIdx.x & (g.rows - 1);
+    const V* x = a + row * g.zp;
+    V* y = b + row * g.zp;
+    for (int bf = threadIdx.x >> g.rshift; bf < nb; bf += ZT >> g.rshift) {
+      const int p = fdiv(bf, magic), q = bf - p * s;
       switch (r) {
+        case 8: butterfly<8, INV>(x, y, tw, p, q, s, m, g.Z); break;
         case 2: butterfly<2, INV>(x, y, tw, p, q, s, m, g.Z); break;
         case 3: butterfly<3, INV>(x, y, tw, p, q, s, m, g.Z); break;
         case 4: butterfly<4, INV>(x, y, tw, p, q, s, m, g.Z); break;
@@ -186,6 +223,7 @@ inline int factorise(int Z, Radices* rad) {
     if (rad->n < MAXRAD) rad->r[rad->n] = r;
     ++rad->n;
   };
+  while (Z % 8 == 0) { push(8); Z /= 8; }
   while (Z % 4 == 0) { push(4); Z /= 4; }
   for (int p : {2, 3, 5, 7})
     while (Z % p == 0) { push(p); Z /= p; }
@@ -194,6 +232,24 @@ inline int factorise(int Z, Radices* rad) {
   if (rad->n > MAXRAD) {
     b200_set_error("FFT length has too many prime factors");
     return B200_EINVAL;
+  }
+  return B200_OK;
+}
+
+// after Z and rows are set: radices, row shift, per-stage division magics
+inline int prepare(Rows* g) {
+  B200_TRY(factorise(g->Z, &g->rad));
+  g->rshift = 0;
+  while ((1 << g->rshift) < g->rows) ++g->rshift;
+  if ((1 << g->rshift) != g->rows || g->rows > ZT) {
+    b200_set_error("internal: FFT tile rows must be a power of two");
+    return B200_EINVAL;
+  }
+  g->zmagic = fdiv_magic((unsigned)g->Z);
+  unsigned s = 1;
+  for (int st = 0; st < g->rad.n; ++st) {
+    g->smagic[st] = fdiv_magic(s);
+    s *= (unsigned)g->rad.r[st];
   }
   return B200_OK;
 }

@@ -60,7 +60,7 @@ __global__ void __launch_bounds__(ZT) k_stack_fftz(const ZArgs g) {
       const float2* src = g.img + (SENSE ? 0 : (size_t)c * vol) + colZ;
       const float2* sm = SENSE ? g.smaps + (size_t)c * vol + colZ : nullptr;
       for (int i = threadIdx.x; i < nrow * Z; i += ZT) {
-        const int row = i / Z, z = i - row * Z;
+        const int row = fdiv(i, g.r.zmagic), z = i - row * Z;
         float2 v = src[i];
         if (SENSE) v = cmulf(v, sm[i]);
         int n = z - h;
@@ -71,7 +71,7 @@ __global__ void __launch_bounds__(ZT) k_stack_fftz(const ZArgs g) {
       const float2* res = fft_rows<false>(bufa, bufb, tw, g.r);
       // fftshift + plane selection + (coil, stack)-major planes: rows (= y) fastest
       for (int i = threadIdx.x; i < g.NZ * rows; i += ZT) {
-        const int j = i / rows, row = i - j * rows;
+        const int j = i >> g.r.rshift, row = i & (rows - 1);
         if (row < nrow) {
           int n = g.zsel[j] - h;
           if (n < 0) n += Z;
@@ -84,7 +84,7 @@ __global__ void __launch_bounds__(ZT) k_stack_fftz(const ZArgs g) {
       for (int i = threadIdx.x; i < rows * zp; i += ZT) bufa[i] = make_float2(0.f, 0.f);
       __syncthreads();
       for (int i = threadIdx.x; i < g.NZ * rows; i += ZT) {
-        const int j = i / rows, row = i - j * rows;
+        const int j = i >> g.r.rshift, row = i & (rows - 1);
         if (row < nrow) {
           int n = g.zsel[j] - h;
           if (n < 0) n += Z;
@@ -96,7 +96,7 @@ __global__ void __launch_bounds__(ZT) k_stack_fftz(const ZArgs g) {
       float2* dst = g.out + (SENSE ? 0 : (size_t)c * vol) + colZ;
       const float2* sm = SENSE ? g.smaps + (size_t)c * vol + colZ : nullptr;
       for (int i = threadIdx.x; i < nrow * Z; i += ZT) {
-        const int row = i / Z, z = i - row * Z;
+        const int row = fdiv(i, g.r.zmagic), z = i - row * Z;
         int n = z - h;
         if (n < 0) n += Z;
         float2 v = res[row * zp + n];
@@ -120,7 +120,6 @@ __global__ void __launch_bounds__(ZT) k_stack_fftz(const ZArgs g) {
 // ---------------------------------------------------------------- host side
 template <bool ADJ>
 int launch(ZArgs& g, bool sense, cudaStream_t st) {
-  B200_TRY(factorise(g.r.Z, &g.r.rad));
   B200_TRY(twiddles<float2>(g.r.Z, &g.tw));
   g.r.zp = g.r.Z | 1;
   const int nbuf = (ADJ && sense) ? 3 : 2;
@@ -133,6 +132,7 @@ int launch(ZArgs& g, bool sense, cudaStream_t st) {
     return B200_EINVAL;
   }
   g.r.rows = rows;
+  B200_TRY(prepare(&g.r));
   const long long tiles = (long long)g.X * ((g.Y + rows - 1) / rows);
   if (tiles > 0x7fffffffLL || g.C > 65535) {
     b200_set_error("b200_stack_fftz: volume too large for one launch");

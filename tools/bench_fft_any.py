@@ -1,8 +1,9 @@
 #!/usr/bin/env python
 """op / adj_op times of configurations whose grids go through the any-length FFT passes (csrc/fft_any.cu):
-grids that are not powers of two and complex128 plans.  One JSON line per configuration; `fft_ms` is the
+grids that are not powers of two and complex128 plans.  B200_FFT_METHOD=4 selects them (option key 2), the default is cuFFT.  One JSON line per configuration; `fft_ms` is the
 library's own event timing of the FFT stage where the plan records it (single precision)."""
 import json
+import os
 import sys
 from pathlib import Path
 
@@ -34,6 +35,7 @@ def run(tag, shape, M, C, precision="single"):
     d = len(shape)
     traj = rng.uniform(-0.5, 0.5, (M, d)).astype(np.float64 if precision == "double" else np.float32)
     op = mrinufft.get_operator("b200")(traj, shape, n_coils=C, squeeze_dims=False, precision=precision)
+    op.raw_op.plan.set_option(2, int(os.environ.get("B200_FFT_METHOD", "0")))  # 4: the own any-length passes
     cdt = torch.complex128 if precision == "double" else torch.complex64
     img = torch.randn((1, C, *shape), dtype=cdt, device="cuda")
     ksp = torch.randn((1, C, M), dtype=cdt, device="cuda")
