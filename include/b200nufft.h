@@ -204,6 +204,15 @@ int b200_stack_fftz_adjoint(const void* planes, const void* smaps, void* out, co
                             int C, int X, int Y, int Z, int NZ, float scale, void* stream);
 
 /*
+ * In-place FFT along every axis of T contiguous C-order arrays (dim = 1..3 axes of ANY length, complex64 or
+ * complex128; unnormalised, sign < 0: exp(-i ...)): the library's own any-length passes (shared-memory Stockham,
+ * csrc/fft_any.cu).  No plan.  Replaces the `fftn` of the Toeplitz kernel assembly
+ * (src/mrinufft/operators/toeplitz.py:89-93); option key 2 = 4 routes the plans' non-power-of-two and
+ * complex128 grids through the same passes.
+ */
+int b200_fft_c2c(void* data, int T, int dim, const int64_t* n, int sign, int dbl, void* stream);
+
+/*
  * Vector updates of the iterative solvers, one pass over memory each: replace the array expressions of
  * `lsqr` / `lsmr` / `cg` (src/mrinufft/extras/optim.py:402-446, 669-724, 866-883).  Vectors are device arrays
  * of B x n complex64 (dbl = 0) or complex128 (dbl = 1) elements, batch-major; scalars are HOST arrays of B

@@ -63,6 +63,7 @@ _SIGNATURES = {
     "b200_plan_rows_class": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int64)]),
     "b200_plan_last_timings": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
     "b200_plan_enable_timing": (C.c_int, [C.c_void_p, C.c_int]),
+    "b200_fft_c2c": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_int64), C.c_int, C.c_int, C.c_void_p]),
     "b200_vec_axpby": (
         C.c_int,
         [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_int,
@@ -259,6 +260,12 @@ def stack_fftz(adjoint, src, smaps, dst, zsel, C_, X, Y, Z, NZ, scale, stream=0)
     fn = load().b200_stack_fftz_adjoint if adjoint else load().b200_stack_fftz_forward
     check(fn(src, smaps, dst, zsel, int(C_), int(X), int(Y), int(Z), int(NZ), float(scale), stream),
           "b200_stack_fftz_adjoint" if adjoint else "b200_stack_fftz_forward")
+
+
+def fft_c2c(ptr, T, shape, sign, double=False, stream=0):
+    """In-place own FFT of T contiguous arrays of `shape` (raw device pointer; see include/b200nufft.h)."""
+    n = (C.c_int64 * len(shape))(*[int(v) for v in shape])
+    check(load().b200_fft_c2c(ptr, int(T), len(shape), n, int(sign), int(double), stream), "b200_fft_c2c")
 
 
 def header_symbols(header: Path | None = None):

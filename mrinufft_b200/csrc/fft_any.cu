@@ -143,3 +143,25 @@ int fft_grids(V* fw, int T, const Geom& g, int sign, cudaStream_t st) {
 // Unnormalised FFT (sign < 0: exp(-i ...), else exp(+i ...)) of T grids of the plan's oversampled size, in place.
 int fft_any_c64(float2* fw, int T, const Geom& g, int sign, cudaStream_t st) { return fft_grids<float2>(fw, T, g, sign, st); }
 int fft_any_c128(double2* fw, int T, const Geom& g, int sign, cudaStream_t st) { return fft_grids<double2>(fw, T, g, sign, st); }
+
+// Plan-less entry point: T contiguous C-order arrays of `dim` axes n[0..dim), complex64 (dbl = 0) or complex128,
+// transformed in place along every axis (unnormalised; sign < 0: exp(-i ...)).
+extern "C" int b200_fft_c2c(void* data, int T, int dim, const int64_t* n, int sign, int dbl, void* stream) {
+  if (!data || !n || T < 1 || dim < 1 || dim > 3) {
+    b200_set_error("b200_fft_c2c: bad arguments (T=%d, dim=%d)", T, dim);
+    return B200_EINVAL;
+  }
+  Geom g{};
+  g.dim = dim;
+  g.nftot = 1;
+  for (int a = 0; a < 3; ++a) {
+    g.nf[a] = a < dim ? (int)n[a] : 1;
+    if (g.nf[a] < 1 || (a < dim && n[a] > (1 << 20))) {
+      b200_set_error("b200_fft_c2c: axis %d has length %lld", a, (long long)n[a]);
+      return B200_EINVAL;
+    }
+    g.nftot *= g.nf[a];
+  }
+  return dbl ? fft_grids<double2>((double2*)data, T, g, sign, (cudaStream_t)stream)
+             : fft_grids<float2>((float2*)data, T, g, sign, (cudaStream_t)stream);
+}

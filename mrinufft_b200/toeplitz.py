@@ -15,8 +15,8 @@ zero-padded convolution never reads -- is cleared, and one FFT gives the spectru
 number of adjoints with the Hermitian symmetry and a real inverse FFT of a half array; with single-coil
 adjoints at 3 ms apiece -- coil class 1 of the row kernels -- the plain tiling is not worth complicating.)
 
-The adjoints are the expensive part and run in ``libb200nufft.so``; what is here is bookkeeping on torch
-tensors (any device, any dimension).  The spectrum is applied by ``b200_toeplitz_apply``
+The adjoints are the expensive part and run in ``libb200nufft.so``, and so does the final FFT of the lag
+array (``b200_fft_c2c``); what is here is bookkeeping on torch tensors (any device, any dimension).  The spectrum is applied by ``b200_toeplitz_apply``
 (``include/b200nufft.h``).
 """
 
@@ -48,7 +48,21 @@ def assemble_toeplitz_kernel(adj, shape, scale: float) -> torch.Tensor:
         lags[tuple(slice(0, n) if s > 0 else slice(n, 2 * n) for s, n in zip(signs, shape))] = window
     for axis, n in enumerate(shape):
         lags.select(axis, n).zero_()
-    return torch.fft.fftn(lags).real * (scale / math.sqrt(math.prod(full)))
+    return _fftn(lags).real * (scale / math.sqrt(math.prod(full)))
+
+
+def _fftn(lags: torch.Tensor) -> torch.Tensor:
+    """Forward DFT of the lag array: the library's own any-length FFT on the device (``b200_fft_c2c``).  CPU
+    tensors only occur in the host-logic test (tests/test_toeplitz_cpu.py, reference NDFT, no GPU)."""
+    if not lags.is_cuda:
+        return torch.fft.fftn(lags)
+    from . import _lib
+
+    out = lags.contiguous().clone()
+    with torch.cuda.device(out.device):
+        _lib.fft_c2c(out.data_ptr(), 1, out.shape, -1, out.dtype == torch.complex128,
+                     torch.cuda.current_stream(out.device).cuda_stream)
+    return out
 
 
 def modulated_weights(weights: torch.Tensor, omega: torch.Tensor, signs, shape) -> torch.Tensor:

@@ -1229,6 +1229,25 @@ def test_own_any_length_fft_matches_the_library_fft(mods, shape, precision):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("shape,dbl", [((3000,), False), ((40, 36), False), ((64, 64), True), ((12, 10, 22), False),
+                                        ((16, 32, 8), True), ((7, 13, 1), False)])
+def test_plan_less_fft_entry_point(mods, shape, dbl):
+    """`b200_fft_c2c` (csrc/fft_any.cu): both signs, several arrays per call, against numpy's fftn in double."""
+    _, _, torch = mods
+    from mrinufft_b200 import _lib
+
+    rng = np.random.default_rng(5)
+    T = 3
+    x = (rng.standard_normal((T, *shape)) + 1j * rng.standard_normal((T, *shape))).astype(np.complex128 if dbl else np.complex64)
+    axes = tuple(range(1, 1 + len(shape)))
+    for sign, ref in ((-1, np.fft.fftn(x.astype(np.complex128), axes=axes)),
+                      (+1, np.fft.ifftn(x.astype(np.complex128), axes=axes) * np.prod(shape))):
+        d = torch.from_numpy(x.copy()).cuda()
+        _lib.fft_c2c(d.data_ptr(), T, shape, sign, dbl, torch.cuda.current_stream().cuda_stream)
+        assert rel_l2(d.cpu().numpy(), ref) <= (1e-13 if dbl else 1e-6)
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("Z,Y,C", [(1, 5, 2), (2, 16, 1), (12, 24, 3), (15, 17, 2), (22, 40, 2), (49, 16, 1),
                                     (64, 33, 4), (97, 8, 1), (176, 20, 2), (256, 32, 2), (512, 16, 1)])
 def test_stack_fftz_kernel_against_numpy(mods, Z, Y, C):
