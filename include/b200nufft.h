@@ -204,6 +204,18 @@ int b200_stack_fftz_adjoint(const void* planes, const void* smaps, void* out, co
                             int C, int X, int Y, int Z, int NZ, float scale, void* stream);
 
 /*
+ * Temporal weights of the off-resonance-corrected operator whose L interpolators ride the coil batch as virtual
+ * coils l C + c: replaces the per-interpolator `B[l] * ...` accumulation of `MRIFourierCorrected.op` / `adj_op`
+ * (src/mrinufft/operators/off_resonance.py:232-332).  complex64; K = samples per coil, sample k belongs to
+ * readout position k % NK.
+ *   expand = 0:  y[b, c, k]     = sum_l kv[b, l, c, k] * bw[k % NK, l]
+ *   expand = 1:  kv[b, l, c, k] = conj(bw[k % NK, l]) * y[b, c, k]
+ *   kv (B, L * C, K), bw (NK, L), y (B, C, K)
+ */
+int b200_orc_weights(void* kv, const void* bw, void* y, int B, int L, int C, int64_t K, int NK, int expand,
+                     void* stream);
+
+/*
  * In-place FFT along every axis of T contiguous C-order arrays (dim = 1..3 axes of ANY length, complex64 or
  * complex128; unnormalised, sign < 0: exp(-i ...)): the library's own any-length passes (shared-memory Stockham,
  * csrc/fft_any.cu).  No plan.  Replaces the `fftn` of the Toeplitz kernel assembly

@@ -63,6 +63,10 @@ _SIGNATURES = {
     "b200_plan_rows_class": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int64)]),
     "b200_plan_last_timings": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
     "b200_plan_enable_timing": (C.c_int, [C.c_void_p, C.c_int]),
+    "b200_orc_weights": (
+        C.c_int,
+        [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int, C.c_int, C.c_void_p],
+    ),
     "b200_fft_c2c": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_int64), C.c_int, C.c_int, C.c_void_p]),
     "b200_vec_axpby": (
         C.c_int,

@@ -220,7 +220,48 @@ int entry(int what, void* const* p, int np, int B, int64_t n, const double* s0, 
              : dispatch<float2>(what, p, B, n, sc, red, (cudaStream_t)stream);
 }
 
+// ---- temporal weights of the off-resonance-corrected operator (virtual coil index l C + c) ----------------
+// combine: y[b, c, k] = sum_l kv[b, l, c, k] * Bw[k % NK, l];  expand: kv[b, l, c, k] = conj(Bw[k % NK, l]) * y[b, c, k]
+template <bool EXPAND>
+__global__ void __launch_bounds__(VT) k_orc(float2* __restrict__ kv, const float2* __restrict__ bw, float2* __restrict__ y,
+                                            int L, int C, long long K, int NK) {
+  const long long k = (long long)blockIdx.x * VT + threadIdx.x;
+  if (k >= K) return;
+  const int c = blockIdx.y, b = blockIdx.z;
+  const float2* w = bw + (size_t)(k % NK) * L;
+  float2* v = kv + ((size_t)b * L * C + c) * K + k;
+  float2* yy = y + ((size_t)b * C + c) * K + k;
+  if (EXPAND) {
+    const float2 a = *yy;
+    for (int l = 0; l < L; ++l) {
+      const float2 t = w[l];
+      v[(size_t)l * C * K] = make_float2(t.x * a.x + t.y * a.y, t.x * a.y - t.y * a.x);
+    }
+  } else {
+    float2 acc = make_float2(0.f, 0.f);
+    for (int l = 0; l < L; ++l) {
+      const float2 t = w[l], a = v[(size_t)l * C * K];
+      acc.x += t.x * a.x - t.y * a.y;
+      acc.y += t.x * a.y + t.y * a.x;
+    }
+    *yy = acc;
+  }
+}
+
 }  // namespace
+
+extern "C" int b200_orc_weights(void* kv, const void* bw, void* y, int B, int L, int C, int64_t K, int NK, int expand,
+                                void* stream) {
+  if (!kv || !bw || !y || B < 1 || L < 1 || C < 1 || K < 1 || NK < 1 || C > 65535 || B > 65535) {
+    b200_set_error("b200_orc_weights: bad arguments");
+    return B200_EINVAL;
+  }
+  dim3 grid((unsigned)((K + VT - 1) / VT), C, B);
+  if (expand) k_orc<true><<<grid, VT, 0, (cudaStream_t)stream>>>((float2*)kv, (const float2*)bw, (float2*)y, L, C, K, NK);
+  else k_orc<false><<<grid, VT, 0, (cudaStream_t)stream>>>((float2*)kv, (const float2*)bw, (float2*)y, L, C, K, NK);
+  CHECK_LAUNCH();
+  return B200_OK;
+}
 
 extern "C" int b200_vec_axpby(void* out, const void* x, const void* y, const double* a, const double* b, int B,
                               int64_t n, double* sumsq, int dbl, void* stream) {

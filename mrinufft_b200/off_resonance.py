@@ -23,6 +23,7 @@ import torch
 
 from mrinufft.operators.off_resonance import MRIFourierCorrected
 
+from . import _lib
 from ._arrays import to_device
 
 
@@ -141,6 +142,15 @@ class MRIB200FourierCorrected(MRIFourierCorrected):
                                 paired_batch=paired_batch)
 
     # ------------------------------------------------------------------ operators
+    def _weights(self, kv, bw, y, expand):
+        """Temporal weights between the virtual-coil k-space and the coils' k-space (`b200_orc_weights`)."""
+        Bn, LC, K = kv.shape
+        NK, L = bw.shape
+        with torch.cuda.device(kv.device):
+            _lib.check(_lib.load().b200_orc_weights(kv.data_ptr(), bw.data_ptr(), y.data_ptr(), Bn, L, LC // L, K, NK,
+                                                    int(expand), torch.cuda.current_stream(kv.device).cuda_stream),
+                       "b200_orc_weights")
+
     def op(self, data, *args):
         """Forward model with off-resonance (off_resonance.py:232-281)."""
         if args or not self._ensure_fused():
@@ -153,9 +163,9 @@ class MRIB200FourierCorrected(MRIFourierCorrected):
         L, C, Bn = f["L"], f["C"], fo.n_batchs
         NS, NK = int(self.n_shots), int(self.n_samples_per_shot)
         img, kind, dev = fo._in(data)
-        kv = vop._op_device(img.reshape(Bn, 1, *fo.shape))  # (B, L*C, K), virtual coil index l*C + c
-        kv = kv.reshape(Bn, L, C, NS, NK)
-        y = torch.einsum("blcsn,nl->bcsn", kv, f["B"]).reshape(Bn, C, NS * NK)
+        kv = vop._op_device(img.reshape(Bn, 1, *fo.shape)).contiguous()  # (B, L*C, K), virtual coil index l*C + c
+        y = torch.empty((Bn, C, NS * NK), dtype=kv.dtype, device=kv.device)
+        self._weights(kv, f["B"], y, expand=False)  # y[b, c, s, n] = sum_l kv[b, l, c, s, n] B[n, l]
         return fo._out(self._safe_squeeze(y), kind, dev)
 
     def adj_op(self, coeffs, *args):
@@ -170,7 +180,8 @@ class MRIB200FourierCorrected(MRIFourierCorrected):
         L, C, Bn = f["L"], f["C"], fo.n_batchs
         NS, NK = int(self.n_shots), int(self.n_samples_per_shot)
         ksp, kind, dev = fo._in(coeffs)
-        ksp = ksp.reshape(Bn, 1, C, NS, NK)
-        kv = (torch.conj(f["B"]).t().reshape(1, L, 1, 1, NK) * ksp).reshape(Bn, L * C, NS * NK).contiguous()
+        ksp = ksp.reshape(Bn, C, NS * NK).contiguous()
+        kv = torch.empty((Bn, L * C, NS * NK), dtype=ksp.dtype, device=ksp.device)
+        self._weights(kv, f["B"], ksp, expand=True)  # kv[b, l, c, s, n] = conj(B[n, l]) ksp[b, c, s, n]
         img = vop._adj_device(kv)  # (B, 1, *XYZ): conj(V) multiply and the sum over (l, c) are fused
         return fo._out(self._safe_squeeze(img), kind, dev)
