@@ -91,6 +91,13 @@ struct Cls {
   static constexpr int EU = ESZ / 16;                                                // ... in uint4 units
   static constexpr int IS_OFF = GENERIC ? 0 : 8;                                     // byte offset of {idx, s}
   static constexpr int PKT = 32 + ESZ;                                               // staged packet: P0..P3 | entry
+  // The packets of a block of MBLK visits are staged PIECE-MAJOR: 16-byte piece q of visit k sits at
+  // q * PSTR + 16 k, so that a cp.async instruction (one lane = one visit) writes 512 contiguous bytes = 4
+  // shared-memory wavefronts.  (Packet-major, lane stride PKT = 48 .. 80 bytes, every 128-byte line the 32 copies
+  // touched was a wavefront: 12 .. 32 per instruction, ncu `L1 Wavefronts Shared Excessive` -- in class 4 the
+  // staging copies were 35 % of all shared-memory wavefronts.)  fa(b): address of packet byte b inside a block.
+  static constexpr int PSTR = 16 * 32;
+  __host__ __device__ static constexpr unsigned fa(int b) { return (unsigned)((b >> 4) * PSTR + (b & 15)); }
   // PROD: the entry has room for the 2 G row scales wy[2 gy + r] wz[gz] themselves (3-D class 16, the 2-D
   // classes, whose z weight is 1): a lane loads its pair instead of forming it (one load and two multiplies
   // less per visit); entry = {idx, s, p[gz GY + gy][r]}
@@ -601,7 +608,7 @@ k_rows(Geom g, int T, int nchunks, unsigned S, long long M, const uint4* __restr
   asm volatile("" : "+l"(wsm));
   const unsigned vbuf_a = smem_u32(wsm);                         // [2][SB][TC] (re, im); spreader only
   unsigned char* metap = wsm + (SPREAD ? C::SM_VBUF : 0);
-  const unsigned meta_a = smem_u32(metap);                       // [2][MBLK] packets of PKT bytes
+  const unsigned meta_a = smem_u32(metap);                       // [2] blocks of MBLK packets of PKT bytes, piece-major
   // transpose planes.  Class 32: [32 coils][TBS], lane = coil on the register side; on the grid side a warp
   // instruction moves 8 cells (64 contiguous bytes) of 4 coils.  Smaller classes: one array [32 lanes][16
   // cells] of (re, im) in rows of TCS bytes.
@@ -616,7 +623,8 @@ k_rows(Geom g, int T, int nchunks, unsigned S, long long M, const uint4* __restr
   asm volatile("" : "+l"(ktl));
   // class < 32: this lane's row group and the packet offsets of its window entries
   const int grp = lane / TC, gyi = grp % C::GY, gzi = grp / C::GY;
-  const unsigned yo = (unsigned)(C::WY_OFF + 8 * (C::PROD ? grp : gyi)), zo = (unsigned)(C::WZ_OFF + 4 * gzi);
+  // (block-relative addresses of the lane's window entries in the piece-major staging, see Cls::fa)
+  const unsigned yo = C::fa(C::WY_OFF + 8 * (C::PROD ? grp : gyi)), zo = C::fa(C::WZ_OFF + 4 * gzi);
 
   const int nfx = g.nf[DIM - 1];
   const int nfy = g.nf[DIM - 2];
@@ -873,16 +881,16 @@ k_rows(Geom g, int T, int nchunks, unsigned S, long long M, const uint4* __restr
     // packet block mb: entry -> behind the first 32 bytes of the packet, x weights -> first 32 bytes
     // (cp.async); returns the header mask of the block
     auto stage_block = [&](int mb, const uint2& is) -> unsigned {
-      const unsigned row_a = meta_a + (unsigned)(((mb & 1) * MBLK + lane) * PKT);
+      const unsigned row_a = meta_a + (unsigned)((mb & 1) * MBLK * PKT + lane * 16);
       if (is.x != IDX_NONE) {
         const uint4* e = v + (size_t)(mb * MBLK + lane) * EU;
 #pragma unroll
-        for (int q = 0; q < EU; ++q) cp_async16(row_a + 32u + 16u * q, e + q);
+        for (int q = 0; q < EU; ++q) cp_async16(row_a + (unsigned)((2 + q) * C::PSTR), e + q);
       }
       if (is.x < IDX_NONE) {
         const float* pw = ptab + (long long)is.y * 8;
         cp_async16(row_a, pw);
-        cp_async16(row_a + 16u, pw + 4);
+        cp_async16(row_a + (unsigned)C::PSTR, pw + 4);
       }
       return __ballot_sync(FULL, is.x == IDX_HDR);
     };
@@ -935,7 +943,7 @@ k_rows(Geom g, int T, int nchunks, unsigned S, long long M, const uint4* __restr
       else cp_async_wait<0>();
       __syncwarp();
       const int n = min(SB, nw - j * SB);
-      const unsigned pk_a = meta_a + (unsigned)((((j / SPB) & 1) * MBLK + (j % SPB) * SB) * PKT);
+      const unsigned pk_a = meta_a + (unsigned)(((j / SPB) & 1) * MBLK * PKT + (j % SPB) * SB * 16);
       const unsigned vb_a = vbuf_a + (unsigned)((j & 1) * C::SB * TC + tl) * 8u;
 
       // the sub-block is a sequence of visit runs separated by header entries
@@ -950,16 +958,16 @@ k_rows(Geom g, int T, int nchunks, unsigned S, long long M, const uint4* __restr
           }
           dirty = true;
           if (SPREAD) {
-            rows_loop_spread<W, DIM, TC>(acc, pk_a + (unsigned)(k0 * PKT), k1 - k0, vb_a + (unsigned)(k0 * TC * 8), yo, zo);
+            rows_loop_spread<W, DIM, TC>(acc, pk_a + (unsigned)(k0 * 16), k1 - k0, vb_a + (unsigned)(k0 * TC * 8), yo, zo);
           } else if constexpr (!GEN || C::DIRECT) {
-            rows_loop_interp<W, DIM, TC>(acc, pk_a + (unsigned)(k0 * PKT), k1 - k0, ktl, 0u, yo, zo);
+            rows_loop_interp<W, DIM, TC>(acc, pk_a + (unsigned)(k0 * 16), k1 - k0, ktl, 0u, yo, zo);
           } else {
             // class < 32: pieces of OBV visits; every lane parks its partial sums (this lane's coil, its
             // row group) in OBUF[visit][lane], then lane (v, t) adds the G row groups of coil t of visit v
             // and sends the sum to k-space: one coalesced red per TC coils and visit
             for (int kk = k0; kk < k1; kk += C::OBV) {
               const int nv = min(C::OBV, k1 - kk);
-              const unsigned pkk = pk_a + (unsigned)(kk * PKT);
+              const unsigned pkk = pk_a + (unsigned)(kk * 16);
               rows_loop_interp<W, DIM, TC>(acc, pkk, nv, nullptr, ob_a + (unsigned)lane * 8u, yo, zo);
               __syncwarp();
 #pragma unroll
@@ -974,7 +982,7 @@ k_rows(Geom g, int T, int nchunks, unsigned S, long long M, const uint4* __restr
                     sum.x += q.x;
                     sum.y += q.y;
                   }
-                  const unsigned sp = lds32(pkk + (unsigned)(vv * PKT + 32 + C::IS_OFF + 4));
+                  const unsigned sp = lds32(pkk + (unsigned)(vv * 16) + C::fa(32 + C::IS_OFF + 4));
                   red_add_f32x2(reinterpret_cast<float2*>(const_cast<char*>(ktl)) + (size_t)sp * TC, pack2(sum.x, sum.y), 1);
                 }
               }
@@ -999,7 +1007,7 @@ k_rows(Geom g, int T, int nchunks, unsigned S, long long M, const uint4* __restr
         }
         if (at_end) break;
         hm &= hm - 1;
-        tile_setup((int)lds32(pk_a + (unsigned)(k1 * PKT + 32 + C::IS_OFF + 4)));
+        tile_setup((int)lds32(pk_a + (unsigned)(k1 * 16) + C::fa(32 + C::IS_OFF + 4)));
         started = true;
         loaded = false;
         dirty = false;

@@ -17,7 +17,8 @@ Coil classes.  TC = 32: lane = coil, the warp's tile is 2 rows.  TC < 32 (batche
 lane = (row group g, coil t), g = lane / TC, t = lane % TC; the G = 32 / TC groups hold GY row pairs x
 GZ planes of a larger tile, so a point visits fewer tiles and no lane idles for want of coils.
 
-A visit is staged in shared memory as a packet (read with warp-broadcast loads)
+A visit is staged in shared memory as a packet (read with warp-broadcast loads; the packets of a block of 32
+visits are stored piece-major, 16-byte piece q of visit k at 512 q + 16 k, see `fa`)
     TC = 32 (48 bytes):  P_0..P_3 | s0, s1, idx, s
     TC < 32 (32 + ESZ):  P_0..P_3 | idx, s | wy[2 GY] | wz[GZ] | padding
     (TC < 32 with room in the entry -- 3-D class 16, the 2-D classes: the 2 G products wy[2 gy + r] wz[gz]
@@ -85,23 +86,29 @@ class Layout:
         self.parked = self.generic and not self.direct
 
 
+def fa(b):
+    """Address of packet byte b inside a staged block: the packets are piece-major, 16-byte piece q of visit k at
+    512 q + 16 k (mirrors `Cls::fa` in rows_common.cuh)."""
+    return (b // 16) * 512 + b % 16
+
+
 def load_set(lay, X, k, pred, spread):
     """Load visit packet k (relative to pk) (+ coil value) into register set X; under `pred` (no further
     visit) only mark it."""
-    off_pk, off_vb = k * lay.pkt, k * lay.vstride
+    off_pk, off_vb = k * 16, k * lay.vstride
     L = []
     if pred:
         L.append(f"@{pred} mov.u32 i{X}, 0xffffffff;")
     p = f"@!{pred} " if pred else ""
-    L += [f"{p}ld.shared.v2.b64 {{P{X}0, P{X}1}}, [pk+{off_pk}];",
-          f"{p}ld.shared.v2.b64 {{P{X}2, P{X}3}}, [pk+{off_pk + 16}];"]
+    L += [f"{p}ld.shared.v2.b64 {{P{X}0, P{X}1}}, [pk+{off_pk + fa(0)}];",
+          f"{p}ld.shared.v2.b64 {{P{X}2, P{X}3}}, [pk+{off_pk + fa(16)}];"]
     if lay.generic:
-        L += [f"{p}ld.shared.v2.b32 {{i{X}, n{X}}}, [pk+{off_pk + 32}];",
+        L += [f"{p}ld.shared.v2.b32 {{i{X}, n{X}}}, [pk+{off_pk + fa(32)}];",
               f"{p}ld.shared.v2.b32 {{s{X}0, s{X}1}}, [pky+{off_pk}];"]
         if not lay.prod:
             L.append(f"{p}ld.shared.b32 z{X}, [pkz+{off_pk}];")
     else:
-        L.append(f"{p}ld.shared.v4.b32 {{s{X}0, s{X}1, i{X}, n{X}}}, [pk+{off_pk + 32}];")
+        L.append(f"{p}ld.shared.v4.b32 {{s{X}0, s{X}1, i{X}, n{X}}}, [pk+{off_pk + fa(32)}];")
     if spread:
         L.append(f"{p}ld.shared.b64 v{X}, [vb+{off_vb}];")
     return L
@@ -206,9 +213,9 @@ def gen_loop(W, spread, dim=3, TC=32):
     _, ncase = cases(W)
 
     def step(k):
-        s = [f"add.u32 pk, pk, {k * lay.pkt};"]
+        s = [f"add.u32 pk, pk, {k * 16};"]
         if lay.generic:
-            s += [f"add.u32 pky, pky, {k * lay.pkt};", f"add.u32 pkz, pkz, {k * lay.pkt};"]
+            s += [f"add.u32 pky, pky, {k * 16};", f"add.u32 pkz, pkz, {k * 16};"]
         if spread:
             s.append(f"add.u32 vb, vb, {k * lay.vstride};")
         elif lay.parked:
