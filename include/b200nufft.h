@@ -52,6 +52,11 @@ typedef struct b200_plan b200_plan;
                                 complex128 / float64 (sample coordinates and density included).
                                 Correctness-first kernels; no spread-only mode, sort read-back or Toeplitz. */
 
+#define B200_EXACT_GRID  4   /* keep the oversampled grid at next235even(sigma N) per axis.  Without it a 3-D plan
+                                whose grid has factors 3 / 5 takes the next power of two when that is at most a
+                                third larger on every axis (the fused FFT passes need powers of two; the kernel is
+                                only more accurate on a finer grid).  b200_toeplitz_apply needs exactly 2 N. */
+
 /* Version of this ABI (bumped on any signature change). */
 int b200_abi_version(void);
 
@@ -68,7 +73,7 @@ const char* b200_last_error(void);
  *   n_trans_max  largest number of transforms batched in one execute call
  *   eps          requested tolerance (kernel width w = ceil(log10(10/eps)) at sigma = 2)
  *   upsampfac    sigma; 0 -> 2.0
- *   flags        B200_SPREAD_ONLY: no FFT, no deapodisation, grid size = n_modes
+ *   flags        B200_SPREAD_ONLY: no FFT, no deapodisation, grid size = n_modes; B200_DOUBLE, B200_EXACT_GRID: above
  *   device       CUDA device ordinal
  */
 int b200_plan_create(b200_plan** plan, int dim, const int64_t* n_modes,

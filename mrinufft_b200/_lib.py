@@ -17,6 +17,7 @@ LIB_PATH = _HERE / "csrc" / "libb200nufft.so"
 
 B200_SPREAD_ONLY = 1
 B200_DOUBLE = 2
+B200_EXACT_GRID = 4
 
 # every symbol declared in include/b200nufft.h (tests check the export list against the header)
 _SIGNATURES = {
@@ -147,7 +148,7 @@ class Plan:
     """Thin RAII wrapper of ``b200_plan`` (one device, one trajectory, both transform types)."""
 
     def __init__(self, shape, n_trans_max=1, eps=1e-6, upsampfac=2.0, spread_only=False, device=0,
-                 double=False):
+                 double=False, exact_grid=False):
         self._lib = load()
         self._h = C.c_void_p(None)
         self.shape = tuple(int(s) for s in shape)
@@ -158,7 +159,8 @@ class Plan:
         check(
             self._lib.b200_plan_create(
                 C.byref(self._h), self.dim, n_modes, self.n_trans_max, float(eps), float(upsampfac),
-                (B200_SPREAD_ONLY if spread_only else 0) | (B200_DOUBLE if double else 0), self.device,
+                (B200_SPREAD_ONLY if spread_only else 0) | (B200_DOUBLE if double else 0)
+                | (B200_EXACT_GRID if exact_grid else 0), self.device,
             ),
             "b200_plan_create",
         )

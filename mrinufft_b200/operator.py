@@ -60,6 +60,7 @@ class RawB200Plan:
         self.shape = tuple(int(s) for s in shape)
         self.ndim = len(self.shape)
         self.eps = float(eps)
+        self.upsampfac = float(upsampfac)
         self.n_trans = int(n_trans)
         self.spread_only = bool(spread_only)
         self.isign_flip = False  # toggle_grad_traj: e^{-i} <-> e^{+i}
@@ -854,6 +855,24 @@ class MRIB200NUFFT(FourierOperatorBase):
         self._toeplitz_kernel = kern.to(torch.float32).contiguous()
         return self._toeplitz_kernel
 
+    def _toeplitz_plan(self):
+        """The plan whose grid is exactly ``2N`` (what ``b200_toeplitz_apply`` needs), or ``None``.  Usually the
+        operator's own; a 3-D operator that took a power-of-two grid (B200_EXACT_GRID in b200nufft.h) gets a
+        second, trajectory-less plan for the Gram operator on first use."""
+        want = tuple(2 * s for s in self.shape)
+        if self.ndim not in (2, 3) or self._double or self._spread_only:
+            return None
+        if tuple(self.raw_op.plan.nf) == want:
+            return self.raw_op.plan
+        if getattr(self, "_toep_plan", None) is None:
+            raw = self.raw_op
+            plan = _lib.Plan(self.shape, n_trans_max=raw.n_trans, eps=raw.eps, upsampfac=raw.upsampfac,
+                             device=self.device.index, exact_grid=True)
+            self._toep_plan = plan if tuple(plan.nf) == want else False
+            if self._toep_plan is False:
+                plan.close()
+        return self._toep_plan or None
+
     def _gram_device(self, img: torch.Tensor) -> torch.Tensor:
         """Toeplitz ``A^H A x`` on device tensors: img (B, 1|C, *XYZ) -> same shape."""
         B, C, XYZ = self.n_batchs, self.n_coils, self.shape
@@ -861,7 +880,7 @@ class MRIB200NUFFT(FourierOperatorBase):
             self.compute_toeplitz_kernel()
         kern = self._toeplitz_kernel
         scale = 1.0 / float(np.prod([2 * s for s in XYZ]))
-        plan = self.raw_op.plan
+        plan = self._toeplitz_plan()
         if self.uses_sense:
             img = img.reshape(B, *XYZ)
             out = torch.empty((B, 1, *XYZ), dtype=self._cdt, device=self.device)
@@ -884,8 +903,7 @@ class MRIB200NUFFT(FourierOperatorBase):
         self.check_shape(image=data)
         if not toeplitz:
             return self.adj_op(self.op(data))
-        if tuple(self.raw_op.plan.nf) != tuple(2 * s for s in self.shape) or self.ndim not in (2, 3) \
-                or self._double:
+        if self._toeplitz_plan() is None:
             # oversampled grid is not exactly 2N: reference construction on top of op / adj_op
             from mrinufft.operators.toeplitz import compute_toeplitz_kernel as _ref_kernel
 

@@ -1248,6 +1248,39 @@ def test_plan_less_fft_entry_point(mods, shape, dbl):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("shape", [(24, 24, 12), (24, 28, 12), (48, 24, 26)])
+def test_power_of_two_grid_for_3d_sizes_with_other_factors(mods, shape):
+    """A 3-D plan whose 2N has factors 3 / 5 / 7 takes the next power of two as its grid when that is at most a
+    third larger on every axis (csrc/api.cu; B200_EXACT_GRID keeps next235even): same accuracy bar against the
+    reference's exact NDFT, SENSE maps, both signs; the Toeplitz Gram operator keeps working through its own
+    exact-grid plan where 2N is an admissible grid size."""
+    mrinufft, _, torch = mods
+    rng = np.random.default_rng(3)
+    C, M = 3, 4000
+    samples = rng.uniform(-0.5, 0.5, (M, 3)).astype(np.float32)
+    smaps = (rng.standard_normal((C, *shape)) + 1j * rng.standard_normal((C, *shape))).astype(np.complex64)
+    smaps /= np.linalg.norm(smaps, axis=0)
+    op = mrinufft.get_operator("b200")(samples, shape, n_coils=C, smaps=smaps, squeeze_dims=False)
+    nf = tuple(op.raw_op.plan.nf)
+    assert all(n & (n - 1) == 0 for n in nf) and nf != tuple(2 * s for s in shape)
+    ref = mrinufft.get_operator("numpy")(samples.astype(np.float64), shape, n_coils=C, smaps=smaps.astype(np.complex128))
+    ref.squeeze_dims = False
+    img = (rng.standard_normal((1, 1, *shape)) + 1j * rng.standard_normal((1, 1, *shape))).astype(np.complex64)
+    ksp = (rng.standard_normal((1, C, M)) + 1j * rng.standard_normal((1, C, M))).astype(np.complex64)
+    assert rel_l2(op.op(img), ref.op(img.astype(np.complex128))) <= 5e-6
+    assert rel_l2(op.adj_op(ksp), ref.adj_op(ksp.astype(np.complex128))) <= 5e-6
+    assert rel_l2(op.data_consistency(img, ksp), ref.adj_op(ref.op(img.astype(np.complex128)) - ksp)) <= 5e-6
+    with op.grad_traj_plan():  # opposite sign: conj(A conj(x)) with conjugated maps
+        y_flip = op.op(img)
+    assert y_flip.shape == ksp.shape and np.isfinite(y_flip).all()
+    g = op.gram_op(img, toeplitz=True)
+    assert rel_l2(g, op.adj_op(op.op(img))) <= 2e-5
+    exact = tuple(2 * s for s in shape)
+    if shape == (24, 24, 12):
+        assert op._toeplitz_plan() is not None and tuple(op._toeplitz_plan().nf) == exact
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("Z,Y,C", [(1, 5, 2), (2, 16, 1), (12, 24, 3), (15, 17, 2), (22, 40, 2), (49, 16, 1),
                                     (64, 33, 4), (97, 8, 1), (176, 20, 2), (256, 32, 2), (512, 16, 1)])
 def test_stack_fftz_kernel_against_numpy(mods, Z, Y, C):
