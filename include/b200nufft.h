@@ -52,7 +52,9 @@ typedef struct b200_plan b200_plan;
                                 complex128 / float64 (sample coordinates and density included).
                                 Correctness-first kernels; no spread-only mode, sort read-back or Toeplitz. */
 
-#define B200_EXACT_GRID  4   /* keep the oversampled grid at next235even(sigma N) per axis.  Without it a 3-D plan
+#define B200_EXACT_GRID  4   /* keep the oversampled grid at next235even(sigma N) per axis.  Without it the fastest
+                                axis steps past sizes whose last 16-cell tile is narrower than w - 1 cells (the
+                                tiled kernels do not take those: 450 -> 480), and a 3-D single-precision plan
                                 whose grid has factors 3 / 5 takes the next power of two when that is at most a
                                 third larger on every axis (the fused FFT passes need powers of two; the kernel is
                                 only more accurate on a finer grid).  b200_toeplitz_apply needs exactly 2 N. */

@@ -274,6 +274,50 @@ def fft_c2c(ptr, T, shape, sign, double=False, stream=0):
     check(load().b200_fft_c2c(ptr, int(T), len(shape), n, int(sign), int(double), stream), "b200_fft_c2c")
 
 
+def _next235even(n: int) -> int:
+    n = max(int(n), 2)
+    n += n & 1
+    while True:
+        m = n
+        for f in (2, 3, 5):
+            while m % f == 0:
+                m //= f
+        if m == 1:
+            return n
+        n += 2
+
+
+def grid_size(shape, eps=1e-6, upsampfac=2.0, double=False, exact_grid=False):
+    """The oversampled grid `b200_plan_create` chooses (mirror of csrc/api.cu, checked against `Plan.nf` by the
+    GPU tests): `next235even(sigma N)` per axis; on the fastest axis the next size whose last 16-cell tile is whole
+    or at least w - 1 cells wide; in 3-D single precision the next power of two when that is at most a third
+    larger on every axis.  Used to size the workspace before a plan exists."""
+    sigma = float(upsampfac) if upsampfac else 2.0
+    if sigma == 2.0:
+        w = int(np.ceil(np.log10(10.0 / eps)))
+    else:
+        w = int(np.ceil(-np.log(eps) / (np.pi * np.sqrt(1.0 - 1.0 / max(sigma, 1.001)))))
+    w = min(max(w, 2), 16)
+    dim = len(shape)
+    nf = []
+    for a, n in enumerate(shape):
+        v = _next235even(max(int(np.ceil(sigma * int(n))), 2 * w))
+        if a == dim - 1 and dim >= 2 and not exact_grid:
+            while v % 16 != 0 and v % 16 < w - 1:
+                v = _next235even(v + 2)
+        nf.append(v)
+    if dim == 3 and not double and not exact_grid:
+        p2 = []
+        for v in nf:
+            q = 32
+            while q < v:
+                q <<= 1
+            p2.append(q)
+        if all(q <= 1.34 * v for q, v in zip(p2, nf)) and p2 != nf:
+            nf = p2
+    return tuple(nf)
+
+
 def header_symbols(header: Path | None = None):
     """Names of the functions declared in include/b200nufft.h (used by the CPU tests)."""
     import re

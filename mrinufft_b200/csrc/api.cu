@@ -252,6 +252,12 @@ int b200_plan_create(b200_plan** out, int dim, const int64_t* n_modes, int n_tra
         int target = (int)std::ceil(p->sigma * g.N[a]);
         if (target < 2 * w) target = 2 * w;
         g.nf[a] = next235even(target);
+        // fastest axis: the tiled spread / interp kernels want a last 16-cell tile that is either whole or at
+        // least w - 1 cells wide (a footprint may touch at most two tiles, spread_rows.cu `tiled_supported`);
+        // a grid like 450 = 28 x 16 + 2 would send every transform to the point-driven kernels (224^3 x 8 coils:
+        // 28 / 43 ms per op / adj_op against ~9 ms).  Take the next admissible size instead (450 -> 480).
+        if (a == dim - 1 && dim >= 2 && !(flags & B200_EXACT_GRID))
+          while (g.nf[a] % 16 != 0 && g.nf[a] % 16 < w - 1) g.nf[a] = next235even(g.nf[a] + 2);
       }
     } else {
       g.nf[a] = 1;

@@ -55,7 +55,7 @@ class RawB200Plan:
     ``finufft.py:23-80``, and ``RawCufinufftPlan``, ``cufinufft.py:51-137``)."""
 
     def __init__(self, samples, shape, n_trans=1, eps=1e-6, upsampfac=2.0, spread_only=False,
-                 device=None, double=False):
+                 device=None, double=False, exact_grid=False):
         self.device = torch.device("cuda", torch.cuda.current_device() if device is None else device)
         self.shape = tuple(int(s) for s in shape)
         self.ndim = len(self.shape)
@@ -66,7 +66,8 @@ class RawB200Plan:
         self.isign_flip = False  # toggle_grad_traj: e^{-i} <-> e^{+i}
         self.double = bool(double)
         self.plan = _lib.Plan(self.shape, n_trans_max=self.n_trans, eps=eps, upsampfac=upsampfac,
-                              spread_only=spread_only, device=self.device.index, double=self.double)
+                              spread_only=spread_only, device=self.device.index, double=self.double,
+                              exact_grid=exact_grid)
         self.n_samples = 0
         self._pts = None
         self.pts_version = 0  # bumped by every _set_pts (object ids are recycled, a counter is not)
@@ -165,6 +166,7 @@ class MRIB200NUFFT(FourierOperatorBase):
         spreadinterponly=0,
         isign=None,
         precision="single",
+        exact_grid=False,
         **kwargs,
     ):
         if not _lib.library_built():
@@ -208,6 +210,7 @@ class MRIB200NUFFT(FourierOperatorBase):
         self.eps = float(eps)
         self.upsampfac = float(upsampfac) if upsampfac else 2.0
         self._spread_only = bool(spreadinterponly)
+        self._exact_grid = bool(exact_grid)  # keep finufft's next235even(sigma N) grid (B200_EXACT_GRID)
         self._user_isign_flip = isign is not None and int(isign) > 0
         self._conj_smaps = False
         self._coil_chunk = coil_chunk
@@ -215,7 +218,7 @@ class MRIB200NUFFT(FourierOperatorBase):
 
         self.raw_op = RawB200Plan(
             samples, self.shape, n_trans=self._pick_chunk(), eps=self.eps, upsampfac=self.upsampfac,
-            spread_only=self._spread_only, device=dev_index, double=self._double,
+            spread_only=self._spread_only, device=dev_index, double=self._double, exact_grid=self._exact_grid,
         )
         if self._user_isign_flip:
             self.raw_op.toggle_grad_traj()
@@ -249,9 +252,8 @@ class MRIB200NUFFT(FourierOperatorBase):
             return self.n_trans
         if self._spread_only:
             return min(self.n_coils, 8)
-        sigma = self.upsampfac
-        grid_bytes = (16 if self._double else 8) * float(
-            np.prod([max(2 * 8, int(np.ceil(sigma * s))) for s in self.shape]))
+        grid_bytes = (16 if self._double else 8) * float(np.prod(
+            _lib.grid_size(self.shape, self.eps, self.upsampfac, self._double, self._exact_grid)))
         free, _ = torch.cuda.mem_get_info(self.device)
         # grids + cuFFT work area (same order) may take at most ~45% of the free memory
         cap = int(0.45 * free / (2.0 * grid_bytes))

@@ -125,13 +125,17 @@ def test_density_and_smaps_ride_along(mods):
 @pytest.mark.parametrize("shape", [(20, 36)])
 def test_grids_the_row_spreader_does_not_take_stay_point_driven(mods, shape):
     """Grids whose short last x-tile (72 = 4 * 16 + 8 cells) is narrower than the kernel (w = 13): a footprint
-    could touch three tiles."""
+    could touch three tiles.  A plan avoids such a grid (it takes 80 cells) unless finufft's exact grid is asked for."""
     mrinufft, _, _ = mods
     rng = np.random.default_rng(3)
     samples = rng.uniform(-0.5, 0.5, (500, 2))
-    op = mrinufft.get_operator("b200")(samples, shape, n_coils=2, squeeze_dims=False, eps=1e-12, precision="double")
-    assert op.raw_op.plan.rows_class(2)["class"] == 0
+    kw = dict(n_coils=2, squeeze_dims=False, eps=1e-12, precision="double")
+    auto = mrinufft.get_operator("b200")(samples, shape, **kw)
+    assert tuple(auto.raw_op.plan.nf) == (40, 80) and auto.raw_op.plan.rows_class(2)["class"] == 16
+    op = mrinufft.get_operator("b200")(samples, shape, exact_grid=True, **kw)
+    assert tuple(op.raw_op.plan.nf) == (40, 72) and op.raw_op.plan.rows_class(2)["class"] == 0
     ksp = _c(rng, 1, 2, 500)
     ref = mrinufft.get_operator("numpy")(samples, shape, n_coils=2)
     ref.squeeze_dims = False
     assert rel_l2(op.adj_op(ksp), ref.adj_op(ksp)) <= 1e-10
+    assert rel_l2(auto.adj_op(ksp), ref.adj_op(ksp)) <= 1e-10

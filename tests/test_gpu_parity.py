@@ -1248,6 +1248,20 @@ def test_plan_less_fft_entry_point(mods, shape, dbl):
 
 
 @pytest.mark.gpu
+def test_python_mirror_of_the_grid_choice(mods):
+    """`_lib.grid_size` (sizes the workspace before a plan exists) == the grid `b200_plan_create` chooses."""
+    _, _, torch = mods
+    from mrinufft_b200 import _lib
+
+    for shape in [(30,), (320, 320), (225, 225), (105, 111), (192, 192, 192), (160, 160, 160), (224, 224, 224),
+                  (96, 100, 36), (24, 28, 12), (20, 36), (17, 19, 23), (64, 64, 64), (225, 225, 40)]:
+        for eps, dbl, exact in [(1e-6, False, False), (1e-4, False, False), (1e-12, True, False), (1e-6, False, True)]:
+            plan = _lib.Plan(shape, 1, eps=eps, double=dbl, exact_grid=exact)
+            assert tuple(plan.nf) == _lib.grid_size(shape, eps, 2.0, dbl, exact), (shape, eps, dbl, exact)
+            plan.close()
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("shape", [(24, 24, 12), (24, 28, 12), (48, 24, 26)])
 def test_power_of_two_grid_for_3d_sizes_with_other_factors(mods, shape):
     """A 3-D plan whose 2N has factors 3 / 5 / 7 takes the next power of two as its grid when that is at most a

@@ -22,4 +22,4 @@ def run(shape, M, C):
     ksp = torch.randn((1, C, M), dtype=torch.complex64, device="cuda")
     ref = mrinufft.get_operator("b200")(traj[:2000], shape, n_coils=1, squeeze_dims=False)
     print(json.dumps({"shape": list(shape), "nf": list(op.raw_op.plan.nf), "coils": C, "op_ms": timed(lambda: op.op(img)), "adj_op_ms": timed(lambda: op.adj_op(ksp))}), flush=True)
-run((192,192,192), 1<<21, 8); run((160,160,160), 1<<21, 8); run((224,224,224), 1<<21, 8); run((320,320), 131072, 32); run((384,384), 200000, 8); run((192,192), 100000, 8)
+run((192,192,192), 1<<21, 8); run((225,225), 100000, 8); run((232,232,100), 1<<20, 4); run((160,160,160), 1<<21, 8); run((224,224,224), 1<<21, 8); run((320,320), 131072, 32); run((384,384), 200000, 8); run((192,192), 100000, 8)
